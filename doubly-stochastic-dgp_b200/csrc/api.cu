@@ -1,0 +1,709 @@
+// C-ABI of libdsdgp.so (include/dsdgp.h): context, parameter store, step orchestration (CUDA graphs), NCCL glue.
+// Replaces, for the hot path, what GPflow's Model/autoflow/Session machinery does around dgp.py:61-98.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+#include <map>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+#include "dsdgp_internal.cuh"
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return set_err(DSDGP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- NCCL, resolved at run time so the library loads (and the CPU-side symbol tests run) without it -------------
+typedef void* nccl_comm_t;
+typedef struct { char internal[128]; } nccl_uid_t;
+static struct {
+    void* h;
+    int (*GetUniqueId)(nccl_uid_t*);
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int);
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+    int (*CommDestroy)(nccl_comm_t);
+    const char* (*GetErrorString)(int);
+} g_nccl;
+static int nccl_load() {
+    if (g_nccl.h) return 0;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return set_err(DSDGP_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(nccl_uid_t*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_uid_t, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
+        return set_err(DSDGP_ERR_NCCL, "libnccl lacks required symbols");
+    g_nccl.h = h;
+    return 0;
+}
+#define NCCL_FLOAT 7
+#define NCCL_SUM 0
+
+// ---- context ------------------------------------------------------------------------------------------------------
+enum { MODE_PROPAGATE = 0, MODE_ELBO = 1, MODE_GRAD = 2, MODE_TRAIN = 3 };
+
+struct LayerOff { size_t Z, q_mu, q_sqrt, ls, var; int n_ls; };
+
+struct dsdgp_ctx {
+    dsdgp_desc desc;
+    int num_sms;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1, tm0, tm1;
+    bool ev_valid;
+    bool profile;
+    cudaEvent_t prof_ev[2 * (5 + 3 * DSDGP_MAX_LAYERS)];
+    bool prof_used[5 + 3 * DSDGP_MAX_LAYERS];
+    // flat parameter store
+    size_t n_params;                 // trainables + lik variance slot
+    float *params, *grads /* n_params + 2 */, *free_, *adam_m, *adam_v;
+    unsigned char* kinds;
+    std::vector<LayerOff> off;
+    size_t off_likvar;
+    float* meanW[DSDGP_MAX_LAYERS];
+    float* meanB[DSDGP_MAX_LAYERS];
+    // small-matrix workspaces
+    double* sm64;                    // all fp64 matrices
+    float* sm32;                     // Linv32, LinvT32, q_sqrtT
+    float* accf;                     // Pd, G, qmubar of every layer (zeroed per step)
+    size_t accf_n;
+    LayerSet ls;
+    // activations
+    float *Xd, *Yd;
+    float* U[DSDGP_MAX_LAYERS];
+    float* Fmean[DSDGP_MAX_LAYERS];
+    float* Fvar[DSDGP_MAX_LAYERS];
+    float* F[DSDGP_MAX_LAYERS];
+    float* zs[DSDGP_MAX_LAYERS];
+    float* xbar[DSDGP_MAX_LAYERS];
+    float *mubar, *vbar, *Wbuf;
+    // step scalars
+    StepArgs* sa_dev; StepArgs* sa_host;   // pinned ring of SA_RING slots (steps may be in flight)
+    cudaEvent_t sa_ev[16]; bool sa_used[16]; int sa_slot;
+    Accum* acc;
+    double* result_dev; double* result_host;   // [elbo, status]
+    // optimiser
+    bool adam_on, free_dirty;
+    double lr, beta1, beta2, eps; long long adam_t;
+    // comm
+    nccl_comm_t comm; int rank, world;
+    int n_global_opt, n_offset_opt;
+    // graphs
+    bool use_graph;
+    std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
+    std::map<std::tuple<int, int, int, unsigned>, long long> graph_launches;
+    long long nlaunch;
+    float last_ms;
+};
+
+const char* dsdgp_last_error(void) { return g_err; }
+const char* dsdgp_version(void) { return "dsdgp 0.1 (sm_100a)"; }
+
+static size_t field_count(const dsdgp_ctx* c, int layer, int field) {
+    if (field == DSDGP_F_LIK_VARIANCE) return 1;
+    const dsdgp_layer_desc& d = c->desc.layers[layer];
+    switch (field) {
+        case DSDGP_F_Z: return (size_t)d.M * d.D_in;
+        case DSDGP_F_Q_MU: return (size_t)d.M * d.D_out;
+        case DSDGP_F_Q_SQRT: return (size_t)d.D_out * d.M * d.M;
+        case DSDGP_F_LENGTHSCALES: return d.ard ? d.D_in : 1;
+        case DSDGP_F_VARIANCE: return 1;
+        case DSDGP_F_MEAN_W: return (size_t)d.D_in * d.D_out;
+        case DSDGP_F_MEAN_B: return d.D_out;
+    }
+    return 0;
+}
+static long long field_offset(const dsdgp_ctx* c, int layer, int field) {
+    if (field == DSDGP_F_LIK_VARIANCE) return (long long)c->off_likvar;
+    const LayerOff& o = c->off[layer];
+    switch (field) {
+        case DSDGP_F_Z: return o.Z;
+        case DSDGP_F_Q_MU: return o.q_mu;
+        case DSDGP_F_Q_SQRT: return o.q_sqrt;
+        case DSDGP_F_LENGTHSCALES: return o.ls;
+        case DSDGP_F_VARIANCE: return o.var;
+    }
+    return -1;
+}
+
+template <class T>
+static cudaError_t dmalloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+    return e;
+}
+
+int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
+    if (!out || !desc) return set_err(DSDGP_ERR_INVALID, "null argument");
+    if (desc->L < 1 || desc->L > DSDGP_MAX_LAYERS) return set_err(DSDGP_ERR_INVALID, "L=%d out of range", desc->L);
+    if (desc->N_max < 1 || desc->S_max < 1) return set_err(DSDGP_ERR_INVALID, "N_max/S_max must be >= 1");
+    for (int l = 0; l < desc->L; ++l) {
+        const dsdgp_layer_desc& d = desc->layers[l];
+        if (d.M < 1 || d.D_in < 1 || d.D_out < 1) return set_err(DSDGP_ERR_INVALID, "layer %d: bad sizes", l);
+        if (l > 0 && desc->layers[l - 1].D_out != d.D_in)
+            return set_err(DSDGP_ERR_INVALID, "layer %d: D_in=%d != previous D_out=%d", l, d.D_in, desc->layers[l - 1].D_out);
+        if (d.mean == DSDGP_MEAN_IDENTITY && d.D_in != d.D_out)
+            return set_err(DSDGP_ERR_INVALID, "layer %d: Identity mean needs D_in == D_out", l);
+        if (d.kernel != DSDGP_KERN_RBF && d.kernel != DSDGP_KERN_MATERN52)
+            return set_err(DSDGP_ERR_UNSUPPORTED, "layer %d: kernel %d", l, d.kernel);
+        if (fwd_smem_bytes(d.M, d.D_out, 16) > 220 * 1024 || bwd_smem_bytes(d.M, d.D_out, 16) > 220 * 1024)
+            return set_err(DSDGP_ERR_UNSUPPORTED, "layer %d: M=%d too large for the row-tile kernels", l, d.M);
+    }
+    const dsdgp_layer_desc& last = desc->layers[desc->L - 1];
+    if (desc->likelihood == DSDGP_LIK_GAUSSIAN) {
+        if (desc->D_y != last.D_out) return set_err(DSDGP_ERR_INVALID, "Gaussian likelihood: D_y=%d != last D_out=%d", desc->D_y, last.D_out);
+    } else if (desc->likelihood == DSDGP_LIK_MULTICLASS) {
+        if (desc->num_classes != last.D_out || desc->num_classes < 2 || desc->num_classes > 32)
+            return set_err(DSDGP_ERR_INVALID, "MultiClass: num_classes=%d must equal last D_out=%d (2..32)", desc->num_classes, last.D_out);
+    } else return set_err(DSDGP_ERR_UNSUPPORTED, "likelihood %d", desc->likelihood);
+
+    CK(cudaSetDevice(desc->device));
+    dsdgp_ctx* c = new (std::nothrow) dsdgp_ctx();
+    if (!c) return set_err(DSDGP_ERR_INVALID, "out of host memory");
+    c->desc = *desc;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, desc->device));
+    c->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    CK(cudaEventCreate(&c->tm0)); CK(cudaEventCreate(&c->tm1));
+    c->ev_valid = false; c->profile = false;
+    for (int i = 0; i < 5 + 3 * DSDGP_MAX_LAYERS; ++i) {
+        CK(cudaEventCreate(&c->prof_ev[2 * i])); CK(cudaEventCreate(&c->prof_ev[2 * i + 1]));
+        c->prof_used[i] = false;
+    }
+    CK(layer_kernels_init());
+    CK(small_matrix_init());
+
+    const int L = desc->L;
+    // ---- parameter layout
+    size_t n = 0;
+    c->off.resize(L);
+    for (int l = 0; l < L; ++l) {
+        const dsdgp_layer_desc& d = desc->layers[l];
+        LayerOff& o = c->off[l];
+        o.Z = n; n += (size_t)d.M * d.D_in;
+        o.q_mu = n; n += (size_t)d.M * d.D_out;
+        n = (n + 3) & ~(size_t)3;
+        o.q_sqrt = n; n += (size_t)d.D_out * d.M * d.M;
+        o.n_ls = d.ard ? d.D_in : 1;
+        o.ls = n; n += o.n_ls;
+        o.var = n; n += 1;
+        n = (n + 3) & ~(size_t)3;
+    }
+    c->off_likvar = n; n += 1;
+    c->n_params = n;
+    CK(dmalloc(&c->params, n)); CK(dmalloc(&c->grads, n + 2)); CK(dmalloc(&c->free_, n));
+    CK(dmalloc(&c->adam_m, n)); CK(dmalloc(&c->adam_v, n)); CK(dmalloc(&c->kinds, n));
+    {
+        std::vector<unsigned char> kinds(n, 4);
+        std::vector<float> init(n, 0.f);
+        for (int l = 0; l < L; ++l) {
+            const dsdgp_layer_desc& d = desc->layers[l];
+            const LayerOff& o = c->off[l];
+            for (size_t i = 0; i < (size_t)d.M * d.D_in; ++i) kinds[o.Z + i] = 0;
+            for (size_t i = 0; i < (size_t)d.M * d.D_out; ++i) kinds[o.q_mu + i] = 0;
+            for (int dd = 0; dd < d.D_out; ++dd)
+                for (int i = 0; i < d.M; ++i)
+                    for (int j = 0; j < d.M; ++j) {
+                        size_t k = o.q_sqrt + ((size_t)dd * d.M + i) * d.M + j;
+                        kinds[k] = (j <= i) ? 2 : 3;
+                        init[k] = (i == j) ? 1.f : 0.f;        // layers.py:149  q_sqrt = I
+                    }
+            for (int i = 0; i < o.n_ls; ++i) { kinds[o.ls + i] = 1; init[o.ls + i] = 1.f; }
+            kinds[o.var] = 1; init[o.var] = 1.f;
+        }
+        kinds[c->off_likvar] = desc->likelihood == DSDGP_LIK_GAUSSIAN ? 1 : 4;
+        init[c->off_likvar] = 1.f;
+        CK(cudaMemcpy(c->kinds, kinds.data(), n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->params, init.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    // ---- small-matrix workspaces
+    size_t n64 = 0, n32 = 0, nacc = 0;
+    for (int l = 0; l < L; ++l) {
+        const dsdgp_layer_desc& d = desc->layers[l];
+        size_t mm = (size_t)d.M * d.M;
+        n64 += 8 * mm + 8;
+        n32 += 2 * mm + (size_t)d.D_out * mm;
+        nacc += (size_t)d.D_out * mm + mm + (size_t)d.M * d.D_out;
+    }
+    CK(dmalloc(&c->sm64, n64)); CK(dmalloc(&c->sm32, n32)); CK(dmalloc(&c->accf, nacc));
+    c->accf_n = nacc;
+    // ---- activations
+    const size_t Rmax = (size_t)desc->N_max * desc->S_max;
+    size_t Dmax = 0, Mmax = 0;
+    for (int l = 0; l < L; ++l) { Dmax = max(Dmax, (size_t)desc->layers[l].D_out); Mmax = max(Mmax, (size_t)desc->layers[l].M); }
+    CK(dmalloc(&c->Xd, (size_t)desc->N_max * desc->layers[0].D_in));
+    CK(dmalloc(&c->Yd, (size_t)desc->N_max * desc->D_y));
+    CK(dmalloc(&c->mubar, Rmax * Dmax)); CK(dmalloc(&c->vbar, Rmax * Dmax)); CK(dmalloc(&c->Wbuf, Rmax * Mmax));
+    {
+        double* p64 = c->sm64; float* p32 = c->sm32; float* pa = c->accf;
+        c->ls.L = L;
+        for (int l = 0; l < L; ++l) {
+            const dsdgp_layer_desc& d = desc->layers[l];
+            const LayerOff& o = c->off[l];
+            size_t mm = (size_t)d.M * d.M;
+            size_t Rl = (l == 0) ? (size_t)desc->N_max : Rmax;
+            CK(dmalloc(&c->U[l], Rl * d.M));
+            CK(dmalloc(&c->Fmean[l], Rl * d.D_out)); CK(dmalloc(&c->Fvar[l], Rl * d.D_out));
+            CK(dmalloc(&c->F[l], Rmax * d.D_out)); CK(dmalloc(&c->zs[l], Rmax * d.D_out));
+            CK(dmalloc(&c->xbar[l], Rl * d.D_in));
+            CK(dmalloc(&c->meanW[l], (size_t)d.D_in * d.D_out)); CK(dmalloc(&c->meanB[l], (size_t)d.D_out));
+            LayerDev& P = c->ls.l[l];
+            P.M = d.M; P.Din = d.D_in; P.Dout = d.D_out; P.kern = d.kernel; P.ard = d.ard; P.white = d.white;
+            P.mean = d.mean; P.n_ls = o.n_ls; P.idx = l;
+            P.Z = c->params + o.Z; P.q_mu = c->params + o.q_mu; P.q_sqrt = c->params + o.q_sqrt;
+            P.ls = c->params + o.ls; P.var = c->params + o.var; P.meanW = c->meanW[l]; P.meanB = c->meanB[l];
+            P.gZ = c->grads + o.Z; P.gq_mu = c->grads + o.q_mu; P.gq_sqrt = c->grads + o.q_sqrt;
+            P.gls = c->grads + o.ls; P.gvar = c->grads + o.var;
+            P.K64 = p64; P.Lu64 = p64 + mm; P.Linv64 = p64 + 2 * mm; P.Kinv64 = p64 + 3 * mm; P.Ssum64 = p64 + 4 * mm;
+            P.T1 = p64 + 5 * mm; P.KbarKL = p64 + 6 * mm; P.Gsym = p64 + 7 * mm; P.scal = p64 + 8 * mm; p64 += 8 * mm + 8;
+            P.Linv32 = p32; P.LinvT32 = p32 + mm; P.q_sqrtT = p32 + 2 * mm; p32 += 2 * mm + (size_t)d.D_out * mm;
+            P.Pd = pa; P.G = pa + (size_t)d.D_out * mm; P.qmubar = P.G + mm; pa += (size_t)d.D_out * mm + mm + (size_t)d.M * d.D_out;
+        }
+    }
+    CK(dmalloc(&c->sa_dev, 1)); CK(cudaMallocHost((void**)&c->sa_host, 16 * sizeof(StepArgs)));
+    for (int i = 0; i < 16; ++i) { CK(cudaEventCreateWithFlags(&c->sa_ev[i], cudaEventDisableTiming)); c->sa_used[i] = false; }
+    c->sa_slot = 0;
+    CK(dmalloc(&c->acc, 1));
+    CK(dmalloc(&c->result_dev, 2)); CK(cudaMallocHost((void**)&c->result_host, 2 * sizeof(double)));
+    memset(c->sa_host, 0, 16 * sizeof(StepArgs));
+    c->adam_on = false; c->free_dirty = true; c->adam_t = 0;
+    c->lr = 0.01; c->beta1 = 0.9; c->beta2 = 0.999; c->eps = 1e-8;
+    c->comm = nullptr; c->rank = 0; c->world = 1; c->n_global_opt = -1; c->n_offset_opt = -1;
+    c->use_graph = true; c->nlaunch = 0; c->last_ms = 0.f;
+    *out = c;
+    return DSDGP_OK;
+}
+
+int dsdgp_destroy(dsdgp_ctx* c) {
+    if (!c) return DSDGP_OK;
+    cudaSetDevice(c->desc.device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    float* fl[] = {c->params, c->grads, c->free_, c->adam_m, c->adam_v, c->sm32, c->accf, c->Xd, c->Yd, c->mubar, c->vbar, c->Wbuf};
+    for (float* p : fl) cudaFree(p);
+    cudaFree(c->kinds); cudaFree(c->sm64); cudaFree(c->sa_dev); cudaFree(c->acc); cudaFree(c->result_dev);
+    for (int l = 0; l < c->desc.L; ++l) {
+        float* pl[] = {c->U[l], c->Fmean[l], c->Fvar[l], c->F[l], c->zs[l], c->xbar[l], c->meanW[l], c->meanB[l]};
+        for (float* p : pl) cudaFree(p);
+    }
+    cudaFreeHost(c->sa_host); cudaFreeHost(c->result_host);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
+    for (int i = 0; i < 2 * (5 + 3 * DSDGP_MAX_LAYERS); ++i) cudaEventDestroy(c->prof_ev[i]);
+    for (int i = 0; i < 16; ++i) cudaEventDestroy(c->sa_ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return DSDGP_OK;
+}
+
+static int check_field(dsdgp_ctx* c, int layer, int field, size_t n) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    if (field == DSDGP_F_LIK_VARIANCE) {
+        if (n != 1) return set_err(DSDGP_ERR_INVALID, "lik variance: n=%zu != 1", n);
+        return 0;
+    }
+    if (layer < 0 || layer >= c->desc.L) return set_err(DSDGP_ERR_INVALID, "layer %d out of range", layer);
+    if (field < 0 || field > DSDGP_F_MEAN_B) return set_err(DSDGP_ERR_INVALID, "field %d unknown", field);
+    size_t want = field_count(c, layer, field);
+    if (n != want) return set_err(DSDGP_ERR_INVALID, "layer %d field %d: n=%zu, expected %zu", layer, field, n, want);
+    return 0;
+}
+
+int dsdgp_set_param(dsdgp_ctx* c, int layer, int field, const double* host, size_t n) {
+    int rc = check_field(c, layer, field, n);
+    if (rc) return rc;
+    if (!host) return set_err(DSDGP_ERR_INVALID, "null host pointer");
+    CK(cudaSetDevice(c->desc.device));
+    std::vector<float> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = (float)host[i];
+    float* dst;
+    if (field == DSDGP_F_MEAN_W) dst = c->meanW[layer];
+    else if (field == DSDGP_F_MEAN_B) dst = c->meanB[layer];
+    else {
+        dst = c->params + field_offset(c, layer, field);
+        if (field == DSDGP_F_Q_SQRT) {      // LowerTriangular transform: the upper triangle does not exist (layers.py:150)
+            int M = c->desc.layers[layer].M;
+            for (size_t k = 0; k < n; ++k) { int i = (k / M) % M, j = k % M; if (j > i) tmp[k] = 0.f; }
+        }
+        if (field == DSDGP_F_LENGTHSCALES || field == DSDGP_F_VARIANCE || field == DSDGP_F_LIK_VARIANCE)
+            for (size_t k = 0; k < n; ++k)
+                if (!(tmp[k] > 0.f)) return set_err(DSDGP_ERR_INVALID, "positive parameter got %g", (double)tmp[k]);
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(dst, tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    c->free_dirty = true;
+    return DSDGP_OK;
+}
+
+static int get_flat(dsdgp_ctx* c, const float* base, int layer, int field, double* host, size_t n) {
+    int rc = check_field(c, layer, field, n);
+    if (rc) return rc;
+    if (!host) return set_err(DSDGP_ERR_INVALID, "null host pointer");
+    CK(cudaSetDevice(c->desc.device));
+    const float* src;
+    if (field == DSDGP_F_MEAN_W) src = c->meanW[layer];
+    else if (field == DSDGP_F_MEAN_B) src = c->meanB[layer];
+    else src = base + field_offset(c, layer, field);
+    std::vector<float> tmp(n);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(tmp.data(), src, n * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) host[i] = (double)tmp[i];
+    return DSDGP_OK;
+}
+int dsdgp_get_param(dsdgp_ctx* c, int layer, int field, double* host, size_t n) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    return get_flat(c, c->params, layer, field, host, n);
+}
+int dsdgp_get_grad(dsdgp_ctx* c, int layer, int field, double* host, size_t n) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    if (field == DSDGP_F_MEAN_W || field == DSDGP_F_MEAN_B) return set_err(DSDGP_ERR_INVALID, "mean function parameters are fixed");
+    return get_flat(c, c->grads, layer, field, host, n);
+}
+
+// ---- one step, enqueued on the ctx stream (captured into a CUDA graph on first use) --------------------------------
+#define PROF_BEGIN(i) do { if (prof) { cudaEventRecord(c->prof_ev[2 * (i)], st); c->prof_used[i] = true; } } while (0)
+#define PROF_END(i) do { if (prof) cudaEventRecord(c->prof_ev[2 * (i) + 1], st); } while (0)
+static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, long long* nl, bool prof) {
+    const int L = c->desc.L;
+    cudaStream_t st = c->stream;
+    if (prof) for (int i = 0; i < 5 + 3 * L; ++i) c->prof_used[i] = false;
+    const float jit = (float)c->desc.jitter;
+    const bool grad = mode >= MODE_GRAD;
+    CK(cudaMemsetAsync(c->acc, 0, sizeof(Accum), st));
+    if (grad) {
+        CK(cudaMemsetAsync(c->accf, 0, c->accf_n * sizeof(float), st));
+        CK(cudaMemsetAsync(c->grads, 0, (c->n_params + 2) * sizeof(float), st));
+    }
+    PROF_BEGIN(0);
+    launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, st, nl);
+    PROF_END(0);
+    // forward
+    for (int l = 0; l < L; ++l) {
+        FwdArgs a;
+        a.Xin = (l == 0) ? c->Xd : c->F[l - 1];
+        a.N = N; a.jitter = jit; a.sa = c->sa_dev;
+        a.R = (l == 0) ? N : N * S;
+        a.S_rep = (l == 0 && L > 1) ? S : 1;
+        a.U = c->U[l]; a.Fmean = c->Fmean[l]; a.Fvar = c->Fvar[l];
+        a.F = (l < L - 1 || mode == MODE_PROPAGATE) ? c->F[l] : nullptr;
+        if (l == 0 && L == 1 && mode == MODE_PROPAGATE) a.S_rep = S;     // single layer: still S draws for Fs
+        a.z = (zmask >> l) & 1u ? c->zs[l] : nullptr;
+        PROF_BEGIN(5 + 3 * l);
+        launch_fwd(c->ls.l[l], a, c->num_sms, st, nl);
+        PROF_END(5 + 3 * l);
+    }
+    if (mode == MODE_PROPAGATE) return DSDGP_OK;
+    // likelihood
+    const int Rlast = (L == 1) ? N : N * S;
+    PROF_BEGIN(1);
+    if (c->desc.likelihood == DSDGP_LIK_GAUSSIAN)
+        launch_lik_gaussian(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.D_y, c->params + c->off_likvar,
+                            c->mubar, c->vbar, c->acc, c->sa_dev, grad, st, nl);
+    else
+        launch_lik_multiclass(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.num_classes, c->mubar, c->vbar,
+                              c->acc, c->sa_dev, grad, st, nl);
+    PROF_END(1);
+    if (grad) {
+        for (int l = L - 1; l >= 0; --l) {
+            BwdArgs b;
+            b.Xin = (l == 0) ? c->Xd : c->F[l - 1];
+            b.N = N; b.jitter = jit; b.sa = c->sa_dev;
+            b.R = (l == 0) ? N : N * S;
+            b.S_rep = (l == 0 && L > 1) ? S : 1;
+            b.U = c->U[l]; b.Fvar = c->Fvar[l];
+            b.fbar = (l == L - 1) ? nullptr : c->xbar[l + 1];
+            b.z = (zmask >> l) & 1u ? c->zs[l] : nullptr;
+            b.mubar = c->mubar; b.vbar = c->vbar; b.W = c->Wbuf;
+            b.xbar = (l == 0) ? nullptr : c->xbar[l];
+            PROF_BEGIN(6 + 3 * l);
+            launch_bwd_rows(c->ls.l[l], b, c->num_sms, st, nl);
+            PROF_END(6 + 3 * l);
+            PROF_BEGIN(7 + 3 * l);
+            launch_bwd_rowred(c->ls.l[l], b, c->num_sms, st, nl);
+            PROF_END(7 + 3 * l);
+        }
+        PROF_BEGIN(2);
+        launch_fin(c->ls, c->acc, c->sa_dev, st, nl);
+        PROF_END(2);
+    }
+    launch_elbo_finish(c->acc, c->sa_dev, grad ? c->grads + c->off_likvar : nullptr, c->grads + c->n_params, st, nl);
+    if (c->comm) {
+        PROF_BEGIN(3);
+        int rc;
+        if (grad) rc = g_nccl.AllReduce(c->grads, c->grads, c->n_params + 2, NCCL_FLOAT, NCCL_SUM, c->comm, st);
+        else rc = g_nccl.AllReduce(c->grads + c->n_params, c->grads + c->n_params, 2, NCCL_FLOAT, NCCL_SUM, c->comm, st);
+        if (rc) return set_err(DSDGP_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        PROF_END(3);
+    }
+    launch_result(c->acc, c->grads + c->n_params, c->comm != nullptr, c->result_dev, st, nl);
+    if (mode == MODE_TRAIN) {
+        PROF_BEGIN(4);
+        launch_adam(c->params, c->free_, c->adam_m, c->adam_v, c->grads, c->kinds, nullptr, c->n_params, c->sa_dev, st, nl);
+        PROF_END(4);
+    }
+    CK(cudaGetLastError());
+    return DSDGP_OK;
+}
+
+static int stage_inputs(dsdgp_ctx* c, const float* X, const float* Y, int N, int S, const float* const* zs, unsigned flags,
+                        unsigned* zmask) {
+    const dsdgp_desc& d = c->desc;
+    if (N < 1 || N > d.N_max) return set_err(DSDGP_ERR_INVALID, "N=%d outside [1, N_max=%d]", N, d.N_max);
+    if (S < 1 || S > d.S_max) return set_err(DSDGP_ERR_INVALID, "S=%d outside [1, S_max=%d]", S, d.S_max);
+    if (!X) return set_err(DSDGP_ERR_INVALID, "X is null");
+    cudaMemcpyKind kind = (flags & DSDGP_FLAG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CK(cudaMemcpyAsync(c->Xd, X, (size_t)N * d.layers[0].D_in * sizeof(float), kind, c->stream));
+    if (Y) CK(cudaMemcpyAsync(c->Yd, Y, (size_t)N * d.D_y * sizeof(float), kind, c->stream));
+    *zmask = 0;
+    if (zs)
+        for (int l = 0; l < d.L; ++l)
+            if (zs[l]) {
+                CK(cudaMemcpyAsync(c->zs[l], zs[l], (size_t)S * N * d.layers[l].D_out * sizeof(float), kind, c->stream));
+                *zmask |= 1u << l;
+            }
+    return DSDGP_OK;
+}
+
+static int run_step(dsdgp_ctx* c, int mode, int N, int S, double num_data, unsigned zmask, uint64_t seed) {
+    const int L = c->desc.L;
+    // pinned StepArgs ring: a slot is reused only after the copy that read it has completed
+    const int slot = c->sa_slot;
+    c->sa_slot = (c->sa_slot + 1) % 16;
+    if (c->sa_used[slot]) CK(cudaEventSynchronize(c->sa_ev[slot]));
+    StepArgs& sa = c->sa_host[slot];
+    memset(&sa, 0, sizeof(sa));
+    sa.seed = seed;
+    const int S_eff = (L == 1) ? 1 : S;
+    sa.N_global = c->n_global_opt > 0 ? c->n_global_opt : N * c->world;
+    sa.n_offset = c->n_offset_opt >= 0 ? c->n_offset_opt : N * c->rank;
+    sa.lik_scale = num_data / ((double)sa.N_global * S_eff);
+    sa.kl_weight = 1.0 / c->world;
+    if (mode == MODE_TRAIN) {
+        c->adam_t += 1;
+        sa.lr_t = c->lr * sqrt(1.0 - pow(c->beta2, (double)c->adam_t)) / (1.0 - pow(c->beta1, (double)c->adam_t));
+        sa.beta1 = c->beta1; sa.beta2 = c->beta2; sa.eps = c->eps;
+    }
+    CK(cudaMemcpyAsync(c->sa_dev, &sa, sizeof(StepArgs), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->sa_ev[slot], c->stream));
+    c->sa_used[slot] = true;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (!c->use_graph || c->profile) {
+        long long nl = 0;
+        int rc = enqueue_step(c, mode, N, S, zmask, &nl, c->profile);
+        if (rc) return rc;
+        c->nlaunch += nl;
+    } else {
+        auto key = std::make_tuple(mode, N, S, zmask);
+        auto it = c->graphs.find(key);
+        if (it == c->graphs.end()) {
+            long long nl = 0;
+            cudaGraph_t g;
+            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_step(c, mode, N, S, zmask, &nl, false);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (rc) { if (e == cudaSuccess && g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) return set_err(DSDGP_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            cudaGraphExec_t ge;
+            CK(cudaGraphInstantiate(&ge, g, 0));
+            CK(cudaGraphDestroy(g));
+            c->graphs[key] = ge;
+            c->graph_launches[key] = nl;
+            it = c->graphs.find(key);
+        }
+        CK(cudaGraphLaunch(it->second, c->stream));
+        c->nlaunch += c->graph_launches[key];
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
+    return DSDGP_OK;
+}
+
+static int fetch_result(dsdgp_ctx* c, double* elbo) {
+    CK(cudaMemcpyAsync(c->result_host, c->result_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->result_host[1] != 0.0)
+        return set_err(DSDGP_ERR_NOT_PD, "Cholesky of Kuu + jitter*I failed in layer %d (not positive definite)", (int)c->result_host[1] - 1);
+    if (elbo) *elbo = c->result_host[0];
+    return DSDGP_OK;
+}
+
+int dsdgp_propagate(dsdgp_ctx* c, const float* X, int N, int S, const float* const* zs, uint64_t seed, float* const* Fs,
+                    float* const* Fmeans, float* const* Fvars, unsigned flags) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    CK(cudaSetDevice(c->desc.device));
+    unsigned zmask;
+    int rc = stage_inputs(c, X, nullptr, N, S, zs, flags, &zmask);
+    if (rc) return rc;
+    rc = run_step(c, MODE_PROPAGATE, N, S, 1.0, zmask, seed);
+    if (rc) return rc;
+    const int L = c->desc.L;
+    cudaMemcpyKind kind = (flags & DSDGP_FLAG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int l = 0; l < L; ++l) {
+        const size_t D = c->desc.layers[l].D_out, per = (size_t)N * D;
+        if (Fs && Fs[l]) CK(cudaMemcpyAsync(Fs[l], c->F[l], (size_t)S * per * sizeof(float), kind, c->stream));
+        const bool dedup = (l == 0);        // layer 1 holds N rows: the reference returns S identical copies (dgp.py:63)
+        for (int which = 0; which < 2; ++which) {
+            float* const* outp = which ? Fvars : Fmeans;
+            const float* src = which ? c->Fvar[l] : c->Fmean[l];
+            if (!outp || !outp[l]) continue;
+            if (dedup) for (int s = 0; s < S; ++s) CK(cudaMemcpyAsync(outp[l] + (size_t)s * per, src, per * sizeof(float), kind, c->stream));
+            else CK(cudaMemcpyAsync(outp[l], src, (size_t)S * per * sizeof(float), kind, c->stream));
+        }
+    }
+    // status check (Cholesky) -- accumulators are valid in propagate mode too
+    launch_result(c->acc, c->grads + c->n_params, 0, c->result_dev, c->stream, &c->nlaunch);
+    return fetch_result(c, nullptr);
+}
+
+static int elbo_common(dsdgp_ctx* c, int mode, const float* X, const float* Y, int N, int S, double num_data,
+                       const float* const* zs, uint64_t seed, unsigned flags, double* elbo) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    if (!Y) return set_err(DSDGP_ERR_INVALID, "Y is null");
+    if (!(num_data > 0)) return set_err(DSDGP_ERR_INVALID, "num_data must be > 0");
+    CK(cudaSetDevice(c->desc.device));
+    unsigned zmask;
+    int rc = stage_inputs(c, X, Y, N, S, zs, flags, &zmask);
+    if (rc) return rc;
+    if (mode == MODE_TRAIN) {
+        if (!c->adam_on) return set_err(DSDGP_ERR_INVALID, "call dsdgp_adam_init first");
+        if (c->free_dirty) {
+            launch_constrain_init(c->params, c->free_, c->kinds, c->n_params, c->stream, &c->nlaunch);
+            c->free_dirty = false;
+        }
+    }
+    rc = run_step(c, mode, N, S, num_data, zmask, seed);
+    if (rc) return rc;
+    if (mode == MODE_TRAIN && (flags & DSDGP_FLAG_NO_SYNC)) return DSDGP_OK;
+    return fetch_result(c, elbo);
+}
+
+int dsdgp_elbo(dsdgp_ctx* c, const float* X, const float* Y, int N, int S, double num_data, const float* const* zs,
+               uint64_t seed, unsigned flags, double* elbo) {
+    return elbo_common(c, MODE_ELBO, X, Y, N, S, num_data, zs, seed, flags, elbo);
+}
+int dsdgp_elbo_grad(dsdgp_ctx* c, const float* X, const float* Y, int N, int S, double num_data, const float* const* zs,
+                    uint64_t seed, unsigned flags, double* elbo) {
+    return elbo_common(c, MODE_GRAD, X, Y, N, S, num_data, zs, seed, flags, elbo);
+}
+int dsdgp_adam_init(dsdgp_ctx* c, double lr, double beta1, double beta2, double eps) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    if (!(lr > 0) || !(beta1 >= 0 && beta1 < 1) || !(beta2 >= 0 && beta2 < 1) || !(eps > 0))
+        return set_err(DSDGP_ERR_INVALID, "bad Adam hyper-parameters");
+    CK(cudaSetDevice(c->desc.device));
+    c->lr = lr; c->beta1 = beta1; c->beta2 = beta2; c->eps = eps; c->adam_t = 0;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemset(c->adam_m, 0, c->n_params * sizeof(float)));
+    CK(cudaMemset(c->adam_v, 0, c->n_params * sizeof(float)));
+    c->adam_on = true; c->free_dirty = true;
+    return DSDGP_OK;
+}
+int dsdgp_train_step(dsdgp_ctx* c, const float* X, const float* Y, int N, int S, double num_data,
+                     const float* const* zs, uint64_t seed, unsigned flags, double* elbo) {
+    return elbo_common(c, MODE_TRAIN, X, Y, N, S, num_data, zs, seed, flags, elbo);
+}
+int dsdgp_timer_start(dsdgp_ctx* c) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    CK(cudaSetDevice(c->desc.device));
+    CK(cudaEventRecord(c->tm0, c->stream));
+    return DSDGP_OK;
+}
+int dsdgp_timer_stop(dsdgp_ctx* c, float* ms) {
+    if (!c || !ms) return set_err(DSDGP_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->desc.device));
+    CK(cudaEventRecord(c->tm1, c->stream));
+    CK(cudaEventSynchronize(c->tm1));
+    CK(cudaEventElapsedTime(ms, c->tm0, c->tm1));
+    return DSDGP_OK;
+}
+int dsdgp_profile(dsdgp_ctx* c, float* ms, int n) {
+    if (!c || !ms) return set_err(DSDGP_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->desc.device));
+    CK(cudaStreamSynchronize(c->stream));
+    int total = 5 + 3 * c->desc.L;
+    for (int i = 0; i < total && i < n; ++i) {
+        ms[i] = 0.f;
+        if (c->prof_used[i]) CK(cudaEventElapsedTime(&ms[i], c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+    }
+    return total;
+}
+
+int dsdgp_comm_unique_id(void* id128) {
+    if (!id128) return set_err(DSDGP_ERR_INVALID, "null id");
+    int rc = nccl_load();
+    if (rc) return rc;
+    nccl_uid_t id;
+    int e = g_nccl.GetUniqueId(&id);
+    if (e) return set_err(DSDGP_ERR_NCCL, "ncclGetUniqueId: %d", e);
+    memcpy(id128, &id, 128);
+    return DSDGP_OK;
+}
+int dsdgp_comm_init(dsdgp_ctx* c, const void* id128, int rank, int world) {
+    if (!c || !id128) return set_err(DSDGP_ERR_INVALID, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return set_err(DSDGP_ERR_INVALID, "rank %d / world %d", rank, world);
+    int rc = nccl_load();
+    if (rc) return rc;
+    CK(cudaSetDevice(c->desc.device));
+    nccl_uid_t id;
+    memcpy(&id, id128, 128);
+    int e = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (e) return set_err(DSDGP_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+    c->rank = rank; c->world = world;
+    // establish connections now (NCCL allocates lazily, which is not allowed inside stream capture)
+    e = g_nccl.AllReduce(c->grads + c->n_params, c->grads + c->n_params, 2, NCCL_FLOAT, NCCL_SUM, c->comm, c->stream);
+    if (e) return set_err(DSDGP_ERR_NCCL, "warm-up ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear(); c->graph_launches.clear();
+    return DSDGP_OK;
+}
+
+int dsdgp_kl(dsdgp_ctx* c, double* kl) {
+    if (!c || !kl) return set_err(DSDGP_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->desc.device));
+    CK(cudaMemsetAsync(c->acc, 0, sizeof(Accum), c->stream));
+    launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, c->stream, &c->nlaunch);
+    launch_result(c->acc, c->grads + c->n_params, 0, c->result_dev, c->stream, &c->nlaunch);
+    int rc = fetch_result(c, nullptr);
+    if (rc) return rc;
+    for (int l = 0; l < c->desc.L; ++l)
+        CK(cudaMemcpy(&kl[l], c->ls.l[l].scal + 3, sizeof(double), cudaMemcpyDeviceToHost));
+    return DSDGP_OK;
+}
+
+int dsdgp_sync(dsdgp_ctx* c) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    CK(cudaSetDevice(c->desc.device));
+    CK(cudaStreamSynchronize(c->stream));
+    return DSDGP_OK;
+}
+long long dsdgp_launch_count(dsdgp_ctx* c) { return c ? c->nlaunch : 0; }
+int dsdgp_last_step_ms(dsdgp_ctx* c, float* ms) {
+    if (!c || !ms) return set_err(DSDGP_ERR_INVALID, "null argument");
+    if (!c->ev_valid) return set_err(DSDGP_ERR_INVALID, "no step has run");
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return DSDGP_OK;
+}
+int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
+    if (!c || !name) return set_err(DSDGP_ERR_INVALID, "null argument");
+    std::string n(name);
+    if (n == "graph") c->use_graph = value != 0;
+    else if (n == "profile") c->profile = value != 0;
+    else if (n == "n_global") c->n_global_opt = (int)value;
+    else if (n == "n_offset") c->n_offset_opt = (int)value;
+    else return set_err(DSDGP_ERR_INVALID, "unknown option '%s'", name);
+    return DSDGP_OK;
+}

@@ -1,0 +1,172 @@
+// Internal declarations shared by the kernels of libdsdgp.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/dsdgp.h"
+
+#define DSDGP_NT 256          // threads per CTA of the row-tile kernels
+#define DSDGP_KB 16           // k-step of the SIMT tile GEMM
+#define DSDGP_NCH 64          // column chunk of the SIMT tile GEMM
+
+// Per-layer view handed to kernels by value.
+struct LayerDev {
+    int M, Din, Dout, kern, ard, white, mean, n_ls, idx;
+    // parameters (fp32, device)
+    const float *Z, *q_mu, *q_sqrt, *ls, *var, *meanW, *meanB;
+    // gradient destinations (fp32, same layout as the parameters)
+    float *gZ, *gq_mu, *gq_sqrt, *gls, *gvar;
+    // per-step small-matrix results
+    double *K64, *Lu64, *Linv64, *Kinv64, *Ssum64, *T1, *KbarKL, *Gsym;   // M x M each
+    float *Linv32, *LinvT32, *q_sqrtT;                                    // M x M, M x M, D x M x M
+    double *scal;   // [0] sum log diag Lu  [1] sum log diag(q_sqrt)^2  [2] tr(Kinv Ssum)  [3] KL  [4] sum q_sqrt^2+q_mu^2 (white)
+    // row-reduced accumulators (zeroed every step)
+    float *Pd;      // D x M x M : sum_r vbar_rd u_r u_r^T
+    float *G;       // M x M     : sum_r w_r u_r^T
+    float *qmubar;  // M x D     : sum_r u_r mubar_r^T
+};
+
+struct LayerSet { LayerDev l[DSDGP_MAX_LAYERS]; int L; };
+
+// Scalars that change every step live in device memory so that a captured CUDA graph can be replayed.
+struct StepArgs {
+    unsigned long long seed;
+    double lik_scale;      // num_data / (N_global * S_eff)
+    double kl_weight;      // 1/world
+    int N_global, n_offset;
+    // Adam
+    double lr_t, beta1, beta2, eps;
+};
+
+struct Accum {             // fp64 scalar accumulators (zeroed every step)
+    double lik;            // sum of scaled variational expectations (this rank)
+    double kl;             // sum_l KL_l
+    double glikvar;        // d/d lik_var
+    double elbo;           // lik - kl_weight*kl   (after all-reduce: the ELBO)
+    int status;            // nonzero: Cholesky failed (layer index + 1)
+    int pad;
+};
+
+// ----------------------------------------------------------------------------------------------
+// Counter-based RNG: Philox4x32-10 keyed by seed; counter = (n_global, s, layer, dchunk) -> 4 normals.
+// z(s, n, d) is a pure function of (seed, layer, s, n_global, d): results do not depend on how rows
+// are sharded over CTAs or GPUs.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float dsdgp_normal(unsigned long long seed, int layer, int s, int n_global, int d) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)n_global, (uint32_t)s, (uint32_t)layer, (uint32_t)(d >> 2),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    // Box-Muller on the pair holding lane d&3
+    int p = (d & 2);
+    float u1 = ((float)r[p] + 0.5f) * 2.3283064365386963e-10f;       // (0,1)
+    float u2 = ((float)r[p + 1] + 0.5f) * 2.3283064365386963e-10f;
+    float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    return (d & 1) ? rad * sn : rad * cs;
+}
+
+// kernel value and d k / d r2   (r2 already scaled by lengthscales)
+__device__ __forceinline__ void kern_eval_f(int kern, float r2, float var, float& k, float& kp) {
+    if (kern == DSDGP_KERN_RBF) {
+        k = var * expf(-0.5f * r2);
+        kp = -0.5f * k;
+    } else {
+        float r = sqrtf(r2 + 1e-12f);
+        const float s5 = 2.2360679774997896f;
+        float e = expf(-s5 * r);
+        k = var * (1.0f + s5 * r + (5.0f / 3.0f) * r * r) * e;
+        kp = var * e * (-5.0f / 6.0f) * (1.0f + s5 * r);
+    }
+}
+__device__ __forceinline__ void kern_eval_d(int kern, double r2, double var, double& k, double& kp) {
+    if (kern == DSDGP_KERN_RBF) {
+        k = var * exp(-0.5 * r2);
+        kp = -0.5 * k;
+    } else {
+        double r = sqrt(r2 + 1e-12);
+        const double s5 = 2.2360679774997896;
+        double e = exp(-s5 * r);
+        k = var * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * e;
+        kp = var * e * (-5.0 / 6.0) * (1.0 + s5 * r);
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// launch interfaces (implemented in the .cu files)
+// ----------------------------------------------------------------------------------------------
+struct FwdArgs {
+    const float* Xin;     // (R, Din)
+    int R;                // rows of this layer on this rank
+    int N;                // minibatch rows on this rank (row r = s*N + n)
+    int S_rep;            // >1: layer evaluated on N rows, sample S_rep times (layer-1 dedup)
+    float* U;             // (R, M) out
+    float* Fmean;         // (R, Dout) out
+    float* Fvar;          // (R, Dout) out
+    float* F;             // (S_rep*R, Dout) out or NULL
+    const float* z;       // (S_rep*R, Dout) or NULL -> Philox
+    float jitter;
+    const StepArgs* sa;
+};
+
+struct BwdArgs {
+    const float* Xin;     // (R, Din)
+    int R, N, S_rep;
+    const float* U;       // (R, M)
+    const float* Fvar;    // (R, Dout)
+    const float* fbar;    // (S_rep*R, Dout) upstream dE/dF, or NULL when mubar/vbar are given
+    const float* z;       // as in forward
+    float* mubar;         // (R, Dout)  in (last layer) / out
+    float* vbar;          // (R, Dout)
+    float* W;             // (R, M) out
+    float* xbar;          // (R, Din) out or NULL (first layer)
+    float jitter;
+    const StepArgs* sa;
+};
+
+void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
+void launch_fwd(const LayerDev& P, const FwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
+void launch_bwd_rows(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
+void launch_bwd_rowred(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
+void launch_fin(const LayerSet& ls, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
+void launch_lik_gaussian(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy,
+                         const float* lik_var, float* mubar, float* vbar, Accum* acc, const StepArgs* sa,
+                         int want_grad, cudaStream_t st, long long* nlaunch);
+void launch_lik_multiclass(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int K,
+                           float* mubar, float* vbar, Accum* acc, const StepArgs* sa, int want_grad,
+                           cudaStream_t st, long long* nlaunch);
+void launch_elbo_finish(Accum* acc, const StepArgs* sa, float* glikvar, float* elbo_hi_lo, cudaStream_t st, long long* nlaunch);
+void launch_result(const Accum* acc, const float* elbo_hi_lo, int use_hi_lo, double* result, cudaStream_t st, long long* nlaunch);
+cudaError_t layer_kernels_init();
+cudaError_t small_matrix_init();
+void launch_adam(float* params, float* free_, float* m, float* v, const float* grads, const unsigned char* kinds,
+                 const int* tril_m, size_t n, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
+void launch_constrain_init(const float* params, float* free_, const unsigned char* kinds, size_t n, cudaStream_t st,
+                           long long* nlaunch);
+size_t fwd_smem_bytes(int M, int Din, int TR);
+size_t bwd_smem_bytes(int M, int Din, int TR);

@@ -1,0 +1,172 @@
+// Likelihood expectations (+ their adjoints) and the optimiser step.
+// Reference: utils.py:88-93 (BroadcastingLikelihood.variational_expectations -> gpflow Gaussian / MultiClass
+// RobustMax), dgp.py:88-98 (mean over S, sum, scale); Adam = tf.train.AdamOptimizer on GPflow's
+// unconstrained variables.
+#include "dsdgp_internal.cuh"
+
+__constant__ double c_gh_x[20] = {
+    -5.3874808900112328, -4.6036824495507442, -3.9447640401156252, -3.3478545673832163, -2.7888060584281305,
+    -2.2549740020892757, -1.7385377121165861, -1.2340762153953231, -0.73747372854539439, -0.24534070830090124,
+    0.24534070830090124, 0.73747372854539439, 1.2340762153953231, 1.7385377121165861, 2.2549740020892757,
+    2.7888060584281305, 3.3478545673832163, 3.9447640401156252, 4.6036824495507442, 5.3874808900112328};
+__constant__ double c_gh_w[20] = {
+    2.2293936455341447e-13, 4.3993409922731747e-10, 1.0860693707692782e-07, 7.8025564785320599e-06,
+    0.00022833863601635365, 0.0032437733422378567, 0.024810520887463643, 0.10901720602002329, 0.28667550536283415,
+    0.46224366960061009, 0.46224366960061009, 0.28667550536283415, 0.10901720602002329, 0.024810520887463643,
+    0.0032437733422378567, 0.00022833863601635365, 7.8025564785320599e-06, 1.0860693707692782e-07,
+    4.3993409922731747e-10, 2.2293936455341447e-13};
+
+// Gaussian: VE = -1/2 log 2pi - 1/2 log s2 - 1/2 ((y-mu)^2 + v)/s2 ; rows r = s*N + n share y_n (utils.py:72-73)
+__global__ void k_lik_gaussian(const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
+                               int R, int N, int Dy, const float* __restrict__ lik_var, float* __restrict__ mubar,
+                               float* __restrict__ vbar, Accum* acc, const StepArgs* sa, int want_grad) {
+    const double s2 = (double)lik_var[0], c = sa->lik_scale;
+    const double base = -0.5 * 1.8378770664093453 - 0.5 * log(s2);
+    double ve = 0.0, gl = 0.0;
+    size_t total = (size_t)R * Dy;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int r = idx / Dy, d = idx % Dy, n = r % N;
+        double y = Y[(size_t)n * Dy + d], mu = Fmean[idx], v = Fvar[idx];
+        double e2 = (y - mu) * (y - mu) + v;
+        ve += base - 0.5 * e2 / s2;
+        if (want_grad) {
+            mubar[idx] = (float)(c * (y - mu) / s2);
+            vbar[idx] = (float)(-0.5 * c / s2);
+            gl += -0.5 / s2 + 0.5 * e2 / (s2 * s2);
+        }
+    }
+    ve = warp_sum_d(ve); gl = warp_sum_d(gl);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&acc->lik, c * ve);
+        if (want_grad) atomicAdd(&acc->glikvar, c * gl);
+    }
+}
+
+void launch_lik_gaussian(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy, const float* lik_var,
+                         float* mubar, float* vbar, Accum* acc, const StepArgs* sa, int want_grad, cudaStream_t st,
+                         long long* nl) {
+    size_t total = (size_t)R * Dy;
+    int nb = (int)min((size_t)1024, (total + 255) / 256);
+    k_lik_gaussian<<<nb, 256, 0, st>>>(Fmean, Fvar, Y, R, N, Dy, lik_var, mubar, vbar, acc, sa, want_grad);
+    *nl += 1;
+}
+
+// MultiClass / RobustMax(eps = 1e-3): one thread per row; 20-point Gauss-Hermite over the labelled latent.
+#define MC_MAXK 32
+__global__ void k_lik_multiclass(const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
+                                 int R, int N, int K, float* __restrict__ mubar, float* __restrict__ vbar, Accum* acc,
+                                 const StepArgs* sa, int want_grad) {
+    const double c = sa->lik_scale, eps = 1e-3;
+    const double l1 = log(1.0 - eps), l0 = log(eps / (K - 1.0));
+    double ve = 0.0;
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) {
+        int n = r % N;
+        int y = (int)(Y[n] + 0.5f);
+        double mu[MC_MAXK], sd[MC_MAXK], gm[MC_MAXK], gv[MC_MAXK];
+        bool clipped[MC_MAXK];
+        for (int k = 0; k < K; ++k) {
+            double v = Fvar[(size_t)r * K + k];
+            clipped[k] = v < 1e-10;
+            if (clipped[k]) v = 1e-10;
+            mu[k] = Fmean[(size_t)r * K + k]; sd[k] = sqrt(v); gm[k] = 0.0; gv[k] = 0.0;
+        }
+        double p = 0.0;
+        const double s2y = sqrt(2.0) * sd[y];
+        for (int h = 0; h < 20; ++h) {
+            double x = mu[y] + s2y * c_gh_x[h];
+            double w = c_gh_w[h] * 0.56418958354775628;       // / sqrt(pi)
+            double prod = 1.0;
+            double cdf[MC_MAXK], pdf[MC_MAXK];
+            for (int k = 0; k < K; ++k) {
+                if (k == y) continue;
+                double t = (x - mu[k]) / sd[k];
+                cdf[k] = 0.5 * (1.0 + erf(t * 0.70710678118654752)) * (1.0 - 2e-4) + 1e-4;
+                pdf[k] = 0.3989422804014327 * exp(-0.5 * t * t) * (1.0 - 2e-4) / sd[k];      // d cdf / dx
+                prod *= cdf[k];
+            }
+            p += w * prod;
+            if (want_grad) {
+                double dPdx = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    if (k == y) continue;
+                    double others = prod / cdf[k];
+                    double dk = w * others * pdf[k];
+                    dPdx += dk;
+                    gm[k] -= dk;                                           // d/dmu_k = -d/dx
+                    if (!clipped[k]) gv[k] -= dk * (x - mu[k]) / (2.0 * sd[k] * sd[k]);
+                }
+                gm[y] += dPdx;
+                if (!clipped[y]) gv[y] += dPdx * c_gh_x[h] / (s2y);       // dx/dv_y = gh/(sqrt(2) sd_y)
+            }
+        }
+        ve = p * l1 + (1.0 - p) * l0;
+        if (want_grad) {
+            double f = c * (l1 - l0);
+            for (int k = 0; k < K; ++k) {
+                mubar[(size_t)r * K + k] = (float)(f * gm[k]);
+                vbar[(size_t)r * K + k] = (float)(f * gv[k]);
+            }
+        }
+    }
+    ve = warp_sum_d(ve);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&acc->lik, c * ve);
+}
+
+void launch_lik_multiclass(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int K, float* mubar,
+                           float* vbar, Accum* acc, const StepArgs* sa, int want_grad, cudaStream_t st, long long* nl) {
+    k_lik_multiclass<<<(R + 127) / 128, 128, 0, st>>>(Fmean, Fvar, Y, R, N, K, mubar, vbar, acc, sa, want_grad);
+    *nl += 1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Adam on the unconstrained variables.  kinds: 0 identity, 1 positive (softplus + 1e-6), 2 lower-tri entry
+// (trainable, identity transform), 3 structurally-zero upper-tri entry, 4 fixed.
+// tf.train.AdamOptimizer: lr_t = lr sqrt(1-b2^t)/(1-b1^t) (host, StepArgs) ; theta -= lr_t m / (sqrt(v) + eps).
+// ----------------------------------------------------------------------------------------------
+#define POS_LOWER 1e-6f
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
+
+__global__ void k_adam(float* __restrict__ params, float* __restrict__ free_, float* __restrict__ m, float* __restrict__ v,
+                       const float* __restrict__ grads, const unsigned char* __restrict__ kinds, size_t n,
+                       const StepArgs* sa) {
+    const float lr_t = (float)sa->lr_t, b1 = (float)sa->beta1, b2 = (float)sa->beta2, eps = (float)sa->eps;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned char k = kinds[i];
+        if (k >= 3) continue;
+        float f = free_[i];
+        float g = -grads[i];                       // objective = -ELBO
+        if (k == 1) g *= 1.f / (1.f + __expf(-f));  // d softplus
+        float mi = b1 * m[i] + (1.f - b1) * g;
+        float vi = b2 * v[i] + (1.f - b2) * g * g;
+        f -= lr_t * mi / (sqrtf(vi) + eps);
+        m[i] = mi; v[i] = vi; free_[i] = f;
+        params[i] = (k == 1) ? softplus_f(f) + POS_LOWER : f;
+    }
+}
+
+void launch_adam(float* params, float* free_, float* m, float* v, const float* grads, const unsigned char* kinds,
+                 const int*, size_t n, const StepArgs* sa, cudaStream_t st, long long* nl) {
+    int nb = (int)min((size_t)592, (n + 255) / 256);
+    k_adam<<<nb, 256, 0, st>>>(params, free_, m, v, grads, kinds, n, sa);
+    *nl += 1;
+}
+
+__global__ void k_constrain_init(const float* __restrict__ params, float* __restrict__ free_,
+                                 const unsigned char* __restrict__ kinds, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float p = params[i];
+        if (kinds[i] == 1) {
+            double y = (double)p - 1e-6;
+            if (y < 1e-12) y = 1e-12;
+            free_[i] = (float)(y + log(-expm1(-y)));      // softplus^-1
+        } else free_[i] = p;
+    }
+}
+
+void launch_constrain_init(const float* params, float* free_, const unsigned char* kinds, size_t n, cudaStream_t st,
+                           long long* nl) {
+    int nb = (int)min((size_t)592, (n + 255) / 256);
+    k_constrain_init<<<nb, 256, 0, st>>>(params, free_, kinds, n);
+    *nl += 1;
+}

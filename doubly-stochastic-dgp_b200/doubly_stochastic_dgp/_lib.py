@@ -1,0 +1,246 @@
+"""ctypes binding of libdsdgp.so (include/dsdgp.h).  This is the only place the Python host touches
+the device; it fails loudly if the library is missing -- there is no CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+MAX_LAYERS = 16
+F_Z, F_Q_MU, F_Q_SQRT, F_LENGTHSCALES, F_VARIANCE, F_MEAN_W, F_MEAN_B, F_LIK_VARIANCE = range(8)
+FLAG_DEVICE_PTRS, FLAG_NO_SYNC = 1, 2
+ERR_NOT_PD = -3
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [("M", C.c_int), ("D_in", C.c_int), ("D_out", C.c_int), ("kernel", C.c_int),
+                ("ard", C.c_int), ("white", C.c_int), ("mean", C.c_int)]
+
+
+class Desc(C.Structure):
+    _fields_ = [("L", C.c_int), ("layers", LayerDesc * MAX_LAYERS), ("likelihood", C.c_int),
+                ("num_classes", C.c_int), ("D_y", C.c_int), ("jitter", C.c_double), ("N_max", C.c_int),
+                ("S_max", C.c_int), ("device", C.c_int)]
+
+
+class DsdgpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dsdgp error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+FP = C.POINTER(C.c_float)
+DP = C.POINTER(C.c_double)
+FPP = C.POINTER(FP)
+
+SYMBOLS = ["dsdgp_last_error", "dsdgp_version", "dsdgp_create", "dsdgp_destroy", "dsdgp_set_param",
+           "dsdgp_get_param", "dsdgp_get_grad", "dsdgp_propagate", "dsdgp_elbo", "dsdgp_elbo_grad",
+           "dsdgp_adam_init", "dsdgp_train_step", "dsdgp_kl", "dsdgp_comm_unique_id", "dsdgp_comm_init", "dsdgp_sync",
+           "dsdgp_launch_count", "dsdgp_last_step_ms", "dsdgp_set_option", "dsdgp_timer_start",
+           "dsdgp_timer_stop", "dsdgp_profile"]
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libdsdgp.so")
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise DsdgpError(-100, f"{path} not found: build it with `python doubly-stochastic-dgp_b200/build.py` "
+                               "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.dsdgp_last_error.restype = C.c_char_p
+    lib.dsdgp_version.restype = C.c_char_p
+    lib.dsdgp_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Desc)]
+    lib.dsdgp_destroy.argtypes = [C.c_void_p]
+    for f in (lib.dsdgp_set_param, lib.dsdgp_get_param, lib.dsdgp_get_grad):
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, DP, C.c_size_t]
+    lib.dsdgp_propagate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+    for f in (lib.dsdgp_elbo, lib.dsdgp_elbo_grad):
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_uint64,
+                      C.c_uint, DP]
+    lib.dsdgp_adam_init.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.dsdgp_train_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                     C.c_uint64, C.c_uint, DP]
+    lib.dsdgp_timer_start.argtypes = [C.c_void_p]
+    lib.dsdgp_timer_stop.argtypes = [C.c_void_p, FP]
+    lib.dsdgp_profile.argtypes = [C.c_void_p, FP, C.c_int]
+    lib.dsdgp_kl.argtypes = [C.c_void_p, DP]
+    lib.dsdgp_comm_unique_id.argtypes = [C.c_void_p]
+    lib.dsdgp_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.dsdgp_sync.argtypes = [C.c_void_p]
+    lib.dsdgp_launch_count.argtypes = [C.c_void_p]
+    lib.dsdgp_launch_count.restype = C.c_longlong
+    lib.dsdgp_last_step_ms.argtypes = [C.c_void_p, FP]
+    lib.dsdgp_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DsdgpError(rc, load().dsdgp_last_error().decode())
+
+
+def _ptr(a):
+    """host ndarray (float32, C-contiguous) or an int device pointer -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _ptr_array(arrs, L):
+    if arrs is None:
+        return None, None
+    arr = (C.c_void_p * L)()
+    for i in range(L):
+        a = arrs[i] if i < len(arrs) else None
+        arr[i] = None if a is None else (a if isinstance(a, int) else a.ctypes.data)
+    return arr, arrs
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Context:
+    """Owns one dsdgp_ctx."""
+    def __init__(self, layer_descs, likelihood, num_classes, D_y, jitter, N_max, S_max, device=0):
+        lib = load()
+        d = Desc()
+        d.L = len(layer_descs)
+        for i, ld in enumerate(layer_descs):
+            d.layers[i] = LayerDesc(*ld)
+        d.likelihood, d.num_classes, d.D_y = likelihood, num_classes, D_y
+        d.jitter, d.N_max, d.S_max, d.device = jitter, N_max, S_max, device
+        self.desc = d
+        self.L = d.L
+        self.h = C.c_void_p()
+        check(lib.dsdgp_create(C.byref(self.h), C.byref(d)))
+        self.lib = lib
+        self.N_max, self.S_max = N_max, S_max
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.dsdgp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_param(self, layer, field, value):
+        v = np.ascontiguousarray(value, dtype=np.float64).reshape(-1)
+        check(self.lib.dsdgp_set_param(self.h, layer, field, v.ctypes.data_as(DP), v.size))
+
+    def _get(self, fn, layer, field, shape):
+        out = np.empty(int(np.prod(shape)) if len(shape) else 1, dtype=np.float64)
+        check(fn(self.h, layer, field, out.ctypes.data_as(DP), out.size))
+        return out.reshape(shape)
+
+    def get_param(self, layer, field, shape):
+        return self._get(self.lib.dsdgp_get_param, layer, field, shape)
+
+    def get_grad(self, layer, field, shape):
+        return self._get(self.lib.dsdgp_get_grad, layer, field, shape)
+
+    def propagate(self, X, S, zs=None, seed=0, want=(True, True, True), flags=0):
+        X = f32(X)
+        N = X.shape[0]
+        L = self.L
+        douts = [self.desc.layers[l].D_out for l in range(L)]
+        zs32 = None if zs is None else [None if z is None else f32(z) for z in zs]
+        zarr, _ = _ptr_array(zs32, L)
+        outs = []
+        arrs = []
+        for w in want:
+            if w:
+                o = [np.empty((S, N, douts[l]), dtype=np.float32) for l in range(L)]
+                a, _ = _ptr_array(o, L)
+            else:
+                o, a = None, None
+            outs.append(o); arrs.append(a)
+        check(self.lib.dsdgp_propagate(self.h, _ptr(X), N, S, zarr, seed, arrs[0], arrs[1], arrs[2], flags))
+        return outs
+
+    def _elbo(self, fn, X, Y, S, num_data, zs, seed, flags):
+        if isinstance(X, int):
+            raise TypeError("device-pointer calls need explicit N: use elbo_dev")
+        X, Y = f32(X), f32(Y)
+        zs32 = None if zs is None else [None if z is None else f32(z) for z in zs]
+        zarr, _ = _ptr_array(zs32, self.L)
+        e = C.c_double()
+        check(fn(self.h, _ptr(X), _ptr(Y), X.shape[0], S, float(num_data), zarr, seed, flags, C.byref(e)))
+        return e.value
+
+    def elbo(self, X, Y, S, num_data, zs=None, seed=0):
+        return self._elbo(self.lib.dsdgp_elbo, X, Y, S, num_data, zs, seed, 0)
+
+    def elbo_grad(self, X, Y, S, num_data, zs=None, seed=0):
+        return self._elbo(self.lib.dsdgp_elbo_grad, X, Y, S, num_data, zs, seed, 0)
+
+    def adam_init(self, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+        check(self.lib.dsdgp_adam_init(self.h, lr, beta1, beta2, eps))
+
+    def train_step(self, X, Y, N, S, num_data, seed, flags=0, want_elbo=True, zs=None):
+        """X, Y: float32 host arrays (pinned for the e2e path) or int device pointers (with FLAG_DEVICE_PTRS)."""
+        e = C.c_double()
+        zs32 = None if zs is None else [None if z is None else (z if isinstance(z, int) else f32(z)) for z in zs]
+        zarr, _ = _ptr_array(zs32, self.L)
+        check(self.lib.dsdgp_train_step(self.h, _ptr(X), _ptr(Y), N, S, float(num_data), zarr, seed, flags,
+                                        C.byref(e) if want_elbo else None))
+        return e.value if want_elbo else None
+
+    def timer_start(self):
+        check(self.lib.dsdgp_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self.lib.dsdgp_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile(self):
+        n = 5 + 3 * self.L
+        buf = (C.c_float * n)()
+        got = self.lib.dsdgp_profile(self.h, buf, n)
+        if got < 0:
+            check(got)
+        return list(buf)
+
+    def kl(self):
+        out = np.empty(self.L, dtype=np.float64)
+        check(self.lib.dsdgp_kl(self.h, out.ctypes.data_as(DP)))
+        return out
+
+    def comm_init(self, id_bytes, rank, world):
+        buf = C.create_string_buffer(bytes(id_bytes), 128)
+        check(self.lib.dsdgp_comm_init(self.h, buf, rank, world))
+
+    def sync(self):
+        check(self.lib.dsdgp_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.dsdgp_launch_count(self.h))
+
+    def last_step_ms(self):
+        ms = C.c_float()
+        check(self.lib.dsdgp_last_step_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def set_option(self, name, value):
+        check(self.lib.dsdgp_set_option(self.h, name.encode(), float(value)))
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    check(load().dsdgp_comm_unique_id(buf))
+    return buf.raw

@@ -1,0 +1,282 @@
+"""Host mirror of doubly_stochastic_dgp/dgp.py: `DGP_Base` / `DGP` with the reference's constructor signatures
+(dgp.py:42-45,184-187) and methods (propagate dgp.py:61-76, compute_log_likelihood = _build_likelihood
+dgp.py:92-98, predict_* dgp.py:100-126).  Everything numeric runs on the device through _lib.Context; this
+module only owns parameters, minibatching and shapes.  The training step the reference gets from
+`AdamOptimizer().minimize(model)` (demos/run_regression.py:83) is `model.adam_init(lr)` + `model.train_step()`.
+"""
+import numpy as np
+
+from . import _lib, settings
+from .layer_initializations import init_layers_linear
+from .likelihoods import Gaussian, MultiClass
+from .mean_functions import Linear, Zero
+from .params import Parameter, Parameterized
+from .utils import BroadcastingLikelihood
+
+
+class _Minibatch:
+    """gpflow.params.Minibatch(X, batch_size, seed) stand-in: repeat -> shuffle(buffer=N, seed) -> batch
+    (SURVEY App. C.5).  X and Y built with the same seed stay aligned (dgp.py:51-52)."""
+    def __init__(self, data, batch_size, seed=0):
+        self.data = np.asarray(data)
+        self.batch_size = int(batch_size)
+        self.rng = np.random.RandomState(seed)
+        self.perm = self.rng.permutation(len(self.data))
+        self.pos = 0
+
+    def next(self):
+        n = len(self.data)
+        idx = []
+        while len(idx) < self.batch_size:
+            if self.pos >= n:
+                self.perm = self.rng.permutation(n)
+                self.pos = 0
+            take = min(self.batch_size - len(idx), n - self.pos)
+            idx.extend(self.perm[self.pos:self.pos + take])
+            self.pos += take
+        return self.data[np.asarray(idx)]
+
+
+class DGP_Base(Parameterized):
+    """dgp.py:35-126."""
+    def __init__(self, X, Y, likelihood, layers, minibatch_size=None, num_samples=1, num_data=None,
+                 device=0, **kwargs):
+        X = np.asarray(X, dtype=np.float64)
+        Y = np.asarray(Y, dtype=np.float64)
+        self.num_samples = num_samples
+        self.num_data = num_data or X.shape[0]
+        self.minibatch_size = minibatch_size
+        if minibatch_size:
+            self._Xmb = _Minibatch(X, minibatch_size, seed=0)      # dgp.py:51-52
+            self._Ymb = _Minibatch(Y, minibatch_size, seed=0)
+        self.X, self.Y = X, Y
+        self.likelihood = BroadcastingLikelihood(likelihood)        # dgp.py:57
+        self.layers = list(layers)                                   # dgp.py:59
+        self._device = device
+        self._ctx = None
+        self._host_dirty = True
+        self._device_newer = False
+        self._seed = 0x5D6A1
+        self._adam = None
+        self._comm = None
+        for p in self.parameters():
+            p._owner = self
+        for l in self.layers:
+            object.__setattr__(l, "_model", self)
+
+    # ------------------------------------------------------------------ parameter plumbing
+    def parameters(self):
+        out = []
+        for l in self.layers:
+            out += [l.feature.Z, l.q_mu, l.q_sqrt, l.kern.lengthscales, l.kern.variance]
+            if isinstance(l.mean_function, Linear):
+                out += [l.mean_function.A, l.mean_function.b]
+        lik = self.likelihood.likelihood
+        if isinstance(lik, Gaussian):
+            out.append(lik.variance)
+        return out
+
+    def _mark_host_dirty(self):
+        self._host_dirty = True
+
+    def _refresh_from_device(self):
+        if not self._device_newer or self._ctx is None:
+            return
+        self._device_newer = False
+        c = self._ctx
+        for i, l in enumerate(self.layers):
+            l.feature.Z._value = c.get_param(i, _lib.F_Z, l.feature.Z.shape)
+            l.q_mu._value = c.get_param(i, _lib.F_Q_MU, l.q_mu.shape)
+            l.q_sqrt._value = c.get_param(i, _lib.F_Q_SQRT, l.q_sqrt.shape)
+            l.kern.lengthscales._value = c.get_param(i, _lib.F_LENGTHSCALES, l.kern.lengthscales.shape)
+            l.kern.variance._value = c.get_param(i, _lib.F_VARIANCE, ())
+        lik = self.likelihood.likelihood
+        if isinstance(lik, Gaussian):
+            lik.variance._value = c.get_param(-1, _lib.F_LIK_VARIANCE, ())
+
+    def _layer_descs(self):
+        descs = []
+        for l in self.layers:
+            Z = l.feature.Z._value
+            descs.append((Z.shape[0], Z.shape[1], l.num_outputs, l.kern.code, int(l.kern.ARD), int(bool(l.white)),
+                          l.mean_function.code))
+            if l.kern.input_dim != Z.shape[1]:
+                raise ValueError(f"kernel input_dim {l.kern.input_dim} != Z columns {Z.shape[1]}")
+        return descs
+
+    def _ensure_ctx(self, N, S):
+        if self._ctx is not None and (N > self._ctx.N_max or S > self._ctx.S_max):
+            if self._adam is not None:
+                raise RuntimeError(f"call needs N={N}, S={S} beyond the device workspaces "
+                                   f"(N_max={self._ctx.N_max}, S_max={self._ctx.S_max}) after training started; "
+                                   "predict in chunks or construct the model with larger minibatch/num_samples")
+            self._refresh_from_device()
+            N, S = max(N, self._ctx.N_max), max(S, self._ctx.S_max)
+            self._ctx.close()
+            self._ctx = None
+        if self._ctx is None:
+            lik = self.likelihood.likelihood
+            K = lik.num_classes if isinstance(lik, MultiClass) else 0
+            D_y = 1 if K else self.layers[-1].num_outputs
+            N_max = max(N, self.minibatch_size or min(self.X.shape[0], 4096), 128)
+            S_max = max(S, self.num_samples, 8)
+            self._ctx = _lib.Context(self._layer_descs(), lik.code, K, D_y, float(settings.jitter), N_max, S_max,
+                                     device=self._device)
+            if self._comm is not None:
+                self._ctx.comm_init(*self._comm)
+            self._host_dirty = True
+        if self._host_dirty:
+            c = self._ctx
+            for i, l in enumerate(self.layers):
+                c.set_param(i, _lib.F_Z, l.feature.Z._value)
+                c.set_param(i, _lib.F_Q_MU, l.q_mu._value)
+                c.set_param(i, _lib.F_Q_SQRT, l.q_sqrt._value)
+                c.set_param(i, _lib.F_LENGTHSCALES, l.kern.lengthscales._value)
+                c.set_param(i, _lib.F_VARIANCE, l.kern.variance._value)
+                if isinstance(l.mean_function, Linear):
+                    c.set_param(i, _lib.F_MEAN_W, l.mean_function.A._value)
+                    c.set_param(i, _lib.F_MEAN_B, l.mean_function.b._value)
+            lik = self.likelihood.likelihood
+            if isinstance(lik, Gaussian):
+                c.set_param(-1, _lib.F_LIK_VARIANCE, lik.variance._value)
+            self._host_dirty = False
+        return self._ctx
+
+    def _next_seed(self):
+        self._seed = (self._seed * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+        return self._seed
+
+    def _minibatch(self):
+        if self.minibatch_size:
+            return self._Xmb.next(), self._Ymb.next()
+        return self.X, self.Y
+
+    # ------------------------------------------------------------------ reference API
+    def propagate(self, X, full_cov=False, S=1, zs=None):
+        """dgp.py:61-76 -> (Fs, Fmeans, Fvars), lists of (S,N,D_l) float64 arrays."""
+        if full_cov:
+            raise NotImplementedError("full_cov=True is not on the accelerated path yet (SURVEY.md 8(f) rank 3)")
+        X = np.asarray(X, dtype=np.float64)
+        ctx = self._ensure_ctx(X.shape[0], S)
+        Fs, Fmeans, Fvars = ctx.propagate(X, S, zs=zs, seed=self._next_seed())
+        f64 = lambda lst: [a.astype(np.float64) for a in lst]
+        return f64(Fs), f64(Fmeans), f64(Fvars)
+
+    def _build_predict(self, X, full_cov=False, S=1, zs=None):
+        """dgp.py:78-81."""
+        Fs, Fmeans, Fvars = self.propagate(X, full_cov=full_cov, S=S, zs=zs)
+        return Fmeans[-1], Fvars[-1]
+
+    def compute_log_likelihood(self, zs=None, X=None, Y=None):
+        """gpflow Model.compute_log_likelihood -> _build_likelihood (dgp.py:92-98): the ELBO on the (next)
+        minibatch.  `zs` (list of (S,N,D_l) arrays) fixes the draws, like propagate(zs=...)."""
+        if X is None:
+            X, Y = self._minibatch()
+        ctx = self._ensure_ctx(X.shape[0], self.num_samples)
+        return ctx.elbo(X, Y, self.num_samples, self.num_data, zs=zs, seed=self._next_seed())
+
+    def compute_log_likelihood_and_grad(self, zs=None, X=None, Y=None):
+        """ELBO and dELBO/dparam for every trainable (what tf.gradients gives the reference's optimisers)."""
+        if X is None:
+            X, Y = self._minibatch()
+        ctx = self._ensure_ctx(X.shape[0], self.num_samples)
+        e = ctx.elbo_grad(X, Y, self.num_samples, self.num_data, zs=zs, seed=self._next_seed())
+        grads = []
+        for i, l in enumerate(self.layers):
+            grads.append(dict(Z=ctx.get_grad(i, _lib.F_Z, l.feature.Z.shape),
+                              q_mu=ctx.get_grad(i, _lib.F_Q_MU, l.q_mu.shape),
+                              q_sqrt=ctx.get_grad(i, _lib.F_Q_SQRT, l.q_sqrt.shape),
+                              lengthscales=ctx.get_grad(i, _lib.F_LENGTHSCALES, l.kern.lengthscales.shape),
+                              variance=ctx.get_grad(i, _lib.F_VARIANCE, ())))
+        lik_grad = None
+        if isinstance(self.likelihood.likelihood, Gaussian):
+            lik_grad = ctx.get_grad(-1, _lib.F_LIK_VARIANCE, ())
+        return e, grads, lik_grad
+
+    def predict_f(self, Xnew, num_samples):
+        return self._build_predict(Xnew, full_cov=False, S=num_samples)
+
+    def predict_f_full_cov(self, Xnew, num_samples):
+        return self._build_predict(Xnew, full_cov=True, S=num_samples)
+
+    def predict_all_layers(self, Xnew, num_samples):
+        return self.propagate(Xnew, full_cov=False, S=num_samples)
+
+    def predict_all_layers_full_cov(self, Xnew, num_samples):
+        return self.propagate(Xnew, full_cov=True, S=num_samples)
+
+    def predict_y(self, Xnew, num_samples):
+        Fmean, Fvar = self._build_predict(Xnew, full_cov=False, S=num_samples)
+        return self.likelihood.predict_mean_and_var(Fmean, Fvar)
+
+    def predict_density(self, Xnew, Ynew, num_samples):
+        Fmean, Fvar = self._build_predict(Xnew, full_cov=False, S=num_samples)
+        l = self.likelihood.predict_density(Fmean, Fvar, np.asarray(Ynew, dtype=np.float64))
+        a = l - np.log(num_samples)
+        mx = a.max(0)
+        return mx + np.log(np.exp(a - mx).sum(0))          # tf.reduce_logsumexp(axis=0), dgp.py:124-126
+
+    # ------------------------------------------------------------------ training (AdamOptimizer.minimize)
+    def adam_init(self, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+        N = self.minibatch_size or self.X.shape[0]
+        ctx = self._ensure_ctx(N, self.num_samples)
+        ctx.adam_init(lr, beta1, beta2, eps)
+        self._adam = (lr, beta1, beta2, eps)
+
+    def train_step(self, X=None, Y=None, zs=None):
+        """one session.run(minimize_op): minibatch draw + ELBO fwd + bwd + Adam update; returns the ELBO."""
+        if self._adam is None:
+            self.adam_init()
+        if X is None:
+            X, Y = self._minibatch()
+        ctx = self._ensure_ctx(X.shape[0], self.num_samples)
+        e = ctx.train_step(_lib.f32(X), _lib.f32(Y), X.shape[0], self.num_samples, self.num_data, self._next_seed(),
+                           zs=zs)
+        self._device_newer = True
+        return e
+
+    def minimize(self, maxiter=1000, lr=0.01):
+        if self._adam is None:
+            self.adam_init(lr)
+        e = None
+        for _ in range(maxiter):
+            e = self.train_step()
+        return e
+
+    # ------------------------------------------------------------------ multi-GPU
+    def comm_init(self, id_bytes, rank, world):
+        """Attach an NCCL communicator: X,Y given to this rank are its shard of the minibatch; ELBO and gradient
+        are all-reduced inside the step (csrc/api.cu)."""
+        self._comm = (id_bytes, rank, world)
+        if self._ctx is not None:
+            self._ctx.comm_init(id_bytes, rank, world)
+
+    # ------------------------------------------------------------------ per-layer services for layers.py
+    def _layer_conditional(self, layer, X):
+        raise NotImplementedError("layer.conditional_ND on a layer inside a model: use model.propagate")
+
+    def _layer_KL(self, layer):
+        ctx = self._ensure_ctx(1, 1)
+        return ctx.kl()[self.layers.index(layer)]
+
+
+class DGP(DGP_Base):
+    """dgp.py:169-192."""
+    def __init__(self, X, Y, Z, kernels, likelihood, num_outputs=None, mean_function=None, white=False, **kwargs):
+        mean_function = Zero() if mean_function is None else mean_function
+        layers = init_layers_linear(X, Y, Z, kernels, num_outputs=num_outputs, mean_function=mean_function,
+                                    white=white)
+        DGP_Base.__init__(self, X, Y, likelihood, layers, **kwargs)
+
+
+class _SingleLayer(DGP_Base):
+    """Private one-layer model so that a stand-alone SVGP_Layer can evaluate conditional_ND / KL on the device."""
+    def _layer_conditional(self, layer, X):
+        Fs, Fmeans, Fvars = self.propagate(X, S=1)
+        return Fmeans[0][0], Fvars[0][0]
+
+
+def _single_layer_model(layer):
+    D = layer.num_outputs
+    Din = layer.feature.Z.shape[1]
+    return _SingleLayer(np.zeros((1, Din)), np.zeros((1, D)), Gaussian(), [layer])

@@ -1,0 +1,90 @@
+"""Host mirror of doubly_stochastic_dgp/layers.py: `SVGP_Layer` with the reference constructor
+(layers.py:122-165) and attribute names (q_mu, q_sqrt, feature.Z, kern, mean_function, num_outputs, white,
+num_inducing).  The layer is a parameter container; conditional_ND / conditional_SND /
+sample_from_conditional / KL (layers.py:46-119,178-246) are evaluated by the owning model's device context
+(a layer used stand-alone builds a private one-layer context)."""
+import numpy as np
+
+from . import settings
+from .params import Parameter, Parameterized
+
+
+class InducingPoints(Parameterized):
+    """gpflow.features.InducingPoints stand-in: holds Z (layers.py:153)."""
+    def __init__(self, Z):
+        self.Z = Parameter(np.asarray(Z, dtype=np.float64))
+
+    def __len__(self):
+        return self.Z.shape[0]
+
+
+class Layer(Parameterized):
+    def __init__(self, input_prop_dim=None, **kwargs):
+        if input_prop_dim:
+            raise NotImplementedError("input_prop_dim is not on the accelerated path yet (SURVEY.md 8(f) rank 4)")
+        self.input_prop_dim = input_prop_dim
+
+
+class SVGP_Layer(Layer):
+    def __init__(self, kern, Z, num_outputs, mean_function, white=False, input_prop_dim=None, **kwargs):
+        Layer.__init__(self, input_prop_dim, **kwargs)
+        Z = np.asarray(Z, dtype=np.float64)
+        self.num_inducing = Z.shape[0]
+        self.q_mu = Parameter(np.zeros((self.num_inducing, num_outputs)))                     # layers.py:146-147
+        self.q_sqrt = Parameter(np.tile(np.eye(self.num_inducing)[None], [num_outputs, 1, 1]))  # layers.py:149-151
+        self.feature = InducingPoints(Z)
+        self.kern = kern
+        self.mean_function = mean_function
+        self.num_outputs = num_outputs
+        self.white = white
+        self._model = None
+        if not self.white:
+            # layers.py:160-163 "initialize to prior": q_sqrt = chol(K(Z,Z) + jitter I).  This runs once at
+            # construction on M x M host data (NumPy in the reference too: np.linalg.cholesky, layers.py:162).
+            Ku = _host_K(kern, Z)
+            Lu = np.linalg.cholesky(Ku + np.eye(Z.shape[0]) * settings.jitter)
+            self.q_sqrt = np.tile(Lu[None], [num_outputs, 1, 1])
+
+    # ---- evaluation through the device
+    def _ctx_model(self):
+        if self._model is None:
+            from .dgp import _single_layer_model
+            object.__setattr__(self, "_model", _single_layer_model(self))
+        return self._model
+
+    def conditional_ND(self, X, full_cov=False):
+        """layers.py:178-219: mean, var of q(f(X)), both (N, num_outputs)."""
+        if full_cov:
+            raise NotImplementedError("full_cov=True is not on the accelerated path yet (SURVEY.md 8(f) rank 3)")
+        return self._ctx_model()._layer_conditional(self, np.asarray(X))
+
+    def conditional_SND(self, X, full_cov=False):
+        """layers.py:52-74."""
+        X = np.asarray(X)
+        S, N, D = X.shape
+        m, v = self.conditional_ND(X.reshape(S * N, D), full_cov=full_cov)
+        return m.reshape(S, N, self.num_outputs), v.reshape(S, N, self.num_outputs)
+
+    def sample_from_conditional(self, X, z=None, full_cov=False):
+        """layers.py:76-119: returns samples, mean, var, each (S,N,num_outputs)."""
+        mean, var = self.conditional_SND(X, full_cov=full_cov)
+        if z is None:
+            z = np.random.randn(*mean.shape)
+        from .utils import reparameterize
+        return reparameterize(mean, var, np.asarray(z)), mean, var
+
+    def KL(self):
+        """layers.py:221-246."""
+        return self._ctx_model()._layer_KL(self)
+
+
+def _host_K(kern, Z):
+    """K(Z,Z) for the construction-time q_sqrt initialisation only (M x M, once)."""
+    ls = np.asarray(kern.lengthscales.value, dtype=np.float64)
+    d = (Z[:, None, :] - Z[None, :, :]) / ls
+    r2 = np.sum(d * d, -1)
+    var = float(kern.variance.value)
+    if kern.code == 0:
+        return var * np.exp(-0.5 * r2)
+    r = np.sqrt(r2 + 1e-12)
+    return var * (1 + np.sqrt(5.0) * r + 5.0 / 3.0 * r * r) * np.exp(-np.sqrt(5.0) * r)

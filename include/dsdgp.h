@@ -1,0 +1,162 @@
+/*
+ * dsdgp.h -- C-ABI of libdsdgp.so: the B200-native doubly-stochastic DGP hot path.
+ *
+ * The reference (UCL-SML/Doubly-Stochastic-DGP) has no FFI: its boundary is the Python object API
+ * called by GPflow's Model/optimiser machinery.  This header is the boundary BASELINE.json's
+ * north_star defines ("Python host over a thin C-ABI (ctypes)"); each entry point names the
+ * reference interface it replaces (file:line relative to /root/reference).  The ctypes binding a
+ * maintainer would add is shown in INTEGRATION.md and implemented in
+ * doubly-stochastic-dgp_b200/doubly_stochastic_dgp/_lib.py.
+ *
+ * Conventions: every function returns 0 on success or a negative DSDGP_ERR_* code; no C++
+ * exception crosses the boundary; dsdgp_last_error() returns a thread-local message.  All arrays
+ * are row-major, layouts exactly the reference's: X (N,D_in), Y (N,D_y), Z (M,D_in), q_mu (M,D_out),
+ * q_sqrt (D_out,M,M) lower-triangular dense, z / F / Fmean / Fvar (S,N,D_out).
+ * Data (X, Y, z, F*) is float32 (the arithmetic type of the per-row kernels); parameters cross the
+ * boundary as float64 (the reference's float_type) and are held in fp32 on the device, with the
+ * per-step M x M factorisations done in fp64.
+ * A ctx is bound to one device and is not thread-safe.  Work is enqueued on the ctx's stream;
+ * calls that return a host scalar synchronise.
+ */
+#ifndef DSDGP_H
+#define DSDGP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DSDGP_API __attribute__((visibility("default")))
+#else
+#define DSDGP_API
+#endif
+
+#define DSDGP_MAX_LAYERS 16
+
+/* error codes */
+#define DSDGP_OK 0
+#define DSDGP_ERR_INVALID (-1)      /* bad argument / shape */
+#define DSDGP_ERR_CUDA (-2)         /* CUDA runtime error (message has the detail) */
+#define DSDGP_ERR_NOT_PD (-3)       /* Kuu + jitter*I not positive definite (tf.cholesky would raise) */
+#define DSDGP_ERR_NCCL (-4)
+#define DSDGP_ERR_UNSUPPORTED (-5)
+
+/* kernels: gpflow.kernels.RBF / Matern52 (call sites layers.py:161,171,184,213) */
+#define DSDGP_KERN_RBF 0
+#define DSDGP_KERN_MATERN52 1
+/* mean functions: gpflow.mean_functions.Zero / Identity / Linear (layers.py:219) */
+#define DSDGP_MEAN_ZERO 0
+#define DSDGP_MEAN_IDENTITY 1
+#define DSDGP_MEAN_LINEAR 2
+/* likelihoods: gpflow.likelihoods.Gaussian / MultiClass(RobustMax) (utils.py:88-93) */
+#define DSDGP_LIK_GAUSSIAN 0
+#define DSDGP_LIK_MULTICLASS 1
+
+/* parameter fields for set/get_param, get_grad */
+#define DSDGP_F_Z 0
+#define DSDGP_F_Q_MU 1
+#define DSDGP_F_Q_SQRT 2
+#define DSDGP_F_LENGTHSCALES 3      /* 1 value, or D_in values when ard */
+#define DSDGP_F_VARIANCE 4
+#define DSDGP_F_MEAN_W 5            /* Linear mean: (D_in,D_out), fixed (layer_initializations.py:41-42) */
+#define DSDGP_F_MEAN_B 6
+#define DSDGP_F_LIK_VARIANCE 7      /* layer = -1 */
+
+/* flags */
+#define DSDGP_FLAG_DEVICE_PTRS 1u   /* X, Y, zs, outputs are device pointers (default: host) */
+#define DSDGP_FLAG_NO_SYNC 2u       /* train_step: do not wait for / return the ELBO */
+
+typedef struct dsdgp_ctx dsdgp_ctx;
+
+/* One SVGP_Layer (layers.py:122-165). */
+typedef struct {
+    int M;        /* num_inducing */
+    int D_in;     /* kern.input_dim */
+    int D_out;    /* num_outputs */
+    int kernel;   /* DSDGP_KERN_* */
+    int ard;      /* 0: one lengthscale, 1: D_in lengthscales */
+    int white;    /* layers.py:124 `white` */
+    int mean;     /* DSDGP_MEAN_* */
+} dsdgp_layer_desc;
+
+/* The model (dgp.py:42-59 DGP_Base.__init__). */
+typedef struct {
+    int L;
+    dsdgp_layer_desc layers[DSDGP_MAX_LAYERS];
+    int likelihood;      /* DSDGP_LIK_* */
+    int num_classes;     /* MultiClass only */
+    int D_y;             /* columns of Y */
+    double jitter;       /* gpflow settings.jitter (layers.py:162,171; utils.py:41) */
+    int N_max;           /* largest minibatch / Xnew rows per call (per rank) */
+    int S_max;           /* largest num_samples per call */
+    int device;          /* CUDA ordinal */
+} dsdgp_desc;
+
+DSDGP_API const char* dsdgp_last_error(void);
+DSDGP_API const char* dsdgp_version(void);
+
+/* DGP_Base.__init__ (dgp.py:42-59): allocates every workspace once. */
+DSDGP_API int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc);
+DSDGP_API int dsdgp_destroy(dsdgp_ctx* ctx);
+
+/* `layer.q_mu = ndarray` etc. (tests/test_dgp.py:91-92, demos/run_regression.py:72-74).
+ * host float64 in/out; n = element count (checked). */
+DSDGP_API int dsdgp_set_param(dsdgp_ctx* ctx, int layer, int field, const double* host, size_t n);
+DSDGP_API int dsdgp_get_param(dsdgp_ctx* ctx, int layer, int field, double* host, size_t n);
+/* dELBO/dparam of the last dsdgp_elbo_grad call (what tf.gradients(likelihood_tensor) gives). */
+DSDGP_API int dsdgp_get_grad(dsdgp_ctx* ctx, int layer, int field, double* host, size_t n);
+
+/* DGP_Base.propagate (dgp.py:61-76) with full_cov=False.  zs: NULL => in-kernel Philox keyed by
+ * (seed, layer, s, n, d); else L pointers (entries may be NULL) to (S,N,D_out_l) float32.
+ * Fs/Fmeans/Fvars: NULL or arrays of L pointers (entries may be NULL) receiving (S,N,D_out_l). */
+DSDGP_API int dsdgp_propagate(dsdgp_ctx* ctx, const float* X, int N, int S, const float* const* zs,
+                    uint64_t seed, float* const* Fs, float* const* Fmeans, float* const* Fvars,
+                    unsigned flags);
+
+/* DGP_Base._build_likelihood (dgp.py:92-98) == compute_log_likelihood(): ELBO scalar. */
+DSDGP_API int dsdgp_elbo(dsdgp_ctx* ctx, const float* X, const float* Y, int N, int S, double num_data,
+               const float* const* zs, uint64_t seed, unsigned flags, double* elbo);
+
+/* ELBO and its gradient wrt every trainable (TF autodiff of dgp.py:92-98). With a
+ * communicator (dsdgp_comm_init) X,Y are this rank's rows and ELBO/gradient are all-reduced. */
+DSDGP_API int dsdgp_elbo_grad(dsdgp_ctx* ctx, const float* X, const float* Y, int N, int S, double num_data,
+                    const float* const* zs, uint64_t seed, unsigned flags, double* elbo);
+
+/* gpflow.training.AdamOptimizer(lr).minimize step (demos/run_regression.py:83): Adam on GPflow's
+ * unconstrained variables (softplus for positive parameters, lower triangle for q_sqrt). */
+DSDGP_API int dsdgp_adam_init(dsdgp_ctx* ctx, double lr, double beta1, double beta2, double eps);
+/* One session.run(minimize_op): minibatch in, ELBO (before the update) out.  zs as in dsdgp_propagate
+ * (NULL: Philox draws keyed by seed, the normal training mode). */
+DSDGP_API int dsdgp_train_step(dsdgp_ctx* ctx, const float* X, const float* Y, int N, int S, double num_data,
+                     const float* const* zs, uint64_t seed, unsigned flags, double* elbo);
+
+/* NCCL communicator for row-sharded data parallelism (no counterpart in the reference).
+ * id = 128-byte ncclUniqueId produced by dsdgp_comm_unique_id on rank 0 and broadcast by the host. */
+DSDGP_API int dsdgp_comm_unique_id(void* id128);
+DSDGP_API int dsdgp_comm_init(dsdgp_ctx* ctx, const void* id128, int rank, int world);
+
+/* SVGP_Layer.KL() for every layer (layers.py:221-246): kl[L], evaluated from the current parameters. */
+DSDGP_API int dsdgp_kl(dsdgp_ctx* ctx, double* kl);
+
+DSDGP_API int dsdgp_sync(dsdgp_ctx* ctx);
+/* Number of kernels of this library launched (or replayed inside CUDA graphs) by this ctx so far. */
+DSDGP_API long long dsdgp_launch_count(dsdgp_ctx* ctx);
+/* Time the last graph-replayed step spent on the device, from CUDA events on the ctx stream (ms). */
+DSDGP_API int dsdgp_last_step_ms(dsdgp_ctx* ctx, float* ms);
+/* CUDA-event stopwatch on the ctx stream (the stream every kernel of this ctx is launched on). */
+DSDGP_API int dsdgp_timer_start(dsdgp_ctx* ctx);
+DSDGP_API int dsdgp_timer_stop(dsdgp_ctx* ctx, float* ms);
+/* Per-stage device time of the last step run with option "profile"=1 (eager launches bracketed by events).
+ * Fills up to n entries: [0] prep, [1] lik, [2] fin, [3] comm, [4] adam, then per layer l:
+ * [5+3l] forward, [6+3l] backward rows, [7+3l] row reductions.  Returns the number of entries. */
+DSDGP_API int dsdgp_profile(dsdgp_ctx* ctx, float* ms, int n);
+/* Tuning / diagnostics knobs: "graph" (0/1), "profile" (0/1), "n_global", "n_offset". */
+DSDGP_API int dsdgp_set_option(dsdgp_ctx* ctx, const char* name, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSDGP_H */

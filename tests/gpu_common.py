@@ -1,0 +1,30 @@
+"""Helpers for the -m gpu parity tests: build the product model (ctypes -> libdsdgp.so) from a synthetic problem."""
+import numpy as np
+
+from doubly_stochastic_dgp import settings
+from doubly_stochastic_dgp.dgp import DGP_Base
+from doubly_stochastic_dgp.kernels import RBF, Matern52
+from doubly_stochastic_dgp.layers import SVGP_Layer
+from doubly_stochastic_dgp.likelihoods import Gaussian, MultiClass
+from doubly_stochastic_dgp.mean_functions import Identity, Linear, Zero
+
+
+def build_model(prob, **kw):
+    settings.jitter = prob['jitter']
+    kcls = RBF if prob['kern'] == 'rbf' else Matern52
+    layers = []
+    for lay in prob['layers']:
+        kern = kcls(lay['din'], variance=lay['var'], lengthscales=lay['ls'])
+        mf = {'zero': Zero, 'identity': Identity}.get(lay['mean'], None)
+        mf = mf() if mf else Linear(lay['W'])
+        layer = SVGP_Layer(kern, lay['Z'], lay['dout'], mf, white=lay['white'])
+        layer.q_mu = lay['q_mu']
+        layer.q_sqrt = lay['q_sqrt']
+        layers.append(layer)
+    lik = MultiClass(prob['n_classes']) if prob['n_classes'] else Gaussian(prob['lik_var'])
+    return DGP_Base(prob['X'], prob['Y'], lik, layers, num_samples=prob['S'], num_data=prob['num_data'], **kw)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
