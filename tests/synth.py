@@ -3,10 +3,22 @@
 import numpy as np
 
 
+def _gram(kern, Z, ls, var):
+    d = (Z[:, None, :] - Z[None, :, :]) / ls
+    r2 = np.sum(d * d, -1)
+    if kern == 'rbf':
+        return var * np.exp(-0.5 * r2)
+    r = np.sqrt(r2 + 1e-12)
+    return var * (1 + np.sqrt(5) * r + 5 / 3 * r * r) * np.exp(-np.sqrt(5) * r)
+
+
 def make_problem(dims, N, M, S, seed, kern='rbf', white=False, ard=False, inner_var=0.05,
                  final_var=1.0, lik_var=0.05, jitter=1e-6, inner_q_scale=1e-5, num_data=None,
-                 n_classes=0):
-    """dims = [D_in, D_1, ..., D_L].  Returns a dict of float64 arrays (per-layer lists)."""
+                 n_classes=0, max_cond=3e4):
+    """dims = [D_in, D_1, ..., D_L].  Returns a dict of float64 arrays (per-layer lists).
+    Lengthscales start at sqrt(D_in) and are shrunk until cond(Kuu + jitter I) <= max_cond, the
+    conditioning regime of the north-star config (1.7e4): the per-row kernels are fp32, whose error scales as
+    eps_fp32 * cond(Kuu) (DESIGN.md "Numerics"), so parity problems are kept where fp32 is meaningful."""
     rng = np.random.default_rng(seed)
     L = len(dims) - 1
     X = rng.normal(size=(N, dims[0]))
@@ -37,6 +49,10 @@ def make_problem(dims, N, M, S, seed, kern='rbf', white=False, ard=False, inner_
             else:
                 W = np.concatenate([np.eye(din), np.zeros((din, dout - din))], 1)
         Z = Zrun.copy()
+        for _ in range(40):
+            if max_cond is None or np.linalg.cond(_gram(kern, Z, ls, var) + jitter * np.eye(M)) <= max_cond:
+                break
+            ls = ls * 0.85
         q_mu = 0.3 * rng.normal(size=(M, dout))
         layers.append(dict(kern=kern, Z=Z, q_mu=q_mu, ls=ls, var=var, white=white, mean=mean, W=W,
                            din=din, dout=dout, last=last))
@@ -44,13 +60,7 @@ def make_problem(dims, N, M, S, seed, kern='rbf', white=False, ard=False, inner_
             Zrun = Zrun @ W
     # q_sqrt needs Kuu -> filled by the caller-independent helper below
     for lay in layers:
-        d = (lay['Z'][:, None, :] - lay['Z'][None, :, :]) / lay['ls']
-        r2 = np.sum(d * d, -1)
-        if kern == 'rbf':
-            K = lay['var'] * np.exp(-0.5 * r2)
-        else:
-            r = np.sqrt(r2 + 1e-12)
-            K = lay['var'] * (1 + np.sqrt(5) * r + 5 / 3 * r * r) * np.exp(-np.sqrt(5) * r)
+        K = _gram(kern, lay['Z'], lay['ls'], lay['var'])
         Lu = np.linalg.cholesky(K + jitter * np.eye(M))
         if lay['last']:
             q = np.tril(0.1 * rng.normal(size=(lay['dout'], M, M))) + 0.3 * np.eye(M)[None]
