@@ -101,6 +101,8 @@ struct dsdgp_ctx {
     int n_global_opt, n_offset_opt;
     // graphs
     bool use_graph;
+    int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
+    float* wpack[DSDGP_MAX_LAYERS];
     std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, int, int, unsigned>, long long> graph_launches;
     long long nlaunch;
@@ -184,6 +186,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
         c->prof_used[i] = false;
     }
     CK(layer_kernels_init());
+    CK(layer_tc_init());
     CK(small_matrix_init());
 
     const int L = desc->L;
@@ -261,6 +264,9 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
             CK(dmalloc(&c->xbar[l], Rl * d.D_in));
             CK(dmalloc(&c->meanW[l], (size_t)d.D_in * d.D_out)); CK(dmalloc(&c->meanB[l], (size_t)d.D_out));
             LayerDev& P = c->ls.l[l];
+            c->wpack[l] = nullptr;
+            if (d.M <= 128 && d.M >= 8 && d.D_in <= 16 && d.D_out <= 32) CK(dmalloc(&c->wpack[l], tc_fwd_pack_bytes(d.M, d.D_out, d.white) / sizeof(float)));
+            P.wpack_fwd = c->wpack[l];
             P.M = d.M; P.Din = d.D_in; P.Dout = d.D_out; P.kern = d.kernel; P.ard = d.ard; P.white = d.white;
             P.mean = d.mean; P.n_ls = o.n_ls; P.idx = l;
             P.Z = c->params + o.Z; P.q_mu = c->params + o.q_mu; P.q_sqrt = c->params + o.q_sqrt;
@@ -282,7 +288,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     c->adam_on = false; c->free_dirty = true; c->adam_t = 0;
     c->lr = 0.01; c->beta1 = 0.9; c->beta2 = 0.999; c->eps = 1e-8;
     c->comm = nullptr; c->rank = 0; c->world = 1; c->n_global_opt = -1; c->n_offset_opt = -1;
-    c->use_graph = true; c->nlaunch = 0; c->last_ms = 0.f;
+    c->use_graph = true; c->nlaunch = 0; c->last_ms = 0.f; c->path = 1;
     *out = c;
     return DSDGP_OK;
 }
@@ -297,7 +303,7 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     for (float* p : fl) cudaFree(p);
     cudaFree(c->kinds); cudaFree(c->sm64); cudaFree(c->sa_dev); cudaFree(c->acc); cudaFree(c->result_dev);
     for (int l = 0; l < c->desc.L; ++l) {
-        float* pl[] = {c->U[l], c->Fmean[l], c->Fvar[l], c->F[l], c->zs[l], c->xbar[l], c->meanW[l], c->meanB[l]};
+        float* pl[] = {c->U[l], c->Fmean[l], c->Fvar[l], c->F[l], c->zs[l], c->xbar[l], c->meanW[l], c->meanB[l], c->wpack[l]};
         for (float* p : pl) cudaFree(p);
     }
     cudaFreeHost(c->sa_host); cudaFreeHost(c->result_host);
@@ -389,6 +395,9 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     }
     PROF_BEGIN(0);
     launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, st, nl);
+    bool any_tc = false;
+    for (int l = 0; l < L; ++l) any_tc |= c->path == 1 && tc_fwd_supported(c->ls.l[l]);
+    if (any_tc) launch_pack_fwd(c->ls, st, nl);
     PROF_END(0);
     // forward
     for (int l = 0; l < L; ++l) {
@@ -402,7 +411,8 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         if (l == 0 && L == 1 && mode == MODE_PROPAGATE) a.S_rep = S;     // single layer: still S draws for Fs
         a.z = (zmask >> l) & 1u ? c->zs[l] : nullptr;
         PROF_BEGIN(5 + 3 * l);
-        launch_fwd(c->ls.l[l], a, c->num_sms, st, nl);
+        if (c->path == 1 && tc_fwd_supported(c->ls.l[l])) launch_fwd_tc(c->ls.l[l], a, st, nl);
+        else launch_fwd(c->ls.l[l], a, c->num_sms, st, nl);
         PROF_END(5 + 3 * l);
     }
     if (mode == MODE_PROPAGATE) return DSDGP_OK;
@@ -702,6 +712,11 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     std::string n(name);
     if (n == "graph") c->use_graph = value != 0;
     else if (n == "profile") c->profile = value != 0;
+    else if (n == "path") {
+        c->path = (int)value;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    }
     else if (n == "n_global") c->n_global_opt = (int)value;
     else if (n == "n_offset") c->n_offset_opt = (int)value;
     else return set_err(DSDGP_ERR_INVALID, "unknown option '%s'", name);

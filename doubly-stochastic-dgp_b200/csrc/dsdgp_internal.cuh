@@ -20,6 +20,7 @@ struct LayerDev {
     // per-step small-matrix results
     double *K64, *Lu64, *Linv64, *Kinv64, *Ssum64, *T1, *KbarKL, *Gsym;   // M x M each
     float *Linv32, *LinvT32, *q_sqrtT;                                    // M x M, M x M, D x M x M
+    float *wpack_fwd;                                                     // tcgen05 path: packed tf32 weight tiles (or NULL)
     double *scal;   // [0] sum log diag Lu  [1] sum log diag(q_sqrt)^2  [2] tr(Kinv Ssum)  [3] KL  [4] sum q_sqrt^2+q_mu^2 (white)
     // row-reduced accumulators (zeroed every step)
     float *Pd;      // D x M x M : sum_r vbar_rd u_r u_r^T
@@ -163,6 +164,11 @@ void launch_lik_multiclass(const float* Fmean, const float* Fvar, const float* Y
 void launch_elbo_finish(Accum* acc, const StepArgs* sa, float* glikvar, float* elbo_hi_lo, cudaStream_t st, long long* nlaunch);
 void launch_result(const Accum* acc, const float* elbo_hi_lo, int use_hi_lo, double* result, cudaStream_t st, long long* nlaunch);
 cudaError_t layer_kernels_init();
+cudaError_t layer_tc_init();
+bool tc_fwd_supported(const LayerDev& P);
+size_t tc_fwd_pack_bytes(int M, int D, int white);
+void launch_pack_fwd(const LayerSet& ls, cudaStream_t st, long long* nlaunch);
+void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nlaunch);
 cudaError_t small_matrix_init();
 void launch_adam(float* params, float* free_, float* m, float* v, const float* grads, const unsigned char* kinds,
                  const int* tril_m, size_t n, const StepArgs* sa, cudaStream_t st, long long* nlaunch);

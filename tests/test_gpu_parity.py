@@ -9,9 +9,16 @@ from tests.synth import build_oracle, make_problem, round_f32
 pytestmark = pytest.mark.gpu
 
 
-def _model(prob):
+def _model(prob, path=1):
     from tests.gpu_common import build_model
-    return build_model(prob)
+    m = build_model(prob)
+    m._ensure_ctx(prob['N'], prob['S']).set_option("path", path)
+    return m
+
+
+# path 0 = fp32 SIMT row kernels everywhere; path 1 = tcgen05 kernels where supported (3xTF32 projections,
+# 1xTF32 variance / gradient GEMMs).  Tolerances are stated per path.
+PATHS = [0, 1]
 
 
 SMALL = [
@@ -23,21 +30,23 @@ SMALL = [
 ]
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("white", [False, True])
 @pytest.mark.parametrize("case", range(len(SMALL)))
-def test_propagate_matches_oracle(case, white):
+def test_propagate_matches_oracle(case, white, path):
     """Per-layer Fmean / Fvar / F with injected z (propagate(zs=...), dgp.py:62-70).  fp32 row kernels, errors
     compound through the layers at ~eps_fp32*cond(Kuu): tolerance 5e-4 of the layer's scale (1e-3 for the draw)."""
     prob = round_f32(make_problem(seed=200 + case, white=white, inner_q_scale=0.3, **SMALL[case]))
-    m = _model(prob)
+    m = _model(prob, path)
+    tol = 1.0 if path == 0 else 6.0      # single-pass TF32 on the |L_d^T u|^2 GEMM: ~2^-11 per product
     Fs, Fm, Fv = m.propagate(prob['X'], S=prob['S'], zs=prob['zs'])
     o = build_oracle(prob)
     oFs, oFm, oFv = o.propagate(prob['X'], S=prob['S'], zs=prob['zs'])
     for l in range(len(Fs)):
         sc = max(1.0, float(np.abs(oFm[l].numpy()).max()))
-        assert_allclose(Fm[l], oFm[l].numpy(), atol=5e-4 * sc, rtol=0, err_msg=f"Fmean l={l}")
-        assert_allclose(Fv[l], oFv[l].numpy(), atol=5e-4 * sc, rtol=0, err_msg=f"Fvar l={l}")
-        assert_allclose(Fs[l], oFs[l].numpy(), atol=1e-3 * sc, rtol=0, err_msg=f"F l={l}")
+        assert_allclose(Fm[l], oFm[l].numpy(), atol=5e-4 * sc * tol, rtol=0, err_msg=f"Fmean l={l}")
+        assert_allclose(Fv[l], oFv[l].numpy(), atol=5e-4 * sc * tol, rtol=0, err_msg=f"Fvar l={l}")
+        assert_allclose(Fs[l], oFs[l].numpy(), atol=1e-3 * sc * tol, rtol=0, err_msg=f"F l={l}")
 
 
 CONFIGS = {
@@ -48,28 +57,32 @@ CONFIGS = {
 }
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("white", [False, True])
 @pytest.mark.parametrize("name", list(CONFIGS))
-def test_elbo_within_1e4(name, white):
+def test_elbo_within_1e4(name, white, path):
     """ELBO vs the float64 oracle evaluated on the ORIGINAL float64 inputs: rel err <= 1e-4 (north_star)."""
     prob = make_problem(seed=1000 * (1 + list(CONFIGS).index(name)), white=white, num_data=8192, **CONFIGS[name])
-    m = _model(prob)
+    m = _model(prob, path)
     e = m.compute_log_likelihood(zs=prob['zs'])
     o = build_oracle(prob)
     e_ref = o.compute_log_likelihood(zs=prob['zs'])
     assert abs(e - e_ref) <= 1e-4 * abs(e_ref), (e, e_ref)
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("white", [False, True])
 @pytest.mark.parametrize("case", range(len(SMALL)))
-def test_gradients_match_autograd(case, white):
-    """dELBO/dparam vs oracle autograd; tolerance 2e-3 of each tensor's max |g| (fp32 row kernels)."""
+def test_gradients_match_autograd(case, white, path):
+    """dELBO/dparam vs oracle autograd; tolerance 2e-3 (fp32 SIMT) / 1e-2 (TF32 tensor-core GEMMs) of each
+    tensor's max |g|; ELBO 1e-5 / 1e-4."""
     prob = round_f32(make_problem(seed=300 + case, white=white, inner_q_scale=0.3, num_data=500, **SMALL[case]))
-    m = _model(prob)
+    m = _model(prob, path)
+    gtol = 2e-3 if path == 0 else 1e-2
     e, grads, glik = m.compute_log_likelihood_and_grad(zs=prob['zs'])
     o = build_oracle(prob)
     e_ref, g_ref = o.elbo_and_grad(zs=prob['zs'])
-    assert abs(e - e_ref) <= 1e-5 * abs(e_ref)
+    assert abs(e - e_ref) <= (1e-5 if path == 0 else 1e-4) * abs(e_ref)
     i = 0
     for l, g in enumerate(grads):
         Z, q_mu, q_sqrt, var, ls = [x.numpy() for x in g_ref[i:i + 5]]
@@ -77,8 +90,8 @@ def test_gradients_match_autograd(case, white):
         for name, got, ref in (("Z", g['Z'], Z), ("q_mu", g['q_mu'], q_mu), ("q_sqrt", g['q_sqrt'], np.tril(q_sqrt)),
                                ("variance", g['variance'], var), ("lengthscales", g['lengthscales'], ls)):
             sc = np.max(np.abs(ref)) + 1e-12
-            assert_allclose(got, ref, atol=2e-3 * sc, rtol=0, err_msg=f"{name} l={l}")
-    assert_allclose(glik, g_ref[i].numpy(), rtol=2e-3)
+            assert_allclose(got, ref, atol=gtol * sc, rtol=0, err_msg=f"{name} l={l}")
+    assert_allclose(glik, g_ref[i].numpy(), rtol=gtol)
 
 
 def test_gradients_northstar_shape():
@@ -222,3 +235,23 @@ def test_ragged_and_tiny_shapes():
         e = m.compute_log_likelihood(zs=prob['zs'])
         e_ref = build_oracle(prob).compute_log_likelihood(zs=prob['zs'])
         assert abs(e - e_ref) <= 1e-4 * abs(e_ref) + 1e-4, (N, M, e, e_ref)
+
+
+@pytest.mark.parametrize("white", [False, True])
+def test_tcgen05_forward_matches_simt_forward(white):
+    """The tensor-core forward (3xTF32 projections + 1xTF32 variance GEMM) against the fp32 SIMT forward of the
+    same library and the oracle, per layer.  TF32 single-pass on |c_d|^2 costs ~1e-4 relative on Fvar."""
+    prob = round_f32(make_problem(seed=1234, dims=[8, 8, 8, 1], N=300, M=100, S=3, white=white, inner_q_scale=0.3))
+    m = _model(prob)
+    ctx = m._ensure_ctx(prob['N'], prob['S'])
+    out = {}
+    for path in (0, 1):
+        ctx.set_option("path", path)
+        out[path] = m.propagate(prob['X'], S=prob['S'], zs=prob['zs'])
+    o = build_oracle(prob).propagate(prob['X'], S=prob['S'], zs=prob['zs'])
+    for l in range(3):
+        for which, name in ((1, "Fmean"), (2, "Fvar"), (0, "F")):
+            ref = o[which][l].numpy()
+            sc = max(1.0, float(np.abs(ref).max()))
+            assert_allclose(out[1][which][l], out[0][which][l], atol=1e-3 * sc, rtol=0, err_msg=f"tc vs simt {name} l={l}")
+            assert_allclose(out[1][which][l], ref, atol=1e-3 * sc, rtol=0, err_msg=f"tc vs oracle {name} l={l}")
