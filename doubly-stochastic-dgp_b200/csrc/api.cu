@@ -102,6 +102,7 @@ struct dsdgp_ctx {
     // graphs
     bool use_graph;
     int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
+    int dbg_layer; long long* dbg_buf;
     float* wpack[DSDGP_MAX_LAYERS];
     std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, int, int, unsigned>, long long> graph_launches;
@@ -289,6 +290,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     c->lr = 0.01; c->beta1 = 0.9; c->beta2 = 0.999; c->eps = 1e-8;
     c->comm = nullptr; c->rank = 0; c->world = 1; c->n_global_opt = -1; c->n_offset_opt = -1;
     c->use_graph = true; c->nlaunch = 0; c->last_ms = 0.f; c->path = 1;
+    c->dbg_layer = -1; CK(dmalloc(&c->dbg_buf, 64));
     *out = c;
     return DSDGP_OK;
 }
@@ -410,6 +412,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         a.F = (l < L - 1 || mode == MODE_PROPAGATE) ? c->F[l] : nullptr;
         if (l == 0 && L == 1 && mode == MODE_PROPAGATE) a.S_rep = S;     // single layer: still S draws for Fs
         a.z = (zmask >> l) & 1u ? c->zs[l] : nullptr;
+        a.dbg = (c->dbg_layer == l) ? c->dbg_buf : nullptr;
         PROF_BEGIN(5 + 3 * l);
         if (c->path == 1 && tc_fwd_supported(c->ls.l[l])) launch_fwd_tc(c->ls.l[l], a, st, nl);
         else launch_fwd(c->ls.l[l], a, c->num_sms, st, nl);
@@ -712,7 +715,16 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     std::string n(name);
     if (n == "graph") c->use_graph = value != 0;
     else if (n == "profile") c->profile = value != 0;
-    else if (n == "path") {
+    else if (n == "dbg_layer") {
+        c->dbg_layer = (int)value;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "dbg_dump") {
+        long long h[64];
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpy(h, c->dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 41; ++i) if (h[i]) fprintf(stderr, "dbg[%d] = %lld (+%lld)\n", i, h[i] - h[0], i ? h[i] - h[i - 1] : 0);
+    } else if (n == "path") {
         c->path = (int)value;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();

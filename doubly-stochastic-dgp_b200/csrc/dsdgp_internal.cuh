@@ -94,6 +94,19 @@ __device__ __forceinline__ void kern_eval_f(int kern, float r2, float var, float
         kp = var * e * (-5.0f / 6.0f) * (1.0f + s5 * r);
     }
 }
+// fast-path variant for the tensor-core kernels: ex2.approx-based exponential (rel. error ~|x| 2^-23)
+__device__ __forceinline__ void kern_eval_fast(int kern, float r2, float var, float& k, float& kp) {
+    if (kern == DSDGP_KERN_RBF) {
+        k = var * __expf(-0.5f * r2);
+        kp = -0.5f * k;
+    } else {
+        float r = sqrtf(r2 + 1e-12f);
+        const float s5 = 2.2360679774997896f;
+        float e = __expf(-s5 * r);
+        k = var * (1.0f + s5 * r + (5.0f / 3.0f) * r * r) * e;
+        kp = var * e * (-5.0f / 6.0f) * (1.0f + s5 * r);
+    }
+}
 __device__ __forceinline__ void kern_eval_d(int kern, double r2, double var, double& k, double& kp) {
     if (kern == DSDGP_KERN_RBF) {
         k = var * exp(-0.5 * r2);
@@ -133,6 +146,7 @@ struct FwdArgs {
     const float* z;       // (S_rep*R, Dout) or NULL -> Philox
     float jitter;
     const StepArgs* sa;
+    long long* dbg;       // optional clock64() stamps of CTA 0 (diagnostics), else NULL
 };
 
 struct BwdArgs {

@@ -11,9 +11,9 @@
 #include "tc_common.cuh"
 
 #define TC_ROWS 128
-#define TC_NSTAGE 5
+#define TC_NSTAGE 4
 #define TC_CHUNK_BYTES 16384
-#define TC_THREADS 160
+#define TC_THREADS 320
 
 // ----------------------------------------------------------------------------------------------
 // weight packing: chunk stream consumed by k_layer_fwd_tc
@@ -49,8 +49,10 @@ void launch_pack_fwd(const LayerSet& ls, cudaStream_t st, long long* nl) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// forward kernel
+// forward kernel.  288 threads: warps 0-7 = row warps (two threads per row: thread t and t+128 share TMEM lane t&127
+// and split the accumulator columns / the inducing points between them), warp 8 = control (TMA + MMA issue).
 // ----------------------------------------------------------------------------------------------
+#define TC_ROWTHREADS 256
 template <int DINP, int DOUTP>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdArgs a) {
     using namespace tc;
@@ -59,7 +61,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t A_hi = sbase, A_lo = sbase + 65536, Bring = sbase + 131072;
     const uint32_t misc = Bring + TC_NSTAGE * TC_CHUNK_BYTES;
-    // barriers (8 B each)
     const uint32_t bar_full = misc, bar_empty = misc + 8 * TC_NSTAGE;
     const uint32_t bar_a = bar_empty + 8 * TC_NSTAGE;        // a_ready[3]
     const uint32_t bar_acc = bar_a + 24;                      // acc_full[2]
@@ -67,7 +68,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     const uint32_t bar_acc2e = bar_acc2f + 16;                // acc2_empty[2]
     const uint32_t tmem_slot = bar_acc2e + 16;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + (tmem_slot - sbase));
-    float* mean_s = reinterpret_cast<float*>(sgen + (A_lo - sbase));       // [128][D] scratch, valid once A_lo is dead
+    float* part_s = reinterpret_cast<float*>(sgen + (misc + 256 - sbase));        // [2][128] |b|^2 partials
+    float* Zs = part_s + 256;                                                       // [M][Din]
+    float* qmu_s = Zs + ((P.M * P.Din + 3) & ~3);                                   // [M][D], 16-byte aligned
+    // scratch aliased on A_lo once it is dead (G2 reads A_hi only): mean partials [2][128][D], |c_d|^2 partials [2][D][128]
+    float* mean_p = reinterpret_cast<float*>(sgen + (A_lo - sbase));
+    float* csq_p = mean_p + 2 * 128 * P.Dout;
 
     const int M = P.M, Din = P.Din, D = P.Dout;
     const int nkb = (M + 31) / 32, NPAD = (M + 15) & ~15;
@@ -77,11 +83,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int i = 0; i < 3; ++i) mbar_init(bar_a + 8 * i, 128);
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc + 8 * i, 1); mbar_init(bar_acc2f + 8 * i, 1); mbar_init(bar_acc2e + 8 * i, 128); }
+        for (int i = 0; i < 3; ++i) mbar_init(bar_a + 8 * i, TC_ROWTHREADS);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc + 8 * i, 1); mbar_init(bar_acc2f + 8 * i, 1); mbar_init(bar_acc2e + 8 * i, TC_ROWTHREADS); }
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) Zs[e] = P.Z[e];
+    for (int e = threadIdx.x; e < M * D; e += TC_THREADS) qmu_s[e] = P.q_mu[e];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -89,71 +97,108 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     const uint32_t idesc = make_idesc_tf32(128, NPAD);
     const int n1 = 2 * nkb, n1p = P.white ? 0 : 2 * nkb, NC = n1 + n1p + D * nkb;
 
-    if (warp == 4) {
-        // ===================== control warp: TMA producer + MMA issuer (one lane) =====================
+    if (warp == 8) {
+        // ===================== TMA producer (one lane): streams the packed weight chunks through the ring ==========
         if (lane == 0) {
             const char* wsrc = reinterpret_cast<const char*>(P.wpack_fwd);
-            const int PRE = TC_NSTAGE - 1;
-            for (int it = 0; it < NC + PRE; ++it) {
-                if (it < NC) {
-                    int s = it % TC_NSTAGE, n = it / TC_NSTAGE;
-                    mbar_wait(bar_empty + 8 * s, (n & 1) ^ 1);
-                    mbar_arrive_expect_tx(bar_full + 8 * s, copy_bytes);
-                    tma_bulk_g2s(Bring + s * TC_CHUNK_BYTES, wsrc + (size_t)it * TC_CHUNK_BYTES, copy_bytes, bar_full + 8 * s);
-                }
-                int j = it - PRE;
-                if (j < 0) continue;
-                int s = j % TC_NSTAGE, n = j / TC_NSTAGE;
-                // decode chunk
-                int gemm, kb, part = 0, d = 0;
-                if (j < n1) { gemm = 0; kb = j >> 1; part = j & 1; }
-                else if (j < n1 + n1p) { gemm = 1; kb = (j - n1) >> 1; part = (j - n1) & 1; }
-                else { gemm = 2; d = (j - n1 - n1p) / nkb; kb = (j - n1 - n1p) % nkb; }
-                // activation / accumulator dependencies
-                if (gemm == 0 && j == 0) mbar_wait(bar_a, 0);
-                if (gemm == 1 && j == n1) mbar_wait(bar_a + 8, 0);
-                if (gemm == 2 && kb == 0) {
-                    if (d == 0) mbar_wait(bar_a + 16, 0);
-                    if (d >= 2) mbar_wait(bar_acc2e + 8 * (d & 1), ((d >> 1) - 1) & 1);
-                }
-                mbar_wait(bar_full + 8 * s, n & 1);
+            int s = 0, it = 0;
+            uint32_t ph = 1;      // producer waits on the "previous" phase of empty[s] first
+            // rows [r0, r0+nr) of chunk `it` are needed (the weight matrices are triangular); always lands at the slot start
+            auto load = [&](int r0, int nr) {
+                mbar_wait(bar_empty + 8 * s, ph);
+                mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)nr * 128u);
+                tma_bulk_g2s(Bring + s * TC_CHUNK_BYTES, wsrc + (size_t)it * TC_CHUNK_BYTES + (size_t)r0 * 128, (uint32_t)nr * 128u,
+                             bar_full + 8 * s);
+                ++it;
+                if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
+            };
+            // G1 (B[n][k] = Linv[n][k], k <= n): k-block kb touches rows n >= 32 kb
+            for (int kb = 0; kb < nkb; ++kb) { load(32 * kb, NPAD - 32 * kb); load(32 * kb, NPAD - 32 * kb); }
+            // G1' and G2 (k >= n): k-block kb touches rows n < 32 (kb+1); issued from the last k-block down
+            if (!P.white) for (int kb = nkb - 1; kb >= 0; --kb) { it = n1 + 2 * kb; load(0, min(NPAD, 32 * kb + 32)); load(0, min(NPAD, 32 * kb + 32)); }
+            for (int d = 0; d < D; ++d)
+                for (int kb = nkb - 1; kb >= 0; --kb) { it = n1 + n1p + d * nkb + kb; load(0, min(NPAD, 32 * kb + 32)); }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer (one lane) =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            auto mkdesc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
+            // one weight chunk: D[:, c0 : c0+ncol) (+)= A[:, k-block kb] * B^T ; `fresh` = first chunk of this accumulator
+            auto do_chunk = [&](uint32_t dcol, int kb, int c0, int ncol, int mode /*0: A_hi & A_lo, 1: A_hi only*/, bool fresh) {
+                mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
                 const int nks = min(4, (M - 32 * kb + 7) / 8);
-                const uint32_t dcol = gemm == 0 ? 0u : gemm == 1 ? 128u : 256u + 128u * (uint32_t)(d & 1);
+                const uint32_t bbase = Bring + s * TC_CHUNK_BYTES, abase = kb * TC_CHUNK_BYTES;
+                const uint32_t id = make_idesc_tf32(128, ncol);
                 for (int ks = 0; ks < nks; ++ks) {
-                    uint64_t bd = make_desc_sw128_kmajor(Bring + s * TC_CHUNK_BYTES + ks * 32, 1024);
-                    uint64_t ah = make_desc_sw128_kmajor(A_hi + kb * TC_CHUNK_BYTES + ks * 32, 1024);
-                    uint32_t first = (kb | ks) == 0 ? 0u : 1u;
-                    if (gemm < 2) {
-                        if (part == 0) {
-                            uint64_t al = make_desc_sw128_kmajor(A_lo + kb * TC_CHUNK_BYTES + ks * 32, 1024);
-                            mma_tf32(tmem + dcol, ah, bd, idesc, first);
-                            mma_tf32(tmem + dcol, al, bd, idesc, 1u);
-                        } else {
-                            mma_tf32(tmem + dcol, ah, bd, idesc, 1u);
-                        }
-                    } else {
-                        mma_tf32(tmem + dcol, ah, bd, idesc, first);
-                    }
+                    const uint64_t bd = mkdesc(bbase + ks * 32), ah = mkdesc(A_hi + abase + ks * 32);
+                    const uint32_t acc = (fresh && ks == 0) ? 0u : 1u;
+                    mma_tf32(tmem + dcol + c0, ah, bd, id, acc);
+                    if (mode == 0) mma_tf32(tmem + dcol + c0, mkdesc(A_lo + abase + ks * 32), bd, id, 1u);
                 }
                 mma_commit(bar_empty + 8 * s);
-                if (gemm == 0 && j == n1 - 1) mma_commit(bar_acc);
-                if (gemm == 1 && j == n1 + n1p - 1) mma_commit(bar_acc + 8);
-                if (gemm == 2 && kb == nkb - 1) mma_commit(bar_acc2f + 8 * (d & 1));
+                if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
+            };
+            // G1: b = Linv k   (3xTF32)
+            mbar_wait(bar_a, 0);
+            tc_fence_after();
+            for (int kb = 0; kb < nkb; ++kb) {
+                do_chunk(0u, kb, 32 * kb, NPAD - 32 * kb, 0, kb == 0);     // B_hi: A_hi*B_hi + A_lo*B_hi
+                do_chunk(0u, kb, 32 * kb, NPAD - 32 * kb, 1, false);       // B_lo: A_hi*B_lo
+            }
+            mma_commit(bar_acc);
+            if (!P.white) {
+                // G1': u = Linv^T b   (3xTF32)
+                mbar_wait(bar_a + 8, 0);
+                tc_fence_after();
+                for (int kb = nkb - 1; kb >= 0; --kb) {
+                    do_chunk(128u, kb, 0, min(NPAD, 32 * kb + 32), 0, kb == nkb - 1);
+                    do_chunk(128u, kb, 0, min(NPAD, 32 * kb + 32), 1, false);
+                }
+                mma_commit(bar_acc + 8);
+            }
+            // G2: c_d = L_d^T u   (1xTF32), accumulators double-buffered
+            mbar_wait(bar_a + 16, 0);
+            tc_fence_after();
+            for (int d = 0; d < D; ++d) {
+                if (d >= 2) { mbar_wait(bar_acc2e + 8 * (d & 1), ((d >> 1) - 1) & 1); tc_fence_after(); }
+                for (int kb = nkb - 1; kb >= 0; --kb)
+                    do_chunk(256u + 128u * (uint32_t)(d & 1), kb, 0, min(NPAD, 32 * kb + 32), 1, kb == nkb - 1);
+                mma_commit(bar_acc2f + 8 * (d & 1));
             }
         }
     } else {
-        // ===================== row warps: thread t owns row t of the tile (TMEM lane t) =====================
-        const int t = threadIdx.x, row = row0 + t;
+        // ===================== row warps =====================
+        const int t = threadIdx.x & 127, half = threadIdx.x >> 7, row = row0 + t;
+        const bool dbg = a.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+        int dbi = 0;
+#define STAMP() do { if (dbg) a.dbg[dbi++] = clock64(); } while (0)
+        STAMP();
         const bool valid = row < R;
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t rsw = (uint32_t)(t & 7);
         const uint32_t rowoff = (uint32_t)((t >> 3) * 1024 + (t & 7) * 128);
         auto a_store4 = [&](uint32_t base, int k4, float4 v) {      // k4: first of 4 consecutive k (multiple of 4)
             uint32_t off = (uint32_t)(k4 >> 5) * TC_CHUNK_BYTES + rowoff + (((uint32_t)((k4 & 31) >> 2) ^ rsw) << 4);
             *reinterpret_cast<float4*>(sgen + (base - sbase) + off) = v;
         };
-        // ---- Gram: k_i = k(z_i, x) -> A_hi / A_lo (tf32 split)
+        auto split_store = [&](int k4, const float* v, bool write_lo) {
+            float4 hi, lo;
+            hi.x = tf32_rna(v[0]); hi.y = tf32_rna(v[1]); hi.z = tf32_rna(v[2]); hi.w = tf32_rna(v[3]);
+            a_store4(A_hi, k4, hi);
+            if (write_lo) {
+                lo.x = tf32_rna(v[0] - hi.x); lo.y = tf32_rna(v[1] - hi.y); lo.z = tf32_rna(v[2] - hi.z); lo.w = tf32_rna(v[3] - hi.w);
+                a_store4(A_lo, k4, lo);
+            }
+        };
+        // column range of this half: [c_lo, c_hi), multiples of 8
+        const int NH = ((NPAD >> 1) + 7) & ~7;
+        const int c_lo = half ? NH : 0, c_hi = half ? NPAD : NH;
+
+        // ---- Gram: k_i = k(z_i, x) -> A_hi / A_lo (tf32 split); the halves take alternate groups of 4
         float x[DINP], il[DINP];
 #pragma unroll
         for (int q = 0; q < DINP; ++q) {
@@ -161,148 +206,163 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
             il[q] = q < Din ? 1.0f / P.ls[P.ard ? q : 0] : 0.f;
         }
         const float var0 = P.var[0];
-        for (int i4 = 0; i4 < nkb * 32; i4 += 4) {
+        for (int i4 = 4 * half; i4 < nkb * 32; i4 += 8) {
+            float r2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = min(i4 + u, M - 1);
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < DINP; ++q) {
+                    if (q < Din) {
+                        float dd = (x[q] - Zs[i * Din + q]) * il[q];
+                        s = fmaf(dd, dd, s);
+                    }
+                }
+                r2[u] = s;
+            }
             float kv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                int i = i4 + u;
-                float k = 0.f;
-                if (i < M) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int q = 0; q < DINP; ++q) {
-                        float zq = q < Din ? __ldg(&P.Z[(size_t)i * Din + q]) : 0.f;
-                        float dd = (x[q] - zq) * il[q];
-                        s = fmaf(dd, dd, s);
-                    }
-                    float kp;
-                    kern_eval_f(P.kern, s, var0, k, kp);
-                }
-                kv[u] = k;
+                float k, kp;
+                kern_eval_fast(P.kern, r2[u], var0, k, kp);
+                kv[u] = (i4 + u < M) ? k : 0.f;
             }
-            float4 hi, lo;
-            hi.x = tf32_rna(kv[0]); hi.y = tf32_rna(kv[1]); hi.z = tf32_rna(kv[2]); hi.w = tf32_rna(kv[3]);
-            lo.x = tf32_rna(kv[0] - hi.x); lo.y = tf32_rna(kv[1] - hi.y); lo.z = tf32_rna(kv[2] - hi.z); lo.w = tf32_rna(kv[3] - hi.w);
-            a_store4(A_hi, i4, hi);
-            a_store4(A_lo, i4, lo);
+            split_store(i4, kv, true);
         }
         fence_proxy_async();
         mbar_arrive(bar_a);
+        STAMP();      // 1: Gram done
 
-        // ---- E1: b from TMEM columns [0, NPAD)
+        // ---- E1 (b) and E1' (u): this half's columns
         float bn = 0.f;
         float meanv[DOUTP];
 #pragma unroll
         for (int d = 0; d < DOUTP; ++d) meanv[d] = 0.f;
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
-        auto consume_cols = [&](uint32_t dcol, bool is_u, bool write_lo) {
-            // reads NPAD accumulator columns of this row; optionally splits them back into the A operand buffers
-            for (int c0 = 0; c0 < NPAD; c0 += 16) {
-                float v[16];
+        auto consume = [&](uint32_t dcol, bool acc_bn, bool is_u, bool write_lo) {
+            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+                float v[8];
                 __syncwarp();
-                tmem_ld16(lane_addr + dcol + c0, v);
-                if (!is_u) {
+                tmem_ld8(lane_addr + dcol + c0, v);
+                if (acc_bn) {
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) bn = fmaf(v[u], v[u], bn);
+                    for (int u = 0; u < 8; ++u) bn = fmaf(v[u], v[u], bn);
                 }
-                if (is_u) {
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        int i = c0 + u;
-                        if (i < M) {
-#pragma unroll
-                            for (int d = 0; d < DOUTP; ++d)
-                                if (d < D) meanv[d] = fmaf(v[u], __ldg(&P.q_mu[i * D + d]), meanv[d]);
-                            if (valid) a.U[(size_t)row * M + i] = v[u];
-                        }
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float4 hi, lo;
-                    hi.x = tf32_rna(v[4 * g]); hi.y = tf32_rna(v[4 * g + 1]); hi.z = tf32_rna(v[4 * g + 2]); hi.w = tf32_rna(v[4 * g + 3]);
-                    a_store4(A_hi, c0 + 4 * g, hi);
-                    if (write_lo) {
-                        lo.x = tf32_rna(v[4 * g] - hi.x); lo.y = tf32_rna(v[4 * g + 1] - hi.y);
-                        lo.z = tf32_rna(v[4 * g + 2] - hi.z); lo.w = tf32_rna(v[4 * g + 3] - hi.w);
-                        a_store4(A_lo, c0 + 4 * g, lo);
-                    }
-                }
+                split_store(c0, v, write_lo);
+                split_store(c0 + 4, v + 4, write_lo);
             }
         };
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        STAMP();      // 2: G1 accumulators ready
         if (P.white) {
-            // u = b
-            for (int c0 = 0; c0 < NPAD; c0 += 16) {
-                float v[16];
-                __syncwarp();
-                tmem_ld16(lane_addr + c0, v);
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    bn = fmaf(v[u], v[u], bn);
-                    int i = c0 + u;
-                    if (i < M) {
-#pragma unroll
-                        for (int d = 0; d < DOUTP; ++d)
-                            if (d < D) meanv[d] = fmaf(v[u], __ldg(&P.q_mu[i * D + d]), meanv[d]);
-                        if (valid) a.U[(size_t)row * M + i] = v[u];
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float4 hi;
-                    hi.x = tf32_rna(v[4 * g]); hi.y = tf32_rna(v[4 * g + 1]); hi.z = tf32_rna(v[4 * g + 2]); hi.w = tf32_rna(v[4 * g + 3]);
-                    a_store4(A_hi, c0 + 4 * g, hi);
-                }
-            }
+            consume(0u, true, false, false);
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_a + 16);
         } else {
-            consume_cols(0u, false, true);
+            consume(0u, true, false, true);
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_a + 8);
-            // ---- E1': u from TMEM columns [128, 128+NPAD)
+            STAMP();  // 3: E1 done
             mbar_wait(bar_acc + 8, 0);
             tc_fence_after();
-            consume_cols(128u, true, false);
+            STAMP();  // 4: G1' ready
+            consume(128u, false, false, false);       // critical path: u -> A_hi only
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_a + 16);
         }
-        // mean scratch (A_lo is dead: G2 reads A_hi only)
+        STAMP();      // 5: operands for G2 published
+        // off the critical path (interleaved with the G2 epilogues): mean = u . q_mu and the U store, re-reading u from TMEM
+        const uint32_t ucol = P.white ? 0u : 128u;
+        auto deferred = [&](int c0) {
+            {
+                float v[8];
+                __syncwarp();
+                tmem_ld8(lane_addr + ucol + c0, v);
 #pragma unroll
-        for (int d = 0; d < DOUTP; ++d)
-            if (d < D) mean_s[t * D + d] = meanv[d];
+                for (int u = 0; u < 8; ++u) {
+                    const int i = c0 + u;
+                    if (i < M) {
+                        bool done = false;
+                        if constexpr (DOUTP % 4 == 0) {
+                            if (D == DOUTP) {
+                                const float4* qr = reinterpret_cast<const float4*>(qmu_s + i * DOUTP);
+#pragma unroll
+                                for (int d4 = 0; d4 < DOUTP / 4; ++d4) {
+                                    float4 qv = qr[d4];
+                                    meanv[4 * d4] = fmaf(v[u], qv.x, meanv[4 * d4]);
+                                    meanv[4 * d4 + 1] = fmaf(v[u], qv.y, meanv[4 * d4 + 1]);
+                                    meanv[4 * d4 + 2] = fmaf(v[u], qv.z, meanv[4 * d4 + 2]);
+                                    meanv[4 * d4 + 3] = fmaf(v[u], qv.w, meanv[4 * d4 + 3]);
+                                }
+                                done = true;
+                            }
+                        }
+                        if (!done) {
+#pragma unroll
+                            for (int d = 0; d < DOUTP; ++d)
+                                if (d < D) meanv[d] = fmaf(v[u], qmu_s[i * D + d], meanv[d]);
+                        }
+                    }
+                }
+                if (valid) {
+                    if (c0 + 8 <= M && (M & 3) == 0) {
+                        float4* dst = reinterpret_cast<float4*>(a.U + (size_t)row * M + c0);
+                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) if (c0 + u < M) a.U[(size_t)row * M + c0 + u] = v[u];
+                    }
+                }
+            }
+        };
+        part_s[half * 128 + t] = bn;
 
-        // ---- E2: |c_d|^2, variance, draw
-        const float jit = a.jitter;
-        const unsigned long long seed = a.sa->seed;
-        const int noff = a.sa->n_offset;
+        // ---- E2: |c_d|^2 partials of this half's columns
+        const int ndef = (c_hi - c_lo) >> 3;
         for (int d = 0; d < D; ++d) {
             const int b = d & 1;
+            for (int j = d; j < ndef; j += D) deferred(c_lo + 8 * j);
             mbar_wait(bar_acc2f + 8 * b, (d >> 1) & 1);
             tc_fence_after();
+            STAMP();  // 6+2d: G2[d] ready
             float s = 0.f;
-            for (int c0 = 0; c0 < NPAD; c0 += 16) {
-                float v[16];
+            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+                float v[8];
                 __syncwarp();
-                tmem_ld16(lane_addr + 256 + 128 * b + c0, v);
+                tmem_ld8(lane_addr + 256 + 128 * b + c0, v);
 #pragma unroll
-                for (int u = 0; u < 16; ++u) s = fmaf(v[u], v[u], s);
+                for (int u = 0; u < 8; ++u) s = fmaf(v[u], v[u], s);
             }
             tc_fence_before();
             mbar_arrive(bar_acc2e + 8 * b);
-            if (valid) {
-                float mean = mean_s[t * D + d];
-                if (P.mean == DSDGP_MEAN_IDENTITY) mean += a.Xin[(size_t)row * Din + d];
+            csq_p[(half * D + d) * 128 + t] = s;
+            STAMP();  // 7+2d: E2[d] done
+        }
+#pragma unroll
+        for (int d = 0; d < DOUTP; ++d)
+            if (d < D) mean_p[(half * 128 + t) * D + d] = meanv[d];      // A_lo is dead (G1/G1' completed long ago)
+        named_bar_sync(1, TC_ROWTHREADS);
+        STAMP();
+        // ---- finalise: half h handles outputs d = h, h+2, ...
+        const float jit = a.jitter;
+        const unsigned long long seed = a.sa->seed;
+        const int noff = a.sa->n_offset;
+        const float bnt = part_s[t] + part_s[128 + t];
+        if (valid) {
+            for (int d = half; d < D; d += 2) {
+                float mean = mean_p[t * D + d] + mean_p[(128 + t) * D + d];
+                if (P.mean == DSDGP_MEAN_IDENTITY) mean += x[d < DINP ? d : 0];
                 else if (P.mean == DSDGP_MEAN_LINEAR) {
                     float ms = P.meanB[d];
                     for (int q = 0; q < Din; ++q) ms = fmaf(a.Xin[(size_t)row * Din + q], __ldg(&P.meanW[q * D + d]), ms);
                     mean += ms;
                 }
-                float v = var0 - bn + s;
+                float v = var0 - bnt + csq_p[d * 128 + t] + csq_p[(D + d) * 128 + t];
                 a.Fmean[(size_t)row * D + d] = mean;
                 a.Fvar[(size_t)row * D + d] = v;
                 if (a.F) {
@@ -322,12 +382,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
             }
         }
     }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[40] = clock64();
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-static size_t tc_fwd_smem() { return 1024 + 131072 + TC_NSTAGE * TC_CHUNK_BYTES + 256; }
+static size_t tc_fwd_smem(int M, int Din, int D) { return 1024 + 131072 + TC_NSTAGE * TC_CHUNK_BYTES + 256 + 1024 + sizeof(float) * ((size_t)M * Din + (size_t)M * D); }
 
 bool tc_fwd_supported(const LayerDev& P) { return P.M <= 128 && P.M >= 8 && P.Din <= 16 && P.Dout <= 32 && P.wpack_fwd != nullptr; }
 
@@ -335,7 +396,7 @@ bool tc_fwd_supported(const LayerDev& P) { return P.M <= 128 && P.M >= 8 && P.Di
 
 cudaError_t layer_tc_init() {
     cudaError_t e;
-#define X(a, b) if ((e = cudaFuncSetAttribute(k_layer_fwd_tc<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_fwd_smem()))) return e;
+#define X(a, b) if ((e = cudaFuncSetAttribute(k_layer_fwd_tc<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_fwd_smem(128, 16, 32)))) return e;
     TC_FWD_INSTANCES(X)
 #undef X
     return cudaSuccess;
@@ -349,7 +410,7 @@ size_t tc_fwd_pack_bytes(int M, int D, int white) {
 void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nl) {
     int grid = (a.R + TC_ROWS - 1) / TC_ROWS;
     int dinp = P.Din <= 8 ? 8 : 16, doutp = P.Dout <= 1 ? 1 : P.Dout <= 8 ? 8 : 32;
-#define X(a_, b_) if (dinp == a_ && doutp == b_) k_layer_fwd_tc<a_, b_><<<grid, TC_THREADS, tc_fwd_smem(), st>>>(P, a);
+#define X(a_, b_) if (dinp == a_ && doutp == b_) k_layer_fwd_tc<a_, b_><<<grid, TC_THREADS, tc_fwd_smem(P.M, P.Din, P.Dout), st>>>(P, a);
     TC_FWD_INSTANCES(X)
 #undef X
     *nl += 1;
