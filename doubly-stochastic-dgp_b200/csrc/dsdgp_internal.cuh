@@ -183,6 +183,9 @@ bool tc_fwd_supported(const LayerDev& P);
 size_t tc_fwd_pack_bytes(int M, int D, int white);
 void launch_pack_fwd(const LayerSet& ls, cudaStream_t st, long long* nlaunch);
 void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nlaunch);
+cudaError_t layer_tc_bwd_init();
+bool tc_bwd_supported(const LayerDev& P);
+void launch_bwd_rows_tc(const LayerDev& P, const BwdArgs& a, cudaStream_t st, long long* nlaunch);
 cudaError_t small_matrix_init();
 void launch_adam(float* params, float* free_, float* m, float* v, const float* grads, const unsigned char* kinds,
                  const int* tril_m, size_t n, const StepArgs* sa, cudaStream_t st, long long* nlaunch);

@@ -17,13 +17,13 @@
 
 // ----------------------------------------------------------------------------------------------
 // weight packing: chunk stream consumed by k_layer_fwd_tc
-//   [G1: kb x {hi,lo}] [G1' (non-white): kb x {hi,lo}] [G2: d x kb (hi)]
+//   [G1: kb x {hi,lo}] [G1': kb x {hi,lo}] [G2: d x kb (hi)] [G5: d x kb (hi)]      (G1' unused by white forwards)
 // ----------------------------------------------------------------------------------------------
 __global__ void k_pack_fwd(LayerSet ls) {
     const LayerDev& P = ls.l[blockIdx.y];
     if (!P.wpack_fwd) return;
     const int M = P.M, D = P.Dout, nkb = (M + 31) / 32;
-    const int n1 = 2 * nkb, n1p = P.white ? 0 : 2 * nkb, nchunks = n1 + n1p + D * nkb;
+    const int n1 = 2 * nkb, n1p = 2 * nkb, nchunks = n1 + n1p + 2 * D * nkb;
     const size_t total = (size_t)nchunks * 4096;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         int c = (int)(e >> 12), w = (int)(e & 4095), n = w >> 5, kk = w & 31;
@@ -35,9 +35,12 @@ __global__ void k_pack_fwd(LayerSet ls) {
                 float hi = tc::tf32_rna((float)v);
                 out = part ? tc::tf32_rna((float)(v - (double)hi)) : hi;
             }
-        } else {
+        } else if (c < n1 + n1p + D * nkb) {
             int cc = c - n1 - n1p, d = cc / nkb, kb = cc % nkb, k = kb * 32 + kk;
-            if (n < M && k < M && n <= k) out = tc::tf32_rna(P.q_sqrt[((size_t)d * M + k) * M + n]);   // B[n][k] = L_d[k][n]
+            if (n < M && k < M && n <= k) out = tc::tf32_rna(P.q_sqrt[((size_t)d * M + k) * M + n]);   // G2: B[n][k] = L_d[k][n]
+        } else {
+            int cc = c - n1 - n1p - D * nkb, d = cc / nkb, kb = cc % nkb, k = kb * 32 + kk;
+            if (n < M && k < M && k <= n) out = tc::tf32_rna(P.q_sqrt[((size_t)d * M + n) * M + k]);   // G5: B[n][k] = L_d[n][k]
         }
         *reinterpret_cast<float*>(reinterpret_cast<char*>(P.wpack_fwd) + (size_t)c * TC_CHUNK_BYTES + tc::sw128_offset(n, kk)) = out;
     }
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_gen;
     const uint32_t idesc = make_idesc_tf32(128, NPAD);
-    const int n1 = 2 * nkb, n1p = P.white ? 0 : 2 * nkb, NC = n1 + n1p + D * nkb;
+    const int n1 = 2 * nkb, n1p = 2 * nkb;      // chunk offsets in the pack (G1' chunks exist even for white layers)
 
     if (warp == 8) {
         // ===================== TMA producer (one lane): streams the packed weight chunks through the ring ==========
@@ -404,7 +407,8 @@ cudaError_t layer_tc_init() {
 
 size_t tc_fwd_pack_bytes(int M, int D, int white) {
     int nkb = (M + 31) / 32;
-    return (size_t)((white ? 2 : 4) * nkb + D * nkb) * TC_CHUNK_BYTES;
+    (void)white;
+    return (size_t)(4 * nkb + 2 * D * nkb) * TC_CHUNK_BYTES;
 }
 
 void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nl) {

@@ -1,0 +1,486 @@
+// tcgen05 tensor-core path of one SVGP layer: backward over rows (data gradient + per-row quantities the row-reduction
+// GEMMs need).  Same tiling as the forward (128 rows on the UMMA M dimension, two threads per row, one TMA producer
+// warp, one MMA-issuing warp).  Per tile:
+//   G2[d]: c_d = L_d^T u              1xTF32   (recomputed, as the SIMT path does)
+//   G5[d]: ubar += L_d (2 vbar_d c_d) 1xTF32   accumulated over d in TMEM
+//   G6   : t = Linv ubar              3xTF32   (non-white)      } w = K^-1 ubar needs the accuracy: the solve
+//   G7   : w = Linv^T t               3xTF32                    } amplifies operand rounding by ~sqrt(cond K)
+// then k̄, g = 2 k̄ dk/dr2, x̄, and the Z / lengthscale / variance partials exactly as k_layer_bwd (layer_simt.cu).
+// Math: tests/algo_mirror.py::layer_bwdA ; reference: TF autodiff of layers.py:178-219.
+#include "dsdgp_internal.cuh"
+#include "tc_common.cuh"
+
+#define TC_ROWS 128
+#define TC_NSTAGE 4
+#define TC_CHUNK_BYTES 16384
+#define TC_THREADS 320
+#define TC_ROWTHREADS 256
+
+namespace {
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                   "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+}  // namespace
+
+// shared-memory plan (bytes from the 1024-aligned base)
+struct BwdSmem {
+    uint32_t A_u, A_c, Bring, bars, Zs, qmu, mv, xs, red, total;
+};
+__host__ __device__ inline BwdSmem bwd_smem_plan(int M, int Din, int D) {
+    BwdSmem s;
+    s.A_u = 0; s.A_c = 65536; s.Bring = 131072;
+    s.bars = s.Bring + TC_NSTAGE * TC_CHUNK_BYTES;
+    s.Zs = s.bars + 256;
+    s.qmu = s.Zs + 4 * ((M * Din + 3) & ~3);
+    s.mv = s.qmu + 4 * ((M * D + 3) & ~3);
+    s.xs = s.mv + 4 * 128 * 2 * D;
+    s.red = s.xs + 4 * 128 * Din;
+    s.total = s.red + 4 * 64;
+    return s;
+}
+
+template <int DINP, int DOUTP>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdArgs a) {
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw_b[];
+    const uint32_t sbase = (smem_u32(smem_raw_b) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw_b + (sbase - smem_u32(smem_raw_b));
+    const int M = P.M, Din = P.Din, D = P.Dout;
+    const BwdSmem sp = bwd_smem_plan(M, Din, D);
+    const uint32_t A_u = sbase + sp.A_u, A_c = sbase + sp.A_c, Bring = sbase + sp.Bring, bars = sbase + sp.bars;
+    const uint32_t bar_full = bars, bar_empty = bars + 32;
+    const uint32_t bar_au = bars + 64, bar_acc2f = bars + 72 /*[2]*/, bar_cready = bars + 88, bar_cfree = bars + 96;
+    const uint32_t bar_ubar = bars + 104, bar_s6 = bars + 112, bar_acc6 = bars + 120, bar_s7 = bars + 128, bar_acc7 = bars + 136;
+    const uint32_t tmem_slot = bars + 144;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + sp.bars + 144);
+    float* Zs = reinterpret_cast<float*>(sgen + sp.Zs);
+    float* qmu_s = reinterpret_cast<float*>(sgen + sp.qmu);
+    float* mv_s = reinterpret_cast<float*>(sgen + sp.mv);       // [128][2D]: mubar (D) | vbar (D)
+    float* xs_s = reinterpret_cast<float*>(sgen + sp.xs);       // [128][Din]
+    float* red_s = reinterpret_cast<float*>(sgen + sp.red);     // [64]
+    float* g_s = reinterpret_cast<float*>(sgen + sp.A_c);       // [128][MP] once A_c is dead
+    const int MP = M | 1;                                        // odd row stride: conflict-free column walks
+
+    const int nkb = (M + 31) / 32, NPAD = (M + 15) & ~15;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * TC_ROWS, R = a.R;
+    const int n1 = 2 * nkb, off_g1p = n1, off_g2 = 2 * n1, off_g5 = 2 * n1 + D * nkb;    // chunk offsets in wpack
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_au, TC_ROWTHREADS);
+        mbar_init(bar_acc2f, 1); mbar_init(bar_acc2f + 8, 1);
+        mbar_init(bar_cready, TC_ROWTHREADS); mbar_init(bar_cfree, 1); mbar_init(bar_ubar, 1);
+        mbar_init(bar_s6, TC_ROWTHREADS); mbar_init(bar_acc6, 1); mbar_init(bar_s7, TC_ROWTHREADS); mbar_init(bar_acc7, 1);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) Zs[e] = P.Z[e];
+    for (int e = threadIdx.x; e < M * D; e += TC_THREADS) qmu_s[e] = P.q_mu[e];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_gen;
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const char* wsrc = reinterpret_cast<const char*>(P.wpack_fwd);
+            int s = 0;
+            uint32_t ph = 1;
+            auto load = [&](int chunk, int r0, int nr) {
+                mbar_wait(bar_empty + 8 * s, ph);
+                mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)nr * 128u);
+                tma_bulk_g2s(Bring + s * TC_CHUNK_BYTES, wsrc + (size_t)chunk * TC_CHUNK_BYTES + (size_t)r0 * 128, (uint32_t)nr * 128u,
+                             bar_full + 8 * s);
+                if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
+            };
+            auto g2 = [&](int d) { for (int kb = nkb - 1; kb >= 0; --kb) load(off_g2 + d * nkb + kb, 0, min(NPAD, 32 * kb + 32)); };
+            auto g5 = [&](int d) { for (int kb = 0; kb < nkb; ++kb) load(off_g5 + d * nkb + kb, 32 * kb, NPAD - 32 * kb); };
+            g2(0);
+            if (D > 1) g2(1);
+            for (int d = 0; d < D; ++d) { g5(d); if (d + 2 < D) g2(d + 2); }
+            if (!P.white)
+                for (int kb = 0; kb < nkb; ++kb) { load(2 * kb, 32 * kb, NPAD - 32 * kb); load(2 * kb + 1, 32 * kb, NPAD - 32 * kb); }
+            for (int kb = nkb - 1; kb >= 0; --kb) {
+                load(off_g1p + 2 * kb, 0, min(NPAD, 32 * kb + 32));
+                load(off_g1p + 2 * kb + 1, 0, min(NPAD, 32 * kb + 32));
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues ========
+        int s = 0;
+        uint32_t ph = 0;
+        const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        auto mkdesc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
+        // D[:, c0 : c0+ncol) (+)= Ahi[:, kb] * B^T (+ Alo[:, kb] * B^T when with_lo) ; fresh: first chunk of the accumulator
+        auto do_chunk = [&](uint32_t dcol, uint32_t Ahi, uint32_t Alo, int kb, int c0, int ncol, bool with_lo, bool fresh) {
+            mbar_wait(bar_full + 8 * s, ph);
+            tc_fence_after();
+            const int nks = min(4, (M - 32 * kb + 7) / 8);
+            const uint32_t bbase = Bring + s * TC_CHUNK_BYTES, abase = kb * TC_CHUNK_BYTES;
+            const uint32_t id = make_idesc_tf32(128, ncol);
+            if (elect_one()) {
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint64_t bd = mkdesc(bbase + ks * 32);
+                    mma_tf32(tmem + dcol + c0, mkdesc(Ahi + abase + ks * 32), bd, id, (fresh && ks == 0) ? 0u : 1u);
+                    if (with_lo) mma_tf32(tmem + dcol + c0, mkdesc(Alo + abase + ks * 32), bd, id, 1u);
+                }
+                mma_commit(bar_empty + 8 * s);
+            }
+            __syncwarp();
+            if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
+        };
+        auto commit = [&](uint32_t bar) { if (elect_one()) mma_commit(bar); __syncwarp(); };
+        auto g2 = [&](int d) {
+            for (int kb = nkb - 1; kb >= 0; --kb)
+                do_chunk(128u * (uint32_t)(d & 1), A_u, 0, kb, 0, min(NPAD, 32 * kb + 32), false, kb == nkb - 1);
+            commit(bar_acc2f + 8 * (d & 1));
+        };
+        mbar_wait(bar_au, 0);
+        tc_fence_after();
+        g2(0);
+        if (D > 1) g2(1);
+        for (int d = 0; d < D; ++d) {
+            mbar_wait(bar_cready, d & 1);
+            tc_fence_after();
+            for (int kb = 0; kb < nkb; ++kb)
+                do_chunk(256u, A_c, 0, kb, 32 * kb, NPAD - 32 * kb, false, d == 0 && kb == 0);
+            commit(bar_cfree);
+            if (d == D - 1) commit(bar_ubar);
+            if (d + 2 < D) g2(d + 2);
+        }
+        if (!P.white) {
+            mbar_wait(bar_s6, 0);
+            tc_fence_after();
+            for (int kb = 0; kb < nkb; ++kb) {
+                do_chunk(0u, A_c, A_u, kb, 32 * kb, NPAD - 32 * kb, true, kb == 0);
+                do_chunk(0u, A_c, A_u, kb, 32 * kb, NPAD - 32 * kb, false, false);
+            }
+            commit(bar_acc6);
+        }
+        mbar_wait(bar_s7, 0);
+        tc_fence_after();
+        for (int kb = nkb - 1; kb >= 0; --kb) {
+            do_chunk(128u, A_c, A_u, kb, 0, min(NPAD, 32 * kb + 32), true, kb == nkb - 1);
+            do_chunk(128u, A_c, A_u, kb, 0, min(NPAD, 32 * kb + 32), false, false);
+        }
+        commit(bar_acc7);
+    } else {
+        // ===================== row warps =====================
+        const int t = threadIdx.x & 127, half = threadIdx.x >> 7, row = row0 + t;
+        const bool valid = row < R;
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t rsw = (uint32_t)(t & 7);
+        const uint32_t rowoff = (uint32_t)((t >> 3) * 1024 + (t & 7) * 128);
+        auto a_store4 = [&](uint32_t base, int k4, float4 v) {
+            uint32_t off = (uint32_t)(k4 >> 5) * TC_CHUNK_BYTES + rowoff + (((uint32_t)((k4 & 31) >> 2) ^ rsw) << 4);
+            *reinterpret_cast<float4*>(sgen + (base - sbase) + off) = v;
+        };
+        auto store_hi = [&](uint32_t base, int k4, const float* v) {
+            float4 hi;
+            hi.x = tf32_rna(v[0]); hi.y = tf32_rna(v[1]); hi.z = tf32_rna(v[2]); hi.w = tf32_rna(v[3]);
+            a_store4(base, k4, hi);
+        };
+        auto store_hi_lo = [&](uint32_t bhi, uint32_t blo, int k4, const float* v) {
+            float4 hi, lo;
+            hi.x = tf32_rna(v[0]); hi.y = tf32_rna(v[1]); hi.z = tf32_rna(v[2]); hi.w = tf32_rna(v[3]);
+            lo.x = tf32_rna(v[0] - hi.x); lo.y = tf32_rna(v[1] - hi.y); lo.z = tf32_rna(v[2] - hi.z); lo.w = tf32_rna(v[3] - hi.w);
+            a_store4(bhi, k4, hi);
+            a_store4(blo, k4, lo);
+        };
+        const int NH = ((NPAD >> 1) + 7) & ~7;
+        const int c_lo = half ? NH : 0, c_hi = half ? NPAD : NH;
+        const float jit = a.jitter;
+        const unsigned long long seed = a.sa->seed;
+        const int noff = a.sa->n_offset;
+        const float var0 = P.var[0];
+
+        // ---- R0: x tile, mubar / vbar (this half: d = half, half+2, ...)
+        float x[DINP], il[DINP];
+#pragma unroll
+        for (int q = 0; q < DINP; ++q) {
+            x[q] = (valid && q < Din) ? a.Xin[(size_t)row * Din + q] : 0.f;
+            il[q] = q < Din ? 1.0f / P.ls[P.ard ? q : 0] : 0.f;
+            if (half == 0 && q < Din) xs_s[t * Din + q] = x[q];
+        }
+        for (int d = half; d < D; d += 2) {
+            float m = 0.f, v = 0.f;
+            if (valid) {
+                if (a.fbar) {
+                    float sd = sqrtf(fmaxf(a.Fvar[(size_t)row * D + d] + jit, 1e-30f));
+                    if (a.S_rep == 1) {
+                        int ss = row / a.N, n = row % a.N;
+                        float fb = a.fbar[(size_t)row * D + d];
+                        float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, ss, n + noff, d);
+                        m = fb; v = fb * z / (2.f * sd);
+                    } else {
+                        float sz = 0.f;
+                        for (int ss = 0; ss < a.S_rep; ++ss) {
+                            size_t o = ((size_t)ss * a.N + row) * D + d;
+                            float fb = a.fbar[o];
+                            float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, ss, row + noff, d);
+                            m += fb; sz = fmaf(fb, z, sz);
+                        }
+                        v = sz / (2.f * sd);
+                    }
+                    a.mubar[(size_t)row * D + d] = m;
+                    a.vbar[(size_t)row * D + d] = v;
+                } else {
+                    m = a.mubar[(size_t)row * D + d];
+                    v = a.vbar[(size_t)row * D + d];
+                }
+            }
+            mv_s[t * 2 * D + d] = m;
+            mv_s[t * 2 * D + D + d] = v;
+        }
+        // ---- R1: u (this half's columns) -> A_u as the G2 operand
+        for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+                if (c0 + 4 <= M && (M & 3) == 0) {
+                    float4 uu = *reinterpret_cast<const float4*>(a.U + (size_t)row * M + c0);
+                    v[0] = uu.x; v[1] = uu.y; v[2] = uu.z; v[3] = uu.w;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (c0 + u < M) v[u] = a.U[(size_t)row * M + c0 + u];
+                }
+            }
+            store_hi(A_u, c0, v);
+        }
+        if (half) {          // zero the K padding beyond NPAD (columns NPAD .. 32 nkb) once
+            const float z4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c0 = NPAD; c0 < nkb * 32; c0 += 4) { store_hi(A_u, c0, z4); store_hi(A_c, c0, z4); }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_au);
+        named_bar_sync(1, TC_ROWTHREADS);          // mv_s / xs_s visible
+        float mub[DOUTP], vb[DOUTP], vs = 0.f;
+#pragma unroll
+        for (int d = 0; d < DOUTP; ++d) {
+            mub[d] = d < D ? mv_s[t * 2 * D + d] : 0.f;
+            vb[d] = d < D ? mv_s[t * 2 * D + D + d] : 0.f;
+            vs += vb[d];
+        }
+        // ---- R2 (deferred, interleaved below): r2_i for this half's inducing points -> TMEM scratch columns 384+
+        auto gram_chunk = [&](int c0) {
+            float r2[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = min(c0 + u, M - 1);
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < DINP; ++q) {
+                    if (q < Din) {
+                        float dd = (x[q] - Zs[i * Din + q]) * il[q];
+                        s = fmaf(dd, dd, s);
+                    }
+                }
+                r2[u] = s;
+            }
+            __syncwarp();
+            tmem_st8(lane_addr + 384 + c0, r2);
+        };
+        const int nch = (c_hi - c_lo) >> 3;
+        // ---- R3: d loop -- cbar_d = 2 vbar_d c_d -> A_c
+        for (int d = 0; d < D; ++d) {
+            for (int j = d; j < nch; j += D) gram_chunk(c_lo + 8 * j);
+            mbar_wait(bar_acc2f + 8 * (d & 1), (d >> 1) & 1);
+            if (d > 0) mbar_wait(bar_cfree, (d - 1) & 1);
+            tc_fence_after();
+            float sc = 0.f;
+#pragma unroll
+            for (int dd = 0; dd < DOUTP; ++dd) if (dd == d) sc = 2.f * vb[dd];
+            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+                float v[8];
+                __syncwarp();
+                tmem_ld8(lane_addr + 128 * (d & 1) + c0, v);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] *= sc;
+                store_hi(A_c, c0, v);
+                store_hi(A_c, c0 + 4, v + 4);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(bar_cready);
+        }
+        // ---- R4: ubar = Ubar + sum_d mubar_d m_d - (vs k | 2 vs u)  -> operands of the solve
+        mbar_wait(bar_ubar, 0);
+        tc_fence_after();
+        for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+            float ub[8], r2[8];
+            __syncwarp();
+            tmem_ld8(lane_addr + 256 + c0, ub);
+            __syncwarp();
+            tmem_ld8(lane_addr + 384 + c0, r2);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = c0 + u;
+                float acc = 0.f;
+                if (i < M) {
+                    acc = ub[u];
+#pragma unroll
+                    for (int d = 0; d < DOUTP; ++d)
+                        if (d < D) acc = fmaf(mub[d], qmu_s[i * D + d], acc);
+                    if (P.white) {
+                        float ui = valid ? a.U[(size_t)row * M + i] : 0.f;
+                        acc -= 2.f * vs * ui;
+                    } else {
+                        float k, kp;
+                        kern_eval_fast(P.kern, r2[u], var0, k, kp);
+                        acc -= vs * k;
+                    }
+                }
+                ub[u] = acc;
+            }
+            store_hi_lo(A_c, A_u, c0, ub);
+            store_hi_lo(A_c, A_u, c0 + 4, ub + 4);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        if (!P.white) {
+            mbar_arrive(bar_s6);
+            // ---- R5: t = Linv ubar -> operands of the second triangular product
+            mbar_wait(bar_acc6, 0);
+            tc_fence_after();
+            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+                float v[8];
+                __syncwarp();
+                tmem_ld8(lane_addr + c0, v);
+                store_hi_lo(A_c, A_u, c0, v);
+                store_hi_lo(A_c, A_u, c0 + 4, v + 4);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+        }
+        mbar_arrive(bar_s7);
+        // ---- R6: w -> W (global), kbar, g = 2 kbar dk/dr2 -> g_s ; s2 partial
+        mbar_wait(bar_acc7, 0);
+        tc_fence_after();
+        float s2 = 0.f;
+        const float inv_var = 1.0f / var0;
+        for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+            float w[8], r2[8];
+            __syncwarp();
+            tmem_ld8(lane_addr + 128 + c0, w);
+            __syncwarp();
+            tmem_ld8(lane_addr + 384 + c0, r2);
+            if (valid) {
+                if (c0 + 8 <= M && (M & 3) == 0) {
+                    float4* dst = reinterpret_cast<float4*>(a.W + (size_t)row * M + c0);
+                    dst[0] = make_float4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (c0 + u < M) a.W[(size_t)row * M + c0 + u] = w[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = c0 + u;
+                if (i < M) {
+                    float kb_ = w[u];
+                    if (!P.white) {
+                        float ui = valid ? a.U[(size_t)row * M + i] : 0.f;
+                        kb_ -= vs * ui;
+                    }
+                    float k, kp;
+                    kern_eval_fast(P.kern, r2[u], var0, k, kp);
+                    s2 = fmaf(kb_ * k, inv_var, s2);
+                    g_s[t * MP + i] = 2.f * kb_ * kp;
+                }
+            }
+        }
+        if (half == 0)
+#pragma unroll
+            for (int d = 0; d < DOUTP; ++d) s2 += vb[d];
+        s2 = warp_sum(s2);
+        if (lane == 0) red_s[warp] = s2;
+        if (threadIdx.x < 32) red_s[32 + threadIdx.x] = 0.f;     // lengthscale accumulators
+        named_bar_sync(1, TC_ROWTHREADS);
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+            for (int w8 = 0; w8 < 8; ++w8) tot += red_s[w8];
+            atomicAdd(P.gvar, tot);
+        }
+        // ---- R7a: xbar (this half: q = half, half+2, ...)
+        if (a.xbar && valid) {
+            float accq[DINP];
+#pragma unroll
+            for (int q = 0; q < DINP; ++q) accq[q] = 0.f;
+            for (int i = 0; i < M; ++i) {
+                const float g = g_s[t * MP + i];
+#pragma unroll
+                for (int q = 0; q < DINP; ++q)
+                    if (q < Din && (q & 1) == half) accq[q] = fmaf(g, x[q] - Zs[i * Din + q], accq[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < DINP; ++q) {
+                if (q < Din && (q & 1) == half) {
+                    float s = accq[q] * il[q] * il[q];
+                    if (P.mean == DSDGP_MEAN_IDENTITY) {
+#pragma unroll
+                        for (int d = 0; d < DOUTP; ++d) if (d == q) s += mub[d];
+                    } else if (P.mean == DSDGP_MEAN_LINEAR) {
+#pragma unroll
+                        for (int d = 0; d < DOUTP; ++d) if (d < D) s = fmaf(mub[d], __ldg(&P.meanW[q * D + d]), s);
+                    }
+                    a.xbar[(size_t)row * Din + q] = s;
+                }
+            }
+        }
+        // ---- R7b: Z / lengthscale partials: one (i, q) pair per thread at a time, walking the 128 rows
+        for (int p = threadIdx.x; p < M * Din; p += TC_ROWTHREADS) {
+            const int q = p % Din, i = p / Din;
+            const float z = Zs[p];
+            float sa = 0.f, sb = 0.f;
+            for (int r = 0; r < TC_ROWS; ++r) {
+                float dd = xs_s[r * Din + q] - z, g = g_s[r * MP + i];
+                sa = fmaf(g, dd, sa); sb = fmaf(g * dd, dd, sb);
+            }
+            const float ilq = 1.0f / P.ls[P.ard ? q : 0];
+            atomicAdd(&P.gZ[p], -sa * ilq * ilq);
+            atomicAdd(&red_s[32 + (P.ard ? q : 0)], -sb * ilq * ilq * ilq);
+        }
+        named_bar_sync(1, TC_ROWTHREADS);
+        if (threadIdx.x < (P.ard ? Din : 1)) atomicAdd(&P.gls[threadIdx.x], red_s[32 + threadIdx.x]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+#define TC_BWD_INSTANCES(X) X(8, 1) X(8, 8) X(16, 1) X(16, 8)
+
+bool tc_bwd_supported(const LayerDev& P) {
+    if (!(P.M <= 128 && P.M >= 8 && P.Din <= 16 && P.Dout <= 8 && P.wpack_fwd != nullptr)) return false;
+    if (P.ard && P.Din > 32) return false;
+    return bwd_smem_plan(P.M, P.Din, P.Dout).total + 1024 <= 227 * 1024;
+}
+
+cudaError_t layer_tc_bwd_init() {
+    cudaError_t e;
+#define X(a_, b_) if ((e = cudaFuncSetAttribute(k_layer_bwd_tc<a_, b_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))) return e;
+    TC_BWD_INSTANCES(X)
+#undef X
+    return cudaSuccess;
+}
+
+void launch_bwd_rows_tc(const LayerDev& P, const BwdArgs& a, cudaStream_t st, long long* nl) {
+    int grid = (a.R + TC_ROWS - 1) / TC_ROWS;
+    size_t sm = bwd_smem_plan(P.M, P.Din, P.Dout).total + 1024;
+    int dinp = P.Din <= 8 ? 8 : 16, doutp = P.Dout <= 1 ? 1 : 8;
+#define X(a_, b_) if (dinp == a_ && doutp == b_) k_layer_bwd_tc<a_, b_><<<grid, TC_THREADS, sm, st>>>(P, a);
+    TC_BWD_INSTANCES(X)
+#undef X
+    *nl += 1;
+}
