@@ -189,6 +189,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     CK(layer_kernels_init());
     CK(layer_tc_init());
     CK(layer_tc_bwd_init());
+    CK(rowred_tc_init());
     CK(small_matrix_init());
 
     const int L = desc->L;
@@ -447,7 +448,8 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             else launch_bwd_rows(c->ls.l[l], b, c->num_sms, st, nl);
             PROF_END(6 + 3 * l);
             PROF_BEGIN(7 + 3 * l);
-            launch_bwd_rowred(c->ls.l[l], b, c->num_sms, st, nl);
+            if (c->path == 1 && tc_rowred_supported(c->ls.l[l])) launch_bwd_rowred_tc(c->ls.l[l], b, c->num_sms, st, nl);
+            else launch_bwd_rowred(c->ls.l[l], b, c->num_sms, st, nl);
             PROF_END(7 + 3 * l);
         }
         PROF_BEGIN(2);

@@ -186,6 +186,9 @@ void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long lo
 cudaError_t layer_tc_bwd_init();
 bool tc_bwd_supported(const LayerDev& P);
 void launch_bwd_rows_tc(const LayerDev& P, const BwdArgs& a, cudaStream_t st, long long* nlaunch);
+cudaError_t rowred_tc_init();
+bool tc_rowred_supported(const LayerDev& P);
+void launch_bwd_rowred_tc(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
 cudaError_t small_matrix_init();
 void launch_adam(float* params, float* free_, float* m, float* v, const float* grads, const unsigned char* kinds,
                  const int* tril_m, size_t n, const StepArgs* sa, cudaStream_t st, long long* nlaunch);

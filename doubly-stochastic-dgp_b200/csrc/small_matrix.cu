@@ -8,7 +8,7 @@
 // prepA: one CTA per layer.  K = k(Z,Z) + jitter I ; Lu = chol(K) ; Linv = Lu^-1 (fused elimination).
 // Working matrices live in shared memory when they fit, else in the global output buffers.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) k_prepA(LayerSet ls, double jitter, Accum* acc, int use_smem) {
+__global__ void __launch_bounds__(1024) k_prepA(LayerSet ls, double jitter, Accum* acc, int use_smem) {
     const LayerDev& P = ls.l[blockIdx.x];
     const int M = P.M, Din = P.Din, nt = blockDim.x, tid = threadIdx.x;
     extern __shared__ double smd[];
@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(512) k_prepA(LayerSet ls, double jitter, Accum
 
     __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
+    const int tx = tid & 31, ty = tid >> 5, nwarp = nt >> 5;
     for (int j = 0; j < M; ++j) {
         // phase A: scale column j of A (below the diagonal) and row j of X by 1/sqrt(A[j][j])
         double piv = A[j * M + j];
@@ -46,15 +47,11 @@ __global__ void __launch_bounds__(512) k_prepA(LayerSet ls, double jitter, Accum
         }
         for (int c = tid; c <= j; c += nt) X[j * M + c] *= id;
         __syncthreads();
-        // phase B: trailing update of A and elimination step on X
-        const int n = M - j - 1;
-        for (int idx = tid; idx < n * n; idx += nt) {
-            int i = j + 1 + idx / n, k = j + 1 + idx % n;
-            if (k <= i) A[i * M + k] -= A[i * M + j] * A[k * M + j];
-        }
-        for (int idx = tid; idx < n * (j + 1); idx += nt) {
-            int i = j + 1 + idx / (j + 1), c = idx % (j + 1);
-            X[i * M + c] -= A[i * M + j] * X[j * M + c];
+        // phase B: trailing update of A (lower triangle) and elimination step on X; one warp per row, lanes over columns
+        for (int i = j + 1 + ty; i < M; i += nwarp) {
+            const double lij = A[i * M + j];
+            for (int k = j + 1 + tx; k <= i; k += 32) A[i * M + k] -= lij * A[k * M + j];
+            for (int c = tx; c <= j; c += 32) X[i * M + c] -= lij * X[j * M + c];
         }
         __syncthreads();
     }
@@ -108,7 +105,13 @@ __global__ void k_zero_scal(LayerSet ls) {
     if (threadIdx.x == 0) { ls.l[l].scal[1] = 0.0; ls.l[l].scal[4] = 0.0; }
 }
 
-// Kinv = Linv^T Linv ; Ssum = sum_d L_d L_d^T + q_mu q_mu^T      (non-white layers only)
+// Kinv = Linv^T Linv (blockIdx.z == 0) ; Ssum += L_d L_d^T + q_mu_d q_mu_d^T for d = blockIdx.z - 1   (non-white layers)
+__global__ void k_kl0(LayerSet ls) {
+    const LayerDev& P = ls.l[blockIdx.y];
+    if (P.white) return;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < P.M * P.M) P.Ssum64[idx] = 0.0;
+}
 __global__ void k_kl1(LayerSet ls) {
     const LayerDev& P = ls.l[blockIdx.y];
     if (P.white) return;
@@ -117,16 +120,18 @@ __global__ void k_kl1(LayerSet ls) {
     if (idx >= M * M) return;
     int i = idx / M, j = idx % M;
     int lo = max(i, j), hi = min(i, j);
-    double s = 0.0;
-    for (int k = lo; k < M; ++k) s += P.Linv64[k * M + i] * P.Linv64[k * M + j];
-    P.Kinv64[idx] = s;
-    double t = 0.0;
-    for (int d = 0; d < D; ++d) {
+    if (blockIdx.z == 0) {
+        double s = 0.0;
+        for (int k = lo; k < M; ++k) s += P.Linv64[k * M + i] * P.Linv64[k * M + j];
+        P.Kinv64[idx] = s;
+    } else {
+        const int d = blockIdx.z - 1;
+        if (d >= D) return;
         const float* Ld = P.q_sqrt + (size_t)d * M * M;
+        double t = (double)P.q_mu[i * D + d] * (double)P.q_mu[j * D + d];
         for (int k = 0; k <= hi; ++k) t += (double)Ld[i * M + k] * (double)Ld[j * M + k];
-        t += (double)P.q_mu[i * D + d] * (double)P.q_mu[j * D + d];
+        atomicAdd(&P.Ssum64[idx], t);
     }
-    P.Ssum64[idx] = t;
 }
 
 // T1 = Kinv Ssum ; scal[2] += sum Kinv o Ssum
@@ -177,7 +182,7 @@ void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* 
     for (int l = 0; l < ls.L; ++l) { Mmax = max(Mmax, ls.l[l].M); Dmax = max(Dmax, ls.l[l].Dout); }
     size_t sm = 2 * (size_t)Mmax * Mmax * sizeof(double);
     int use_smem = sm <= 200 * 1024;
-    k_prepA<<<ls.L, 512, use_smem ? sm : 0, st>>>(ls, jitter, acc, use_smem);
+    k_prepA<<<ls.L, 1024, use_smem ? sm : 0, st>>>(ls, jitter, acc, use_smem);
     k_zero_scal<<<ls.L, 32, 0, st>>>(ls);
     int nb = (Mmax * Mmax + 255) / 256;
     k_qsqrtT<<<dim3(min(4 * nb, 1024), ls.L), 256, 0, st>>>(ls);
@@ -185,10 +190,11 @@ void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* 
     for (int l = 0; l < ls.L; ++l) any_nonwhite |= !ls.l[l].white;
     *nl += 3;
     if (any_nonwhite) {
-        k_kl1<<<dim3(nb, ls.L), 256, 0, st>>>(ls);
+        k_kl0<<<dim3(nb, ls.L), 256, 0, st>>>(ls);
+        k_kl1<<<dim3(nb, ls.L, Dmax + 1), 256, 0, st>>>(ls);
         k_kl2<<<dim3(nb, ls.L), 256, 0, st>>>(ls);
         k_kl3<<<dim3(nb, ls.L), 256, 0, st>>>(ls);
-        *nl += 3;
+        *nl += 4;
     }
     k_klval<<<1, 32, 0, st>>>(ls, acc);
     *nl += 1;
