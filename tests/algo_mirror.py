@@ -168,10 +168,14 @@ def gaussian_lik(mean, var, Y, lik_var, c):
     return c * np.sum(ve), mubar, vbar, lvbar
 
 
-def elbo_and_grad(layers, X, Y, lik_var, S, zs, num_data, jitter):
+def elbo_and_grad(layers, X, Y, lik_var, S, zs, num_data, jitter, n_global=None, klw=1.0):
     """Full step in the kernels' order.  X (N,D), zs[l] (S,N,Dout_l).  Layer 1 is evaluated on the N
-    distinct rows only (the reference's tile, dgp.py:63, makes its conditional S-fold redundant)."""
+    distinct rows only (the reference's tile, dgp.py:63, makes its conditional S-fold redundant).
+    n_global / klw: the row-sharded data-parallel protocol of csrc/api.cu -- this rank holds N of n_global minibatch
+    rows, the likelihood term is scaled by num_data / (n_global * S) and the KL term (value and gradient) is
+    weighted by klw = 1/world, so that a plain SUM all-reduce over ranks gives the full ELBO and gradient."""
     N = X.shape[0]
+    n_global = n_global or N
     L = len(layers)
     preps = [prepA(P, jitter) for P in layers]
     # ---------------- forward
@@ -190,10 +194,10 @@ def elbo_and_grad(layers, X, Y, lik_var, S, zs, num_data, jitter):
                 Xin = mean + zs[l].reshape(S * N, -1) * sd
     Xl, mean, var, u, sd = acts[-1]
     if L == 1:
-        c = num_data / N
+        c = num_data / n_global
         Yr = Y
     else:
-        c = num_data / (N * S)
+        c = num_data / (n_global * S)
         Yr = np.tile(Y, (S, 1))
     Lval, mubar, vbar, lvbar = gaussian_lik(mean, var, Yr, lik_var, c)
     # ---------------- backward
@@ -205,7 +209,7 @@ def elbo_and_grad(layers, X, Y, lik_var, S, zs, num_data, jitter):
         Xl, mean, var, u, sd = acts[l]
         xbar, w, Zb, lsb, s2b = layer_bwdA(P, Linv, Xl, u, mubar, vbar)
         Pd, G, qmub = layer_bwdB(u, w, mubar, vbar)
-        KL, gq_mu, gq_sqrt, Zb2, lsb2, s2b2 = layer_fin(P, K, Lu, Linv, Pd, G, qmub)
+        KL, gq_mu, gq_sqrt, Zb2, lsb2, s2b2 = layer_fin(P, K, Lu, Linv, Pd, G, qmub, klw=klw)
         KLs += KL
         lsg = lsb + lsb2
         grads[l] = dict(Z=Zb + Zb2, q_mu=gq_mu, q_sqrt=gq_sqrt,
@@ -221,4 +225,4 @@ def elbo_and_grad(layers, X, Y, lik_var, S, zs, num_data, jitter):
             else:
                 mubar = fbar
                 vbar = fbar * zs[l - 1].reshape(S * N, -1) / (2.0 * psd)
-    return Lval - KLs, grads, lvbar
+    return Lval - klw * KLs, grads, lvbar
