@@ -443,6 +443,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             b.z = (zmask >> l) & 1u ? c->zs[l] : nullptr;
             b.mubar = c->mubar; b.vbar = c->vbar; b.W = c->Wbuf;
             b.xbar = (l == 0) ? nullptr : c->xbar[l];
+            b.dbg = (c->dbg_layer == 100 + l) ? c->dbg_buf : nullptr;
             PROF_BEGIN(6 + 3 * l);
             if (c->path == 1 && tc_bwd_supported(c->ls.l[l])) launch_bwd_rows_tc(c->ls.l[l], b, st, nl);
             else launch_bwd_rows(c->ls.l[l], b, c->num_sms, st, nl);

@@ -67,7 +67,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__device__ __forceinline__ float dsdgp_normal(unsigned long long seed, int layer, int s, int n_global, int d) {
+// (kept out of line: it is called from several places in the big row kernels and I-cache footprint matters there)
+static __device__ __noinline__ float dsdgp_normal(unsigned long long seed, int layer, int s, int n_global, int d) {
     uint32_t r[4];
     philox4x32_10((uint32_t)n_global, (uint32_t)s, (uint32_t)layer, (uint32_t)(d >> 2),
                   (uint32_t)seed, (uint32_t)(seed >> 32), r);
@@ -162,6 +163,7 @@ struct BwdArgs {
     float* xbar;          // (R, Din) out or NULL (first layer)
     float jitter;
     const StepArgs* sa;
+    long long* dbg;       // optional clock64() stamps of CTA 0 (diagnostics), else NULL
 };
 
 void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nlaunch);

@@ -204,6 +204,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         const unsigned long long seed = a.sa->seed;
         const int noff = a.sa->n_offset;
         const float var0 = P.var[0];
+        const bool dbg = a.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+        int dbi = 0;
+#define BSTAMP() do { if (dbg) a.dbg[dbi++] = clock64(); } while (0)
+        BSTAMP();   // 0
 
         // ---- R0: x tile, mubar / vbar (this half: d = half, half+2, ...)
         float x[DINP], il[DINP];
@@ -213,7 +217,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             il[q] = q < Din ? 1.0f / P.ls[P.ard ? q : 0] : 0.f;
             if (half == 0 && q < Din) xs_s[t * Din + q] = x[q];
         }
-        for (int d = half; d < D; d += 2) {
+#pragma unroll
+        for (int dd = 0; dd < (DOUTP + 1) / 2; ++dd) {
+            const int d = 2 * dd + half;
+            if (d >= D) continue;
             float m = 0.f, v = 0.f;
             if (valid) {
                 if (a.fbar) {
@@ -243,19 +250,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             mv_s[t * 2 * D + d] = m;
             mv_s[t * 2 * D + D + d] = v;
         }
-        // ---- R1: u (this half's columns) -> A_u as the G2 operand
-        for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (valid) {
-                if (c0 + 4 <= M && (M & 3) == 0) {
-                    float4 uu = *reinterpret_cast<const float4*>(a.U + (size_t)row * M + c0);
-                    v[0] = uu.x; v[1] = uu.y; v[2] = uu.z; v[3] = uu.w;
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (c0 + u < M) v[u] = a.U[(size_t)row * M + c0 + u];
+        // ---- R1: u (this half's columns) -> A_u as the G2 operand; loads are issued four chunks ahead of their use
+        const bool vec4 = (M & 3) == 0;
+        auto load_u4 = [&](int c0) -> float4 {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && c0 < c_hi) {
+                if (vec4 && c0 + 4 <= M) v = *reinterpret_cast<const float4*>(a.U + (size_t)row * M + c0);
+                else {
+                    if (c0 < M) v.x = a.U[(size_t)row * M + c0];
+                    if (c0 + 1 < M) v.y = a.U[(size_t)row * M + c0 + 1];
+                    if (c0 + 2 < M) v.z = a.U[(size_t)row * M + c0 + 2];
+                    if (c0 + 3 < M) v.w = a.U[(size_t)row * M + c0 + 3];
                 }
             }
-            store_hi(A_u, c0, v);
+            return v;
+        };
+        {
+            float4 q0 = load_u4(c_lo), q1 = load_u4(c_lo + 4), q2 = load_u4(c_lo + 8), q3 = load_u4(c_lo + 12);
+#pragma unroll 1
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+                float4 n0 = load_u4(c0 + 16), n1 = load_u4(c0 + 20), n2 = load_u4(c0 + 24), n3 = load_u4(c0 + 28);
+                const float4 cur[4] = {q0, q1, q2, q3};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (c0 + 4 * e < c_hi) {
+                        const float v[4] = {cur[e].x, cur[e].y, cur[e].z, cur[e].w};
+                        store_hi(A_u, c0 + 4 * e, v);
+                    }
+                }
+                q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+            }
         }
         if (half) {          // zero the K padding beyond NPAD (columns NPAD .. 32 nkb) once
             const float z4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -263,6 +287,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         }
         fence_proxy_async();
         mbar_arrive(bar_au);
+        BSTAMP();   // 1: R0+R1 done
         named_bar_sync(1, TC_ROWTHREADS);          // mv_s / xs_s visible
         float mub[DOUTP], vb[DOUTP], vs = 0.f;
 #pragma unroll
@@ -294,8 +319,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         // ---- R3: d loop -- cbar_d = 2 vbar_d c_d -> A_c
         for (int d = 0; d < D; ++d) {
             for (int j = d; j < nch; j += D) gram_chunk(c_lo + 8 * j);
+            BSTAMP();   // 2+3d: deferred gram done
             mbar_wait(bar_acc2f + 8 * (d & 1), (d >> 1) & 1);
+            BSTAMP();   // 3+3d: G2[d] ready
             if (d > 0) mbar_wait(bar_cfree, (d - 1) & 1);
+            BSTAMP();   // 4+3d: A_c free
             tc_fence_after();
             float sc = 0.f;
 #pragma unroll
@@ -314,44 +342,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             mbar_arrive(bar_cready);
         }
         // ---- R4: ubar = Ubar + sum_d mubar_d m_d - (vs k | 2 vs u)  -> operands of the solve
+        BSTAMP();   // 26: d loop done
         mbar_wait(bar_ubar, 0);
         tc_fence_after();
-        for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
-            float ub[8], r2[8];
-            __syncwarp();
-            tmem_ld8(lane_addr + 256 + c0, ub);
-            __syncwarp();
-            tmem_ld8(lane_addr + 384 + c0, r2);
+        BSTAMP();   // 27: Ubar ready
+        {
+            float4 ua = P.white ? load_u4(c_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ub4 = P.white ? load_u4(c_lo + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+                float4 na = ua, nb4 = ub4;
+                if (P.white) { na = load_u4(c0 + 8); nb4 = load_u4(c0 + 12); }
+                float ub[8], r2[8];
+                __syncwarp();
+                tmem_ld8(lane_addr + 256 + c0, ub);
+                __syncwarp();
+                tmem_ld8(lane_addr + 384 + c0, r2);
+                const float uloc[8] = {ua.x, ua.y, ua.z, ua.w, ub4.x, ub4.y, ub4.z, ub4.w};
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = c0 + u;
-                float acc = 0.f;
-                if (i < M) {
-                    acc = ub[u];
+                for (int u = 0; u < 8; ++u) {
+                    const int i = c0 + u;
+                    float acc = 0.f;
+                    if (i < M) {
+                        acc = ub[u];
+                        bool done = false;
+                        if constexpr (DOUTP % 4 == 0) {
+                            if (D == DOUTP) {
+                                const float4* qr = reinterpret_cast<const float4*>(qmu_s + i * DOUTP);
 #pragma unroll
-                    for (int d = 0; d < DOUTP; ++d)
-                        if (d < D) acc = fmaf(mub[d], qmu_s[i * D + d], acc);
-                    if (P.white) {
-                        float ui = valid ? a.U[(size_t)row * M + i] : 0.f;
-                        acc -= 2.f * vs * ui;
-                    } else {
-                        float k, kp;
-                        kern_eval_fast(P.kern, r2[u], var0, k, kp);
-                        acc -= vs * k;
+                                for (int d4 = 0; d4 < DOUTP / 4; ++d4) {
+                                    float4 qv = qr[d4];
+                                    acc = fmaf(mub[4 * d4], qv.x, acc); acc = fmaf(mub[4 * d4 + 1], qv.y, acc);
+                                    acc = fmaf(mub[4 * d4 + 2], qv.z, acc); acc = fmaf(mub[4 * d4 + 3], qv.w, acc);
+                                }
+                                done = true;
+                            }
+                        }
+                        if (!done) {
+#pragma unroll
+                            for (int d = 0; d < DOUTP; ++d) if (d < D) acc = fmaf(mub[d], qmu_s[i * D + d], acc);
+                        }
+                        if (P.white) acc -= 2.f * vs * uloc[u];
+                        else {
+                            float k, kp;
+                            kern_eval_fast(P.kern, r2[u], var0, k, kp);
+                            acc -= vs * k;
+                        }
                     }
+                    ub[u] = acc;
                 }
-                ub[u] = acc;
+                store_hi_lo(A_c, A_u, c0, ub);
+                store_hi_lo(A_c, A_u, c0 + 4, ub + 4);
+                ua = na; ub4 = nb4;
             }
-            store_hi_lo(A_c, A_u, c0, ub);
-            store_hi_lo(A_c, A_u, c0 + 4, ub + 4);
         }
         tc_fence_before();
         fence_proxy_async();
         if (!P.white) {
             mbar_arrive(bar_s6);
+            BSTAMP();   // 28: R4 done
             // ---- R5: t = Linv ubar -> operands of the second triangular product
             mbar_wait(bar_acc6, 0);
             tc_fence_after();
+            BSTAMP();   // 29: G6 done
             for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
                 float v[8];
                 __syncwarp();
@@ -363,43 +416,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             fence_proxy_async();
         }
         mbar_arrive(bar_s7);
+        BSTAMP();   // 30: R5 done
         // ---- R6: w -> W (global), kbar, g = 2 kbar dk/dr2 -> g_s ; s2 partial
         mbar_wait(bar_acc7, 0);
         tc_fence_after();
+        BSTAMP();   // 31: G7 done
         float s2 = 0.f;
         const float inv_var = 1.0f / var0;
-        for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
-            float w[8], r2[8];
-            __syncwarp();
-            tmem_ld8(lane_addr + 128 + c0, w);
-            __syncwarp();
-            tmem_ld8(lane_addr + 384 + c0, r2);
-            if (valid) {
-                if (c0 + 8 <= M && (M & 3) == 0) {
-                    float4* dst = reinterpret_cast<float4*>(a.W + (size_t)row * M + c0);
-                    dst[0] = make_float4(w[0], w[1], w[2], w[3]);
-                    dst[1] = make_float4(w[4], w[5], w[6], w[7]);
-                } else {
+        {
+            float4 ua = !P.white ? load_u4(c_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ub4 = !P.white ? load_u4(c_lo + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+                float4 na = ua, nb4 = ub4;
+                if (!P.white) { na = load_u4(c0 + 8); nb4 = load_u4(c0 + 12); }
+                float w[8], r2[8];
+                __syncwarp();
+                tmem_ld8(lane_addr + 128 + c0, w);
+                __syncwarp();
+                tmem_ld8(lane_addr + 384 + c0, r2);
+                if (valid) {
+                    if (c0 + 8 <= M && vec4) {
+                        float4* dst = reinterpret_cast<float4*>(a.W + (size_t)row * M + c0);
+                        dst[0] = make_float4(w[0], w[1], w[2], w[3]);
+                        dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+                    } else {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) if (c0 + u < M) a.W[(size_t)row * M + c0 + u] = w[u];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = c0 + u;
-                if (i < M) {
-                    float kb_ = w[u];
-                    if (!P.white) {
-                        float ui = valid ? a.U[(size_t)row * M + i] : 0.f;
-                        kb_ -= vs * ui;
+                        for (int u = 0; u < 8; ++u) if (c0 + u < M) a.W[(size_t)row * M + c0 + u] = w[u];
                     }
-                    float k, kp;
-                    kern_eval_fast(P.kern, r2[u], var0, k, kp);
-                    s2 = fmaf(kb_ * k, inv_var, s2);
-                    g_s[t * MP + i] = 2.f * kb_ * kp;
                 }
+                const float uloc[8] = {ua.x, ua.y, ua.z, ua.w, ub4.x, ub4.y, ub4.z, ub4.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = c0 + u;
+                    if (i < M) {
+                        float kb_ = w[u];
+                        if (!P.white) kb_ -= vs * uloc[u];
+                        float k, kp;
+                        kern_eval_fast(P.kern, r2[u], var0, k, kp);
+                        s2 = fmaf(kb_ * k, inv_var, s2);
+                        g_s[t * MP + i] = 2.f * kb_ * kp;
+                    }
+                }
+                ua = na; ub4 = nb4;
             }
         }
+        BSTAMP();   // 32: R6 done
         if (half == 0)
 #pragma unroll
             for (int d = 0; d < DOUTP; ++d) s2 += vb[d];
@@ -417,11 +479,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             float accq[DINP];
 #pragma unroll
             for (int q = 0; q < DINP; ++q) accq[q] = 0.f;
-            for (int i = 0; i < M; ++i) {
-                const float g = g_s[t * MP + i];
+            if (Din == DINP) {
+#pragma unroll 4
+                for (int i = 0; i < M; ++i) {
+                    const float g = g_s[t * MP + i];
+                    const float4* zr = reinterpret_cast<const float4*>(Zs + i * DINP);
 #pragma unroll
-                for (int q = 0; q < DINP; ++q)
-                    if (q < Din && (q & 1) == half) accq[q] = fmaf(g, x[q] - Zs[i * Din + q], accq[q]);
+                    for (int q4 = 0; q4 < DINP / 4; ++q4) {
+                        const float4 zv = zr[q4];
+                        const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int q = 4 * q4 + e;
+                            if ((q & 1) == half) accq[q] = fmaf(g, x[q] - zz[e], accq[q]);
+                        }
+                    }
+                }
+            } else {
+                for (int i = 0; i < M; ++i) {
+                    const float g = g_s[t * MP + i];
+#pragma unroll
+                    for (int q = 0; q < DINP; ++q)
+                        if (q < Din && (q & 1) == half) accq[q] = fmaf(g, x[q] - Zs[i * Din + q], accq[q]);
+                }
             }
 #pragma unroll
             for (int q = 0; q < DINP; ++q) {
@@ -438,19 +518,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                 }
             }
         }
+        BSTAMP();   // 33: R7a done
         // ---- R7b: Z / lengthscale partials: one (i, q) pair per thread at a time, walking the 128 rows
-        for (int p = threadIdx.x; p < M * Din; p += TC_ROWTHREADS) {
-            const int q = p % Din, i = p / Din;
-            const float z = Zs[p];
-            float sa = 0.f, sb = 0.f;
-            for (int r = 0; r < TC_ROWS; ++r) {
-                float dd = xs_s[r * Din + q] - z, g = g_s[r * MP + i];
-                sa = fmaf(g, dd, sa); sb = fmaf(g * dd, dd, sb);
+        {
+            const int i = threadIdx.x & 127, rh = threadIdx.x >> 7;      // inducing point, row half
+            float sa[DINP], sb[DINP];
+            if (i < M) {
+                float zi[DINP];
+#pragma unroll
+                for (int q = 0; q < DINP; ++q) { sa[q] = 0.f; sb[q] = 0.f; zi[q] = q < Din ? Zs[i * Din + q] : 0.f; }
+                for (int r = rh * 64; r < rh * 64 + 64; ++r) {
+                    const float g = g_s[r * MP + i];
+#pragma unroll
+                    for (int q = 0; q < DINP; ++q) {
+                        if (q < Din) {
+                            const float dd = xs_s[r * Din + q] - zi[q];
+                            sa[q] = fmaf(g, dd, sa[q]);
+                            sb[q] = fmaf(g * dd, dd, sb[q]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < DINP; ++q) {
+                    if (q < Din) {
+                        const float ilq = il[q];
+                        atomicAdd(&P.gZ[i * Din + q], -sa[q] * ilq * ilq);
+                        sb[q] = -sb[q] * ilq * ilq * ilq;
+                    } else sb[q] = 0.f;
+                }
+                if (!P.ard) {
+#pragma unroll
+                    for (int q = 1; q < DINP; ++q) sb[0] += sb[q];
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < DINP; ++q) sb[q] = 0.f;
             }
-            const float ilq = 1.0f / P.ls[P.ard ? q : 0];
-            atomicAdd(&P.gZ[p], -sa * ilq * ilq);
-            atomicAdd(&red_s[32 + (P.ard ? q : 0)], -sb * ilq * ilq * ilq);
+            // one shared atomic per warp (per input dimension when ARD)
+#pragma unroll
+            for (int q = 0; q < DINP; ++q) {
+                if (q < (P.ard ? Din : 1)) {
+                    float tsum = warp_sum(sb[q]);
+                    if (lane == 0) atomicAdd(&red_s[32 + q], tsum);
+                }
+            }
         }
+        BSTAMP();   // 34: R7b done
         named_bar_sync(1, TC_ROWTHREADS);
         if (threadIdx.x < (P.ard ? Din : 1)) atomicAdd(&P.gls[threadIdx.x], red_s[32 + threadIdx.x]);
     }
