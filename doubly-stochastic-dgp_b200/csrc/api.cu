@@ -87,7 +87,12 @@ struct dsdgp_ctx {
     float* F[DSDGP_MAX_LAYERS];
     float* zs[DSDGP_MAX_LAYERS];
     float* xbar[DSDGP_MAX_LAYERS];
-    float *mubar, *vbar, *Wbuf;
+    float* mubar[DSDGP_MAX_LAYERS];
+    float* vbar[DSDGP_MAX_LAYERS];
+    float* Wbuf[DSDGP_MAX_LAYERS];
+    cudaStream_t stream2;                       // side branch of the step DAG (KL prep, row reductions)
+    cudaEvent_t ev_dag[2 * DSDGP_MAX_LAYERS + 4];
+    bool overlap;
     // step scalars
     StepArgs* sa_dev; StepArgs* sa_host;   // pinned ring of SA_RING slots (steps may be in flight)
     cudaEvent_t sa_ev[16]; bool sa_used[16]; int sa_slot;
@@ -252,7 +257,10 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     for (int l = 0; l < L; ++l) { Dmax = max(Dmax, (size_t)desc->layers[l].D_out); Mmax = max(Mmax, (size_t)desc->layers[l].M); }
     CK(dmalloc(&c->Xd, (size_t)desc->N_max * desc->layers[0].D_in));
     CK(dmalloc(&c->Yd, (size_t)desc->N_max * desc->D_y));
-    CK(dmalloc(&c->mubar, Rmax * Dmax)); CK(dmalloc(&c->vbar, Rmax * Dmax)); CK(dmalloc(&c->Wbuf, Rmax * Mmax));
+    CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_dag[i], cudaEventDisableTiming));
+    c->overlap = true;
+    (void)Dmax; (void)Mmax;
     {
         double* p64 = c->sm64; float* p32 = c->sm32; float* pa = c->accf;
         c->ls.L = L;
@@ -265,6 +273,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
             CK(dmalloc(&c->Fmean[l], Rl * d.D_out)); CK(dmalloc(&c->Fvar[l], Rl * d.D_out));
             CK(dmalloc(&c->F[l], Rmax * d.D_out)); CK(dmalloc(&c->zs[l], Rmax * d.D_out));
             CK(dmalloc(&c->xbar[l], Rl * d.D_in));
+            CK(dmalloc(&c->mubar[l], Rl * d.D_out)); CK(dmalloc(&c->vbar[l], Rl * d.D_out)); CK(dmalloc(&c->Wbuf[l], Rl * d.M));
             CK(dmalloc(&c->meanW[l], (size_t)d.D_in * d.D_out)); CK(dmalloc(&c->meanB[l], (size_t)d.D_out));
             LayerDev& P = c->ls.l[l];
             c->wpack[l] = nullptr;
@@ -303,17 +312,20 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-    float* fl[] = {c->params, c->grads, c->free_, c->adam_m, c->adam_v, c->sm32, c->accf, c->Xd, c->Yd, c->mubar, c->vbar, c->Wbuf};
+    float* fl[] = {c->params, c->grads, c->free_, c->adam_m, c->adam_v, c->sm32, c->accf, c->Xd, c->Yd};
     for (float* p : fl) cudaFree(p);
     cudaFree(c->kinds); cudaFree(c->sm64); cudaFree(c->sa_dev); cudaFree(c->acc); cudaFree(c->result_dev);
     for (int l = 0; l < c->desc.L; ++l) {
-        float* pl[] = {c->U[l], c->Fmean[l], c->Fvar[l], c->F[l], c->zs[l], c->xbar[l], c->meanW[l], c->meanB[l], c->wpack[l]};
+        float* pl[] = {c->U[l], c->Fmean[l], c->Fvar[l], c->F[l], c->zs[l], c->xbar[l], c->meanW[l], c->meanB[l], c->wpack[l],
+                       c->mubar[l], c->vbar[l], c->Wbuf[l]};
         for (float* p : pl) cudaFree(p);
     }
     cudaFreeHost(c->sa_host); cudaFreeHost(c->result_host);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
     for (int i = 0; i < 2 * (5 + 3 * DSDGP_MAX_LAYERS); ++i) cudaEventDestroy(c->prof_ev[i]);
     for (int i = 0; i < 16; ++i) cudaEventDestroy(c->sa_ev[i]);
+    cudaStreamDestroy(c->stream2);
+    for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 4; ++i) cudaEventDestroy(c->ev_dag[i]);
     cudaStreamDestroy(c->stream);
     delete c;
     return DSDGP_OK;
@@ -392,13 +404,14 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     if (prof) for (int i = 0; i < 5 + 3 * L; ++i) c->prof_used[i] = false;
     const float jit = (float)c->desc.jitter;
     const bool grad = mode >= MODE_GRAD;
+    const bool side = grad && c->overlap && !prof;      // two-branch DAG (captured into the graph as parallel branches)
     CK(cudaMemsetAsync(c->acc, 0, sizeof(Accum), st));
     if (grad) {
         CK(cudaMemsetAsync(c->accf, 0, c->accf_n * sizeof(float), st));
         CK(cudaMemsetAsync(c->grads, 0, (c->n_params + 2) * sizeof(float), st));
     }
     PROF_BEGIN(0);
-    launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, st, nl);
+    launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, st, side ? c->stream2 : st, c->ev_dag[0], nl);
     bool any_tc = false;
     for (int l = 0; l < L; ++l) any_tc |= c->path == 1 && tc_fwd_supported(c->ls.l[l]);
     if (any_tc) launch_pack_fwd(c->ls, st, nl);
@@ -426,10 +439,10 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     PROF_BEGIN(1);
     if (c->desc.likelihood == DSDGP_LIK_GAUSSIAN)
         launch_lik_gaussian(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.D_y, c->params + c->off_likvar,
-                            c->mubar, c->vbar, c->acc, c->sa_dev, grad, st, nl);
+                            c->mubar[L - 1], c->vbar[L - 1], c->acc, c->sa_dev, grad, st, nl);
     else
-        launch_lik_multiclass(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.num_classes, c->mubar, c->vbar,
-                              c->acc, c->sa_dev, grad, st, nl);
+        launch_lik_multiclass(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.num_classes, c->mubar[L - 1],
+                              c->vbar[L - 1], c->acc, c->sa_dev, grad, st, nl);
     PROF_END(1);
     if (grad) {
         for (int l = L - 1; l >= 0; --l) {
@@ -441,7 +454,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             b.U = c->U[l]; b.Fvar = c->Fvar[l];
             b.fbar = (l == L - 1) ? nullptr : c->xbar[l + 1];
             b.z = (zmask >> l) & 1u ? c->zs[l] : nullptr;
-            b.mubar = c->mubar; b.vbar = c->vbar; b.W = c->Wbuf;
+            b.mubar = c->mubar[l]; b.vbar = c->vbar[l]; b.W = c->Wbuf[l];
             b.xbar = (l == 0) ? nullptr : c->xbar[l];
             b.dbg = (c->dbg_layer == 100 + l) ? c->dbg_buf : nullptr;
             PROF_BEGIN(6 + 3 * l);
@@ -449,10 +462,15 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             else launch_bwd_rows(c->ls.l[l], b, c->num_sms, st, nl);
             PROF_END(6 + 3 * l);
             PROF_BEGIN(7 + 3 * l);
-            if (c->path == 1 && tc_rowred_supported(c->ls.l[l])) launch_bwd_rowred_tc(c->ls.l[l], b, c->num_sms, st, nl);
-            else launch_bwd_rowred(c->ls.l[l], b, c->num_sms, st, nl);
+            // the row reductions of layer l only feed the final gradient assembly: side branch of the DAG, so they
+            // overlap with the (latency-bound, second-wave-starved) row kernel of layer l-1
+            cudaStream_t sr = side ? c->stream2 : st;
+            if (side) { CK(cudaEventRecord(c->ev_dag[2 + l], st)); CK(cudaStreamWaitEvent(c->stream2, c->ev_dag[2 + l], 0)); }
+            if (c->path == 1 && tc_rowred_supported(c->ls.l[l])) launch_bwd_rowred_tc(c->ls.l[l], b, c->num_sms, sr, nl);
+            else launch_bwd_rowred(c->ls.l[l], b, c->num_sms, sr, nl);
             PROF_END(7 + 3 * l);
         }
+        if (side) { CK(cudaEventRecord(c->ev_dag[1], c->stream2)); CK(cudaStreamWaitEvent(st, c->ev_dag[1], 0)); }
         PROF_BEGIN(2);
         launch_fin(c->ls, c->acc, c->sa_dev, st, nl);
         PROF_END(2);
@@ -692,7 +710,7 @@ int dsdgp_kl(dsdgp_ctx* c, double* kl) {
     if (!c || !kl) return set_err(DSDGP_ERR_INVALID, "null argument");
     CK(cudaSetDevice(c->desc.device));
     CK(cudaMemsetAsync(c->acc, 0, sizeof(Accum), c->stream));
-    launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, c->stream, &c->nlaunch);
+    launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, c->stream, c->stream, c->ev_dag[0], &c->nlaunch);
     launch_result(c->acc, c->grads + c->n_params, 0, c->result_dev, c->stream, &c->nlaunch);
     int rc = fetch_result(c, nullptr);
     if (rc) return rc;
@@ -720,6 +738,11 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     std::string n(name);
     if (n == "graph") c->use_graph = value != 0;
     else if (n == "profile") c->profile = value != 0;
+    else if (n == "overlap") {
+        c->overlap = value != 0;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    }
     else if (n == "dbg_layer") {
         c->dbg_layer = (int)value;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);

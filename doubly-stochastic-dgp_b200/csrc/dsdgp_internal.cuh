@@ -166,7 +166,8 @@ struct BwdArgs {
     long long* dbg;       // optional clock64() stamps of CTA 0 (diagnostics), else NULL
 };
 
-void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
+void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* sa, cudaStream_t st, cudaStream_t st_kl,
+                 cudaEvent_t ev_fork, long long* nlaunch);
 void launch_fwd(const LayerDev& P, const FwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
 void launch_bwd_rows(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
 void launch_bwd_rowred(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);

@@ -177,12 +177,17 @@ __global__ void k_klval(LayerSet ls, Accum* acc) {
     atomicAdd(&acc->kl, KL);
 }
 
-void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nl) {
+// prepA on `st` (critical path: everything needs Lu / Linv); the KL-term preparation on `st_kl` (only the final gradient
+// assembly and the ELBO scalar need it), which may be a side branch of the step DAG.
+void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* sa, cudaStream_t st, cudaStream_t st_kl,
+                 cudaEvent_t ev_fork, long long* nl) {
     int Mmax = 0, Dmax = 0;
     for (int l = 0; l < ls.L; ++l) { Mmax = max(Mmax, ls.l[l].M); Dmax = max(Dmax, ls.l[l].Dout); }
     size_t sm = 2 * (size_t)Mmax * Mmax * sizeof(double);
     int use_smem = sm <= 200 * 1024;
     k_prepA<<<ls.L, 1024, use_smem ? sm : 0, st>>>(ls, jitter, acc, use_smem);
+    if (st_kl != st) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(st_kl, ev_fork, 0); }
+    st = st_kl;
     k_zero_scal<<<ls.L, 32, 0, st>>>(ls);
     int nb = (Mmax * Mmax + 255) / 256;
     k_qsqrtT<<<dim3(min(4 * nb, 1024), ls.L), 256, 0, st>>>(ls);
