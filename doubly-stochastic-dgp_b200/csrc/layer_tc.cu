@@ -9,40 +9,47 @@
 // Reference arithmetic: layers.py:178-219; mirrored in tests/algo_mirror.py::layer_fwd.
 #include "dsdgp_internal.cuh"
 #include "tc_common.cuh"
+#include "tc_pack.cuh"
 
 #define TC_ROWS 128
-#define TC_NSTAGE 4
-#define TC_CHUNK_BYTES 16384
+#define TC_NSTAGE 2          // weight ring: two slots of one band block each
+#define TC_CHUNK_BYTES 16384 // one [128 rows] x [32 k] activation k-block
 #define TC_THREADS 320
 
 // ----------------------------------------------------------------------------------------------
-// weight packing: chunk stream consumed by k_layer_fwd_tc
-//   [G1: kb x {hi,lo}] [G1': kb x {hi,lo}] [G2: d x kb (hi)] [G5: d x kb (hi)]      (G1' unused by white forwards)
+// weight packing (layout: tc_pack.cuh).  One thread per stored element; hi = tf32(x), lo = tf32(x - hi).
 // ----------------------------------------------------------------------------------------------
 __global__ void k_pack_fwd(LayerSet ls) {
     const LayerDev& P = ls.l[blockIdx.y];
     if (!P.wpack_fwd) return;
-    const int M = P.M, D = P.Dout, nkb = (M + 31) / 32;
-    const int n1 = 2 * nkb, n1p = 2 * nkb, nchunks = n1 + n1p + 2 * D * nkb;
-    const size_t total = (size_t)nchunks * 4096;
+    const int M = P.M, D = P.Dout, nkb = tcp::nkb_of(M);
+    const uint32_t slot = tcp::slot_bytes(M);
+    const int nblk = tcp::num_blocks(D);
+    const int per_blk = nkb * 128 * 32;                 // (kb, n, kk) index space; rows outside a band are skipped
+    const size_t total = (size_t)nblk * per_blk;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        int c = (int)(e >> 12), w = (int)(e & 4095), n = w >> 5, kk = w & 31;
+        const int blk = (int)(e / per_blk), w = (int)(e % per_blk), kb = w >> 12, n = (w >> 5) & 127, kk = w & 31, k = kb * 32 + kk;
+        const int pat = (blk < 2 || blk >= 4 + D) ? tcp::PAT_LE : tcp::PAT_GE;
+        const int r0 = tcp::band_row0(pat, kb), nr = tcp::band_rows(pat, M, kb);
+        if (n < r0 || n >= r0 + nr) continue;
         float out = 0.f;
-        if (c < n1 + n1p) {
-            int cc = c < n1 ? c : c - n1, kb = cc >> 1, part = cc & 1, k = kb * 32 + kk;
-            if (n < M && k < M) {
-                double v = (c < n1) ? P.Linv64[(size_t)n * M + k] : P.Linv64[(size_t)k * M + n];
-                float hi = tc::tf32_rna((float)v);
+        if (n < M && k < M) {
+            if (blk < 4) {
+                const int part = blk & 1;
+                const double v = (blk < 2) ? P.Linv64[(size_t)n * M + k] : P.Linv64[(size_t)k * M + n];   // G1: Linv[n][k] ; G1': Linv[k][n]
+                const float hi = tc::tf32_rna((float)v);
                 out = part ? tc::tf32_rna((float)(v - (double)hi)) : hi;
+            } else if (blk < 4 + D) {
+                const int d = blk - 4;
+                if (n <= k) out = tc::tf32_rna(P.q_sqrt[((size_t)d * M + k) * M + n]);                     // G2: L_d[k][n]
+            } else {
+                const int d = blk - 4 - D;
+                if (k <= n) out = tc::tf32_rna(P.q_sqrt[((size_t)d * M + n) * M + k]);                     // G5: L_d[n][k]
             }
-        } else if (c < n1 + n1p + D * nkb) {
-            int cc = c - n1 - n1p, d = cc / nkb, kb = cc % nkb, k = kb * 32 + kk;
-            if (n < M && k < M && n <= k) out = tc::tf32_rna(P.q_sqrt[((size_t)d * M + k) * M + n]);   // G2: B[n][k] = L_d[k][n]
-        } else {
-            int cc = c - n1 - n1p - D * nkb, d = cc / nkb, kb = cc % nkb, k = kb * 32 + kk;
-            if (n < M && k < M && k <= n) out = tc::tf32_rna(P.q_sqrt[((size_t)d * M + n) * M + k]);   // G5: B[n][k] = L_d[n][k]
         }
-        *reinterpret_cast<float*>(reinterpret_cast<char*>(P.wpack_fwd) + (size_t)c * TC_CHUNK_BYTES + tc::sw128_offset(n, kk)) = out;
+        char* dst = reinterpret_cast<char*>(P.wpack_fwd) + (size_t)blk * slot + tcp::band_offset(pat, M, kb) +
+                    tc::sw128_offset(n - r0, kk);
+        *reinterpret_cast<float*>(dst) = out;
     }
 }
 
@@ -63,7 +70,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t A_hi = sbase, A_lo = sbase + 65536, Bring = sbase + 131072;
-    const uint32_t misc = Bring + TC_NSTAGE * TC_CHUNK_BYTES;
+    const uint32_t slotb = tcp::slot_bytes(P.M);
+    const uint32_t misc = Bring + TC_NSTAGE * slotb;
     const uint32_t bar_full = misc, bar_empty = misc + 8 * TC_NSTAGE;
     const uint32_t bar_a = bar_empty + 8 * TC_NSTAGE;        // a_ready[3]
     const uint32_t bar_acc = bar_a + 24;                      // acc_full[2]
@@ -98,79 +106,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_gen;
     const uint32_t idesc = make_idesc_tf32(128, NPAD);
-    const int n1 = 2 * nkb, n1p = 2 * nkb;      // chunk offsets in the pack (G1' chunks exist even for white layers)
+
 
     if (warp == 8) {
         // ===================== TMA producer (one lane): streams the packed weight chunks through the ring ==========
         if (lane == 0) {
             const char* wsrc = reinterpret_cast<const char*>(P.wpack_fwd);
-            int s = 0, it = 0;
+            int s = 0;
             uint32_t ph = 1;      // producer waits on the "previous" phase of empty[s] first
-            // rows [r0, r0+nr) of chunk `it` are needed (the weight matrices are triangular); always lands at the slot start
-            auto load = [&](int r0, int nr) {
+            auto load = [&](int blk, int pat) {            // one band block = one bulk copy
+                const uint32_t bytes = tcp::block_bytes(pat, M);
                 mbar_wait(bar_empty + 8 * s, ph);
-                mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)nr * 128u);
-                tma_bulk_g2s(Bring + s * TC_CHUNK_BYTES, wsrc + (size_t)it * TC_CHUNK_BYTES + (size_t)r0 * 128, (uint32_t)nr * 128u,
-                             bar_full + 8 * s);
-                ++it;
+                mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+                tma_bulk_g2s(Bring + s * slotb, wsrc + (size_t)blk * slotb, bytes, bar_full + 8 * s);
                 if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
             };
-            // G1 (B[n][k] = Linv[n][k], k <= n): k-block kb touches rows n >= 32 kb
-            for (int kb = 0; kb < nkb; ++kb) { load(32 * kb, NPAD - 32 * kb); load(32 * kb, NPAD - 32 * kb); }
-            // G1' and G2 (k >= n): k-block kb touches rows n < 32 (kb+1); issued from the last k-block down
-            if (!P.white) for (int kb = nkb - 1; kb >= 0; --kb) { it = n1 + 2 * kb; load(0, min(NPAD, 32 * kb + 32)); load(0, min(NPAD, 32 * kb + 32)); }
-            for (int d = 0; d < D; ++d)
-                for (int kb = nkb - 1; kb >= 0; --kb) { it = n1 + n1p + d * nkb + kb; load(0, min(NPAD, 32 * kb + 32)); }
+            load(tcp::blk_g1(0), tcp::PAT_LE); load(tcp::blk_g1(1), tcp::PAT_LE);
+            if (!P.white) { load(tcp::blk_g1p(0), tcp::PAT_GE); load(tcp::blk_g1p(1), tcp::PAT_GE); }
+            for (int d = 0; d < D; ++d) load(tcp::blk_g2(d), tcp::PAT_GE);
         }
     } else if (warp == 9) {
-        // ===================== MMA issuer (one lane) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer: whole warp runs the uniform control flow, one elected lane issues ==========
+        {
             int s = 0;
             uint32_t ph = 0;
             const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             auto mkdesc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
-            // one weight chunk: D[:, c0 : c0+ncol) (+)= A[:, k-block kb] * B^T ; `fresh` = first chunk of this accumulator
-            auto do_chunk = [&](uint32_t dcol, int kb, int c0, int ncol, int mode /*0: A_hi & A_lo, 1: A_hi only*/, bool fresh) {
+            // one band block: D (+)= A * B^T over all k-blocks.  mode 0: A_hi and A_lo against this block (B_hi of a 3xTF32
+            // product), 1: A_hi only, accumulating (B_lo), 2: A_hi only (1xTF32 product, fresh accumulator)
+            auto do_block = [&](uint32_t dcol, int pat, int mode) {
                 mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
-                const int nks = min(4, (M - 32 * kb + 7) / 8);
-                const uint32_t bbase = Bring + s * TC_CHUNK_BYTES, abase = kb * TC_CHUNK_BYTES;
-                const uint32_t id = make_idesc_tf32(128, ncol);
-                for (int ks = 0; ks < nks; ++ks) {
-                    const uint64_t bd = mkdesc(bbase + ks * 32), ah = mkdesc(A_hi + abase + ks * 32);
-                    const uint32_t acc = (fresh && ks == 0) ? 0u : 1u;
-                    mma_tf32(tmem + dcol + c0, ah, bd, id, acc);
-                    if (mode == 0) mma_tf32(tmem + dcol + c0, mkdesc(A_lo + abase + ks * 32), bd, id, 1u);
+                const uint32_t bslot = Bring + s * slotb;
+                bool first = mode != 1;
+                for (int q = 0; q < nkb; ++q) {
+                    const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
+                    const int nks = min(4, (M - 32 * kb + 7) / 8);
+                    const uint32_t bbase = bslot + tcp::band_offset(pat, M, kb), abase = kb * TC_CHUNK_BYTES;
+                    const uint32_t id = make_idesc_tf32(128, tcp::band_rows(pat, M, kb));
+                    const uint32_t dc = tmem + dcol + (uint32_t)tcp::band_row0(pat, kb);
+                    if (elect_one()) {
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint64_t bd = mkdesc(bbase + ks * 32), ah = mkdesc(A_hi + abase + ks * 32);
+                            mma_tf32(dc, ah, bd, id, (first && ks == 0) ? 0u : 1u);
+                            if (mode == 0) mma_tf32(dc, mkdesc(A_lo + abase + ks * 32), bd, id, 1u);
+                        }
+                    }
+                    __syncwarp();
+                    first = false;
                 }
-                mma_commit(bar_empty + 8 * s);
+                if (elect_one()) mma_commit(bar_empty + 8 * s);
+                __syncwarp();
                 if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
             };
+            auto commit = [&](uint32_t bar) { if (elect_one()) mma_commit(bar); __syncwarp(); };
             // G1: b = Linv k   (3xTF32)
             mbar_wait(bar_a, 0);
             tc_fence_after();
-            for (int kb = 0; kb < nkb; ++kb) {
-                do_chunk(0u, kb, 32 * kb, NPAD - 32 * kb, 0, kb == 0);     // B_hi: A_hi*B_hi + A_lo*B_hi
-                do_chunk(0u, kb, 32 * kb, NPAD - 32 * kb, 1, false);       // B_lo: A_hi*B_lo
-            }
-            mma_commit(bar_acc);
+            do_block(0u, tcp::PAT_LE, 0);
+            do_block(0u, tcp::PAT_LE, 1);
+            commit(bar_acc);
             if (!P.white) {
                 // G1': u = Linv^T b   (3xTF32)
                 mbar_wait(bar_a + 8, 0);
                 tc_fence_after();
-                for (int kb = nkb - 1; kb >= 0; --kb) {
-                    do_chunk(128u, kb, 0, min(NPAD, 32 * kb + 32), 0, kb == nkb - 1);
-                    do_chunk(128u, kb, 0, min(NPAD, 32 * kb + 32), 1, false);
-                }
-                mma_commit(bar_acc + 8);
+                do_block(128u, tcp::PAT_GE, 0);
+                do_block(128u, tcp::PAT_GE, 1);
+                commit(bar_acc + 8);
             }
             // G2: c_d = L_d^T u   (1xTF32), accumulators double-buffered
             mbar_wait(bar_a + 16, 0);
             tc_fence_after();
             for (int d = 0; d < D; ++d) {
                 if (d >= 2) { mbar_wait(bar_acc2e + 8 * (d & 1), ((d >> 1) - 1) & 1); tc_fence_after(); }
-                for (int kb = nkb - 1; kb >= 0; --kb)
-                    do_chunk(256u + 128u * (uint32_t)(d & 1), kb, 0, min(NPAD, 32 * kb + 32), 1, kb == nkb - 1);
-                mma_commit(bar_acc2f + 8 * (d & 1));
+                do_block(256u + 128u * (uint32_t)(d & 1), tcp::PAT_GE, 2);
+                commit(bar_acc2f + 8 * (d & 1));
             }
         }
     } else {
@@ -391,24 +401,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-static size_t tc_fwd_smem(int M, int Din, int D) { return 1024 + 131072 + TC_NSTAGE * TC_CHUNK_BYTES + 256 + 1024 + sizeof(float) * ((size_t)M * Din + (size_t)M * D); }
+static size_t tc_fwd_smem(int M, int Din, int D) { return 1024 + 131072 + TC_NSTAGE * (size_t)tcp::slot_bytes(M) + 256 + 1024 + sizeof(float) * ((size_t)M * Din + (size_t)M * D + 8); }
 
-bool tc_fwd_supported(const LayerDev& P) { return P.M <= 128 && P.M >= 8 && P.Din <= 16 && P.Dout <= 32 && P.wpack_fwd != nullptr; }
+bool tc_fwd_supported(const LayerDev& P) {
+    return P.M <= 128 && P.M >= 8 && P.Din <= 16 && P.Dout <= 32 && P.wpack_fwd != nullptr &&
+           tc_fwd_smem(P.M, P.Din, P.Dout) <= 227 * 1024;
+}
 
 #define TC_FWD_INSTANCES(X) X(8, 1) X(8, 8) X(8, 32) X(16, 1) X(16, 8) X(16, 32)
 
 cudaError_t layer_tc_init() {
     cudaError_t e;
-#define X(a, b) if ((e = cudaFuncSetAttribute(k_layer_fwd_tc<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_fwd_smem(128, 16, 32)))) return e;
+#define X(a, b) if ((e = cudaFuncSetAttribute(k_layer_fwd_tc<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))) return e;
     TC_FWD_INSTANCES(X)
 #undef X
     return cudaSuccess;
 }
 
 size_t tc_fwd_pack_bytes(int M, int D, int white) {
-    int nkb = (M + 31) / 32;
     (void)white;
-    return (size_t)(4 * nkb + 2 * D * nkb) * TC_CHUNK_BYTES;
+    return (size_t)tcp::num_blocks(D) * tcp::slot_bytes(M);
 }
 
 void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nl) {

@@ -9,19 +9,15 @@
 // Math: tests/algo_mirror.py::layer_bwdA ; reference: TF autodiff of layers.py:178-219.
 #include "dsdgp_internal.cuh"
 #include "tc_common.cuh"
+#include "tc_pack.cuh"
 
 #define TC_ROWS 128
-#define TC_NSTAGE 4
+#define TC_NSTAGE 2
 #define TC_CHUNK_BYTES 16384
 #define TC_THREADS 320
 #define TC_ROWTHREADS 256
 
 namespace {
-__device__ __forceinline__ bool elect_one() {
-    uint32_t p;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
-    return p != 0;
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
@@ -38,7 +34,7 @@ struct BwdSmem {
 __host__ __device__ inline BwdSmem bwd_smem_plan(int M, int Din, int D) {
     BwdSmem s;
     s.A_u = 0; s.A_c = 65536; s.Bring = 131072;
-    s.bars = s.Bring + TC_NSTAGE * TC_CHUNK_BYTES;
+    s.bars = s.Bring + TC_NSTAGE * tcp::slot_bytes(M);
     s.Zs = s.bars + 256;
     s.qmu = s.Zs + 4 * ((M * Din + 3) & ~3);
     s.mv = s.qmu + 4 * ((M * D + 3) & ~3);
@@ -58,6 +54,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     const BwdSmem sp = bwd_smem_plan(M, Din, D);
     const uint32_t A_u = sbase + sp.A_u, A_c = sbase + sp.A_c, Bring = sbase + sp.Bring, bars = sbase + sp.bars;
     const uint32_t bar_full = bars, bar_empty = bars + 32;
+    const uint32_t slotb = tcp::slot_bytes(M);
     const uint32_t bar_au = bars + 64, bar_acc2f = bars + 72 /*[2]*/, bar_cready = bars + 88, bar_cfree = bars + 96;
     const uint32_t bar_ubar = bars + 104, bar_s6 = bars + 112, bar_acc6 = bars + 120, bar_s7 = bars + 128, bar_acc7 = bars + 136;
     const uint32_t tmem_slot = bars + 144;
@@ -73,7 +70,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     const int nkb = (M + 31) / 32, NPAD = (M + 15) & ~15;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * TC_ROWS, R = a.R;
-    const int n1 = 2 * nkb, off_g1p = n1, off_g2 = 2 * n1, off_g5 = 2 * n1 + D * nkb;    // chunk offsets in wpack
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -97,24 +93,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             const char* wsrc = reinterpret_cast<const char*>(P.wpack_fwd);
             int s = 0;
             uint32_t ph = 1;
-            auto load = [&](int chunk, int r0, int nr) {
+            auto load = [&](int blk, int pat) {            // one band block = one bulk copy
+                const uint32_t bytes = tcp::block_bytes(pat, M);
                 mbar_wait(bar_empty + 8 * s, ph);
-                mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)nr * 128u);
-                tma_bulk_g2s(Bring + s * TC_CHUNK_BYTES, wsrc + (size_t)chunk * TC_CHUNK_BYTES + (size_t)r0 * 128, (uint32_t)nr * 128u,
-                             bar_full + 8 * s);
+                mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+                tma_bulk_g2s(Bring + s * slotb, wsrc + (size_t)blk * slotb, bytes, bar_full + 8 * s);
                 if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
             };
-            auto g2 = [&](int d) { for (int kb = nkb - 1; kb >= 0; --kb) load(off_g2 + d * nkb + kb, 0, min(NPAD, 32 * kb + 32)); };
-            auto g5 = [&](int d) { for (int kb = 0; kb < nkb; ++kb) load(off_g5 + d * nkb + kb, 32 * kb, NPAD - 32 * kb); };
-            g2(0);
-            if (D > 1) g2(1);
-            for (int d = 0; d < D; ++d) { g5(d); if (d + 2 < D) g2(d + 2); }
-            if (!P.white)
-                for (int kb = 0; kb < nkb; ++kb) { load(2 * kb, 32 * kb, NPAD - 32 * kb); load(2 * kb + 1, 32 * kb, NPAD - 32 * kb); }
-            for (int kb = nkb - 1; kb >= 0; --kb) {
-                load(off_g1p + 2 * kb, 0, min(NPAD, 32 * kb + 32));
-                load(off_g1p + 2 * kb + 1, 0, min(NPAD, 32 * kb + 32));
-            }
+            load(tcp::blk_g2(0), tcp::PAT_GE);
+            if (D > 1) load(tcp::blk_g2(1), tcp::PAT_GE);
+            for (int d = 0; d < D; ++d) { load(tcp::blk_g5(D, d), tcp::PAT_LE); if (d + 2 < D) load(tcp::blk_g2(d + 2), tcp::PAT_GE); }
+            if (!P.white) { load(tcp::blk_g1(0), tcp::PAT_LE); load(tcp::blk_g1(1), tcp::PAT_LE); }
+            load(tcp::blk_g1p(0), tcp::PAT_GE); load(tcp::blk_g1p(1), tcp::PAT_GE);
         }
     } else if (warp == 9) {
         // ===================== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues ========
@@ -122,28 +112,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         uint32_t ph = 0;
         const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         auto mkdesc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
-        // D[:, c0 : c0+ncol) (+)= Ahi[:, kb] * B^T (+ Alo[:, kb] * B^T when with_lo) ; fresh: first chunk of the accumulator
-        auto do_chunk = [&](uint32_t dcol, uint32_t Ahi, uint32_t Alo, int kb, int c0, int ncol, bool with_lo, bool fresh) {
+        // one band block: D (+)= A * B^T over all its k-blocks.  with_lo: also A_lo against the same block; fresh: the
+        // block starts a new accumulator
+        auto do_block = [&](uint32_t dcol, uint32_t Ahi, uint32_t Alo, int pat, bool with_lo, bool fresh) {
             mbar_wait(bar_full + 8 * s, ph);
             tc_fence_after();
-            const int nks = min(4, (M - 32 * kb + 7) / 8);
-            const uint32_t bbase = Bring + s * TC_CHUNK_BYTES, abase = kb * TC_CHUNK_BYTES;
-            const uint32_t id = make_idesc_tf32(128, ncol);
-            if (elect_one()) {
-                for (int ks = 0; ks < nks; ++ks) {
-                    const uint64_t bd = mkdesc(bbase + ks * 32);
-                    mma_tf32(tmem + dcol + c0, mkdesc(Ahi + abase + ks * 32), bd, id, (fresh && ks == 0) ? 0u : 1u);
-                    if (with_lo) mma_tf32(tmem + dcol + c0, mkdesc(Alo + abase + ks * 32), bd, id, 1u);
+            const uint32_t bslot = Bring + s * slotb;
+            for (int q = 0; q < nkb; ++q) {
+                const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
+                const int nks = min(4, (M - 32 * kb + 7) / 8);
+                const uint32_t bbase = bslot + tcp::band_offset(pat, M, kb), abase = kb * TC_CHUNK_BYTES;
+                const uint32_t id = make_idesc_tf32(128, tcp::band_rows(pat, M, kb));
+                const uint32_t dc = tmem + dcol + (uint32_t)tcp::band_row0(pat, kb);
+                if (tc::elect_one()) {
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint64_t bd = mkdesc(bbase + ks * 32);
+                        mma_tf32(dc, mkdesc(Ahi + abase + ks * 32), bd, id, (fresh && q == 0 && ks == 0) ? 0u : 1u);
+                        if (with_lo) mma_tf32(dc, mkdesc(Alo + abase + ks * 32), bd, id, 1u);
+                    }
                 }
-                mma_commit(bar_empty + 8 * s);
+                __syncwarp();
             }
+            if (tc::elect_one()) mma_commit(bar_empty + 8 * s);
             __syncwarp();
             if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
         };
-        auto commit = [&](uint32_t bar) { if (elect_one()) mma_commit(bar); __syncwarp(); };
+        auto commit = [&](uint32_t bar) { if (tc::elect_one()) mma_commit(bar); __syncwarp(); };
         auto g2 = [&](int d) {
-            for (int kb = nkb - 1; kb >= 0; --kb)
-                do_chunk(128u * (uint32_t)(d & 1), A_u, 0, kb, 0, min(NPAD, 32 * kb + 32), false, kb == nkb - 1);
+            do_block(128u * (uint32_t)(d & 1), A_u, 0, tcp::PAT_GE, false, true);
             commit(bar_acc2f + 8 * (d & 1));
         };
         mbar_wait(bar_au, 0);
@@ -153,8 +149,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         for (int d = 0; d < D; ++d) {
             mbar_wait(bar_cready, d & 1);
             tc_fence_after();
-            for (int kb = 0; kb < nkb; ++kb)
-                do_chunk(256u, A_c, 0, kb, 32 * kb, NPAD - 32 * kb, false, d == 0 && kb == 0);
+            do_block(256u, A_c, 0, tcp::PAT_LE, false, d == 0);
             commit(bar_cfree);
             if (d == D - 1) commit(bar_ubar);
             if (d + 2 < D) g2(d + 2);
@@ -162,18 +157,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         if (!P.white) {
             mbar_wait(bar_s6, 0);
             tc_fence_after();
-            for (int kb = 0; kb < nkb; ++kb) {
-                do_chunk(0u, A_c, A_u, kb, 32 * kb, NPAD - 32 * kb, true, kb == 0);
-                do_chunk(0u, A_c, A_u, kb, 32 * kb, NPAD - 32 * kb, false, false);
-            }
+            do_block(0u, A_c, A_u, tcp::PAT_LE, true, true);
+            do_block(0u, A_c, A_u, tcp::PAT_LE, false, false);
             commit(bar_acc6);
         }
         mbar_wait(bar_s7, 0);
         tc_fence_after();
-        for (int kb = nkb - 1; kb >= 0; --kb) {
-            do_chunk(128u, A_c, A_u, kb, 0, min(NPAD, 32 * kb + 32), true, kb == nkb - 1);
-            do_chunk(128u, A_c, A_u, kb, 0, min(NPAD, 32 * kb + 32), false, false);
-        }
+        do_block(128u, A_c, A_u, tcp::PAT_GE, true, true);
+        do_block(128u, A_c, A_u, tcp::PAT_GE, false, false);
         commit(bar_acc7);
     } else {
         // ===================== row warps =====================
