@@ -290,18 +290,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         // ---- R2 (deferred, interleaved below): r2_i for this half's inducing points -> TMEM scratch columns 384+
         auto gram_chunk = [&](int c0) {
             float r2[8];
+            if (Din == DINP) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = min(c0 + u, M - 1);
-                float s = 0.f;
+                for (int u = 0; u < 8; ++u) {
+                    const int i = min(c0 + u, M - 1);
+                    const float4* zr = reinterpret_cast<const float4*>(Zs + i * DINP);
+                    float s = 0.f;
 #pragma unroll
-                for (int q = 0; q < DINP; ++q) {
-                    if (q < Din) {
-                        float dd = (x[q] - Zs[i * Din + q]) * il[q];
-                        s = fmaf(dd, dd, s);
+                    for (int q4 = 0; q4 < DINP / 4; ++q4) {
+                        const float4 zv = zr[q4];
+                        float d0 = (x[4 * q4] - zv.x) * il[4 * q4], d1 = (x[4 * q4 + 1] - zv.y) * il[4 * q4 + 1];
+                        float d2 = (x[4 * q4 + 2] - zv.z) * il[4 * q4 + 2], d3 = (x[4 * q4 + 3] - zv.w) * il[4 * q4 + 3];
+                        s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d2, d2, s); s = fmaf(d3, d3, s);
                     }
+                    r2[u] = s;
                 }
-                r2[u] = s;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = min(c0 + u, M - 1);
+                    float s = 0.f;
+#pragma unroll
+                    for (int q = 0; q < DINP; ++q) {
+                        if (q < Din) {
+                            float dd = (x[q] - Zs[i * Din + q]) * il[q];
+                            s = fmaf(dd, dd, s);
+                        }
+                    }
+                    r2[u] = s;
+                }
             }
             __syncwarp();
             tmem_st8(lane_addr + 384 + c0, r2);
