@@ -427,6 +427,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         a.F = (l < L - 1 || mode == MODE_PROPAGATE) ? c->F[l] : nullptr;
         if (l == 0 && L == 1 && mode == MODE_PROPAGATE) a.S_rep = S;     // single layer: still S draws for Fs
         a.z = (zmask >> l) & 1u ? c->zs[l] : nullptr;
+        a.z_out = (a.z == nullptr && a.F != nullptr && mode >= MODE_GRAD) ? c->zs[l] : nullptr;
         a.dbg = (c->dbg_layer == l) ? c->dbg_buf : nullptr;
         PROF_BEGIN(5 + 3 * l);
         if (c->path == 1 && tc_fwd_supported(c->ls.l[l])) launch_fwd_tc(c->ls.l[l], a, st, nl);
@@ -453,7 +454,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             b.S_rep = (l == 0 && L > 1) ? S : 1;
             b.U = c->U[l]; b.Fvar = c->Fvar[l];
             b.fbar = (l == L - 1) ? nullptr : c->xbar[l + 1];
-            b.z = (zmask >> l) & 1u ? c->zs[l] : nullptr;
+            b.z = c->zs[l];          // injected draws, or the Philox draws the forward pass stored
             b.mubar = c->mubar[l]; b.vbar = c->vbar[l]; b.W = c->Wbuf[l];
             b.xbar = (l == 0) ? nullptr : c->xbar[l];
             b.dbg = (c->dbg_layer == 100 + l) ? c->dbg_buf : nullptr;

@@ -145,6 +145,7 @@ struct FwdArgs {
     float* Fvar;          // (R, Dout) out
     float* F;             // (S_rep*R, Dout) out or NULL
     const float* z;       // (S_rep*R, Dout) or NULL -> Philox
+    float* z_out;         // when z == NULL: the Philox draws are stored here for the backward pass (or NULL)
     float jitter;
     const StepArgs* sa;
     long long* dbg;       // optional clock64() stamps of CTA 0 (diagnostics), else NULL

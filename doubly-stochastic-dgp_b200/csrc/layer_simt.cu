@@ -222,11 +222,13 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_fwd(LayerDev P, FwdArgs a) {
             if (a.S_rep == 1) {
                 int s = row / a.N, n = row % a.N;
                 float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, s, n + noff, d);
+                if (a.z_out) a.z_out[(size_t)row * D + d] = z;
                 a.F[(size_t)row * D + d] = fmaf(z, sd, mean);
             } else {
                 for (int s = 0; s < a.S_rep; ++s) {
                     size_t o = ((size_t)s * a.N + row) * D + d;
                     float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, s, row + noff, d);
+                    if (a.z_out) a.z_out[o] = z;
                     a.F[o] = fmaf(z, sd, mean);
                 }
             }

@@ -401,11 +401,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
                     if (a.S_rep == 1) {
                         int ss = row / a.N, n = row % a.N;
                         float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, ss, n + noff, d);
+                        if (a.z_out) a.z_out[(size_t)row * D + d] = z;
                         a.F[(size_t)row * D + d] = fmaf(z, sd, mean);
                     } else {
                         for (int ss = 0; ss < a.S_rep; ++ss) {
                             size_t o = ((size_t)ss * a.N + row) * D + d;
                             float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, ss, row + noff, d);
+                            if (a.z_out) a.z_out[o] = z;
                             a.F[o] = fmaf(z, sd, mean);
                         }
                     }

@@ -535,14 +535,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                 float zi[DINP];
 #pragma unroll
                 for (int q = 0; q < DINP; ++q) { sa[q] = 0.f; sb[q] = 0.f; zi[q] = q < Din ? Zs[i * Din + q] : 0.f; }
-                for (int r = rh * 64; r < rh * 64 + 64; ++r) {
-                    const float g = g_s[r * MP + i];
+                if (Din == DINP) {
+#pragma unroll 4
+                    for (int r = rh * 64; r < rh * 64 + 64; ++r) {
+                        const float g = g_s[r * MP + i];
+                        const float4* xr = reinterpret_cast<const float4*>(xs_s + r * DINP);
 #pragma unroll
-                    for (int q = 0; q < DINP; ++q) {
-                        if (q < Din) {
-                            const float dd = xs_s[r * Din + q] - zi[q];
-                            sa[q] = fmaf(g, dd, sa[q]);
-                            sb[q] = fmaf(g * dd, dd, sb[q]);
+                        for (int q4 = 0; q4 < DINP / 4; ++q4) {
+                            const float4 xv = xr[q4];
+                            const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float dd = xx[e] - zi[4 * q4 + e];
+                                sa[4 * q4 + e] = fmaf(g, dd, sa[4 * q4 + e]);
+                                sb[4 * q4 + e] = fmaf(g * dd, dd, sb[4 * q4 + e]);
+                            }
+                        }
+                    }
+                } else {
+                    for (int r = rh * 64; r < rh * 64 + 64; ++r) {
+                        const float g = g_s[r * MP + i];
+#pragma unroll
+                        for (int q = 0; q < DINP; ++q) {
+                            if (q < Din) {
+                                const float dd = xs_s[r * Din + q] - zi[q];
+                                sa[q] = fmaf(g, dd, sa[q]);
+                                sb[q] = fmaf(g * dd, dd, sb[q]);
+                            }
                         }
                     }
                 }
