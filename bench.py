@@ -191,37 +191,10 @@ def main_b200(args):
     K, W = args.steps, max(3, args.warmup)
     prob = make_workload()
     N, S = prob['N'], prob['S']
-    strong = args.scaling == "strong"
-    if strong and N % world:
+    if N % world:
         raise SystemExit("N must divide by the number of GPUs")
-    N_loc = N // world if strong else N
-    n_global = N if strong else N * world
-
-    m = build_model(prob, device=local_rank)
-    if world > 1:
-        ids = [_lib.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        m.comm_init(ids[0], rank, world)
-    ctx = m._ensure_ctx(N_loc, S)
-    m.adam_init(0.01)
-
-    # a pool of different minibatches: pinned host copies (e2e leg) and device-resident copies (value leg)
-    POOL = 8
-    rng = np.random.default_rng(100 + rank)
-    hostX, hostY, devX, devY = [], [], [], []
-    for _ in range(POOL):
-        x = torch.from_numpy(rng.normal(size=(N_loc, WORKLOAD['dims'][0])).astype(np.float32)).pin_memory()
-        y = torch.from_numpy((np.sin(x.numpy().sum(1, keepdims=True)) + 0.1 * rng.normal(size=(N_loc, 1))).astype(np.float32)).pin_memory()
-        hostX.append(x); hostY.append(y)
-        devX.append(x.cuda()); devY.append(y.cuda())
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ctx.sync()
-        torch.cuda.synchronize()
+    uid = [None]
 
     def max_over_ranks(v):
         if world == 1:
@@ -230,90 +203,122 @@ def main_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def dev_step(i, sync):
-        j = i % POOL
-        return ctx.train_step(devX[j].data_ptr(), devY[j].data_ptr(), N_loc, S, NUM_DATA, 1000 + i,
-                              flags=_lib.FLAG_DEVICE_PTRS | (0 if sync else _lib.FLAG_NO_SYNC), want_elbo=sync)
+    def run_mode(mode, want_profile, want_e2e):
+        """mode 'weak': every GPU evaluates S=20 samples of the SAME (N=1000) minibatch -- the S-shards of one ELBO with
+        S_total = 20*world are all-reduced (BASELINE: "the S Monte-Carlo samples shard across the GPUs"); per-GPU work fixed.
+        mode 'strong': S_total = 20 fixed; the S*N sample rows are sharded (N/world minibatch rows x all S per GPU)."""
+        strong = mode == "strong"
+        N_loc = N // world if strong else N
+        m = build_model(prob, device=local_rank)
+        if world > 1:
+            ids = [_lib.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            m.comm_init(ids[0], rank, world)
+        ctx = m._ensure_ctx(N_loc, S)
+        m.adam_init(0.01)
+        if world > 1:
+            if strong:
+                ctx.set_option("n_global", N); ctx.set_option("n_offset", rank * N_loc)
+            else:
+                ctx.set_option("n_global", N); ctx.set_option("n_offset", 0)
+                ctx.set_option("s_world", world); ctx.set_option("s_offset", rank * S)
+        # a pool of different minibatches: pinned host copies (e2e leg) and device-resident copies (value leg)
+        POOL = 8
+        rng = np.random.default_rng(100)              # same pool on every rank; strong mode takes this rank's rows
+        hostX, hostY, devX, devY = [], [], [], []
+        for _ in range(POOL):
+            xf = rng.normal(size=(N, WORKLOAD['dims'][0])).astype(np.float32)
+            yf = (np.sin(xf.sum(1, keepdims=True)) + 0.1 * rng.normal(size=(N, 1))).astype(np.float32)
+            lo = rank * N_loc if strong else 0
+            x = torch.from_numpy(np.ascontiguousarray(xf[lo:lo + N_loc])).pin_memory()
+            y = torch.from_numpy(np.ascontiguousarray(yf[lo:lo + N_loc])).pin_memory()
+            hostX.append(x); hostY.append(y)
+            devX.append(x.cuda()); devY.append(y.cuda())
 
-    if not strong or world > 1:
-        ctx.set_option("n_global", n_global)
-    for i in range(W):
-        dev_step(i, True)
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ctx.sync()
+            torch.cuda.synchronize()
 
-    # ---- value leg: device-resident inputs, per-step CUDA events on the ctx stream, L2 flushed between steps
-    clocks = ClockSampler(local_rank)
-    launches0 = ctx.launch_count()
-    barrier()
-    clocks.start()
-    tot_ms = 0.0
-    for i in range(K):
-        flush.fill_(i & 0xFF)
-        torch.cuda.synchronize()
-        dev_step(W + i, False)
-        tot_ms += ctx.last_step_ms()
-    barrier()
-    launches = ctx.launch_count() - launches0
-    tot_ms = max_over_ranks(tot_ms)
-    # back-to-back (no flush), one event pair around K steps
-    barrier()
-    ctx.timer_start()
-    for i in range(K):
-        dev_step(W + K + i, False)
-    b2b_ms = max_over_ranks(ctx.timer_stop())
-    clk = clocks.stop()
-    barrier()
+        def dev_step(i, sync):
+            j = i % POOL
+            return ctx.train_step(devX[j].data_ptr(), devY[j].data_ptr(), N_loc, S, NUM_DATA, 1000 + i,
+                                  flags=_lib.FLAG_DEVICE_PTRS | (0 if sync else _lib.FLAG_NO_SYNC), want_elbo=sync)
 
-    units = 1 if strong else world        # weak: every rank does a full (N=1000, S=20) step per step
-    value = units * K / (tot_ms / 1e3)
-
-    # ---- e2e leg: the public Python API with host (pinned) buffers; H2D of the minibatch + D2H of the ELBO per step
-    e2e = None
-    if not args.no_e2e:
-        Xh = [x.numpy() for x in hostX]
-        Yh = [y.numpy() for y in hostY]
-        for i in range(3):
-            m.train_step(Xh[i % POOL], Yh[i % POOL])
+        for i in range(W):
+            dev_step(i, True)
+        # ---- value leg: device-resident inputs, per-step CUDA events on the ctx stream, L2 flushed between steps
+        clocks = ClockSampler(local_rank)
+        launches0 = ctx.launch_count()
         barrier()
-        t0 = time.perf_counter()
+        clocks.start()
+        tot_ms = 0.0
         for i in range(K):
-            m.train_step(Xh[i % POOL], Yh[i % POOL])
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+            dev_step(W + i, False)
+            tot_ms += ctx.last_step_ms()
         barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": units * K / dt, "unit": "steps/s",
-               "h2d_bytes_per_step": int(Xh[0].nbytes + Yh[0].nbytes), "d2h_bytes_per_step": 16,
-               "timing": "host wall clock around K public-API calls (model.train_step), each returning the ELBO"}
-
-    # ---- per-stage profile (eager launches bracketed by events) -> dominant kernel and its roofline
-    roof = None
-    stage_ms = None
-    if rank == 0 or world > 1:
-        ctx.set_option("profile", 1)
-        acc = None
-        reps = 5
-        for i in range(reps + 1):
-            dev_step(5000 + i, True)
-            p = np.array(ctx.profile())
-            if i > 0:
-                acc = p if acc is None else acc + p
-        ctx.set_option("profile", 0)
-        p = acc / reps
-        L = len(WORKLOAD['dims']) - 1
-        names = ["prep(Kuu,chol,KL)", "likelihood", "grad-assembly", "allreduce", "adam"]
-        for l in range(L):
-            names += [f"layer{l + 1}.fwd", f"layer{l + 1}.bwd_rows", f"layer{l + 1}.rowred"]
-        stage_ms = {n: round(float(v), 4) for n, v in zip(names, p)}
-        fwd_fl, fixed, step_fl = algorithmic_flops(WORKLOAD['dims'], N_loc, WORKLOAD['M'], S)
-        top = int(np.argmax(p[5:])) + 5
-        l = (top - 5) // 3
-        peaks, how = measured_peaks()
-        peak_tf32 = peaks["bf16_tflops"] / 2.0
-        ach = fwd_fl[l] / (p[top] * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get(names[top].split(".")[1])
-        roof = {"bound": "tensor", "kernel": names[top], "achieved": ach, "peak": peak_tf32, "unit": "TFLOP/s",
+        launches = ctx.launch_count() - launches0
+        tot_ms = max_over_ranks(tot_ms)
+        barrier()
+        ctx.timer_start()
+        for i in range(K):
+            dev_step(W + K + i, False)
+        b2b_ms = max_over_ranks(ctx.timer_stop())
+        clk = clocks.stop()
+        barrier()
+        units = 1 if strong else world        # weak: every rank does a full (N=1000, S=20) evaluation per step
+        res = {"value": units * K / (tot_ms / 1e3), "ms_per_step": tot_ms / K, "ms_per_step_back_to_back": b2b_ms / K,
+               "gpu_launches": int(launches), "clocks": clk, "rows_per_gpu": N_loc * S, "N_loc": N_loc, "e2e": None,
+               "stage_ms": None, "roofline": None}
+        # ---- e2e leg: the public Python API with host (pinned) buffers; H2D of the minibatch + D2H of the ELBO per step
+        if want_e2e:
+            Xh = [x.numpy() for x in hostX]
+            Yh = [y.numpy() for y in hostY]
+            for i in range(3):
+                m.train_step(Xh[i % POOL], Yh[i % POOL])
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(K):
+                m.train_step(Xh[i % POOL], Yh[i % POOL])
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            res["e2e"] = {"value": units * K / dt, "unit": "steps/s",
+                          "h2d_bytes_per_step": int(Xh[0].nbytes + Yh[0].nbytes), "d2h_bytes_per_step": 16,
+                          "timing": "host wall clock around K public-API calls (model.train_step), each returning the ELBO"}
+        # ---- per-stage profile (eager launches bracketed by events) -> dominant kernel and its roofline
+        if want_profile:
+            ctx.set_option("profile", 1)
+            acc = None
+            reps = 5
+            for i in range(reps + 1):
+                dev_step(5000 + i, True)
+                p = np.array(ctx.profile())
+                if i > 0:
+                    acc = p if acc is None else acc + p
+            ctx.set_option("profile", 0)
+            p = acc / reps
+            L = len(WORKLOAD['dims']) - 1
+            names = ["prep(Kuu,chol,KL)", "likelihood", "grad-assembly", "allreduce", "adam"]
+            for l in range(L):
+                names += [f"layer{l + 1}.fwd", f"layer{l + 1}.bwd_rows", f"layer{l + 1}.rowred"]
+            res["stage_ms"] = {n: round(float(v), 4) for n, v in zip(names, p)}
+            fwd_fl, fixed, step_fl = algorithmic_flops(WORKLOAD['dims'], N_loc, WORKLOAD['M'], S)
+            top = int(np.argmax(p[5:])) + 5
+            l = (top - 5) // 3
+            peaks, how = measured_peaks()
+            peak_tf32 = peaks["bf16_tflops"] / 2.0
+            ach = fwd_fl[l] / (p[top] * 1e-3) / 1e12
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    traffic = json.load(f).get(names[top].split(".")[1])
+            res["roofline"] = {
+                "bound": "tensor", "kernel": names[top], "achieved": ach, "peak": peak_tf32, "unit": "TFLOP/s",
                 "frac": ach / peak_tf32, "traffic": traffic,
                 "note": f"algorithmic flops/launch = rows*f(l) = {fwd_fl[l]:.4g} (SURVEY 8(d): each of forward, row-backward "
                         f"and row-reduction kernels of a layer carries rows*f(l)); kernel time from CUDA events around the "
@@ -321,6 +326,15 @@ def main_b200(args):
                         "issues tcgen05 kind::tf32, ~1.3-1.4x the algorithmic MMA work because of the 3xTF32 stages); "
                         "traffic = dram read+write bytes per launch from the ncu --set full capture summarised in profiles/",
                 "step_achieved": step_fl / (tot_ms / K * 1e-3) / 1e12, "step_algorithmic_gflop": step_fl / 1e9}
+        m._ctx.close()
+        return res
+
+    primary = run_mode(args.scaling, want_profile=True, want_e2e=not args.no_e2e)
+    other = None
+    if world > 1:
+        other_mode = "strong" if args.scaling == "weak" else "weak"
+        o = run_mode(other_mode, want_profile=False, want_e2e=False)
+        other = {"scaling": other_mode, "value": o["value"], "ms_per_step": o["ms_per_step"], "rows_per_gpu": o["rows_per_gpu"]}
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample
     cpu = None
@@ -331,17 +345,24 @@ def main_b200(args):
                          "reference-faithful tiling, autograd backward, Adam), not TF 1.8"}
 
     if rank == 0:
+        weak = args.scaling == "weak"
         out = {
-            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "metric": METRIC, "value": primary["value"], "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": primary["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "tf32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[2]: 5-layer RBF DGP N=1000 M=100 S=20 dims 8-8-8-8-8-1", **WORKLOAD,
-                       "rows_per_gpu": N_loc * S, "global_rows": n_global * S, "parallelism": f"dp{world} (minibatch rows x all S)",
+                       "rows_per_gpu": primary["rows_per_gpu"],
+                       "parallelism": (f"dp{world}: S sharded -- every GPU draws S=20 samples of the N=1000 minibatch, S_total={S * world}, "
+                                       "one NCCL all-reduce of [grad || ELBO]; value counts (N=1000,S=20) evaluations/s"
+                                       if weak else
+                                       f"dp{world}: S_total=20 fixed, the S*N sample rows sharded ({primary['N_loc']} minibatch rows x all S per GPU), "
+                                       "one NCCL all-reduce of [grad || ELBO]"),
                        "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events on the launch stream",
                        "precision": "tcgen05 kind::tf32 (3xTF32 for the whitened projections / solves, 1xTF32 elsewhere), "
                                     "fp32 epilogues, fp64 MxM factorisation + KL"},
-            "ms_per_step_back_to_back": b2b_ms / K, "gpu_launches": int(launches), "clocks": clk,
-            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "stage_ms": stage_ms,
+            "ms_per_step_back_to_back": primary["ms_per_step_back_to_back"], "gpu_launches": primary["gpu_launches"],
+            "clocks": primary["clocks"], "e2e": primary["e2e"], "roofline": primary["roofline"], "cpu_baseline": cpu,
+            "stage_ms": primary["stage_ms"], "other_scaling": other,
         }
         print(json.dumps(out))
     if world > 1:
@@ -355,7 +376,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=20)

@@ -104,6 +104,7 @@ struct dsdgp_ctx {
     // comm
     nccl_comm_t comm; int rank, world;
     int n_global_opt, n_offset_opt;
+    int s_offset_opt, s_world_opt;   // S-sharded mode: this rank's first global sample, number of S-shards
     // graphs
     bool use_graph;
     int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
@@ -300,6 +301,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     c->adam_on = false; c->free_dirty = true; c->adam_t = 0;
     c->lr = 0.01; c->beta1 = 0.9; c->beta2 = 0.999; c->eps = 1e-8;
     c->comm = nullptr; c->rank = 0; c->world = 1; c->n_global_opt = -1; c->n_offset_opt = -1;
+    c->s_offset_opt = 0; c->s_world_opt = 1;
     c->use_graph = true; c->nlaunch = 0; c->last_ms = 0.f; c->path = 1;
     c->dbg_layer = -1; CK(dmalloc(&c->dbg_buf, 64));
     *out = c;
@@ -526,7 +528,8 @@ static int run_step(dsdgp_ctx* c, int mode, int N, int S, double num_data, unsig
     const int S_eff = (L == 1) ? 1 : S;
     sa.N_global = c->n_global_opt > 0 ? c->n_global_opt : N * c->world;
     sa.n_offset = c->n_offset_opt >= 0 ? c->n_offset_opt : N * c->rank;
-    sa.lik_scale = num_data / ((double)sa.N_global * S_eff);
+    sa.s_offset = c->s_offset_opt;
+    sa.lik_scale = num_data / ((double)sa.N_global * S_eff * (L == 1 ? 1 : c->s_world_opt));
     sa.kl_weight = 1.0 / c->world;
     if (mode == MODE_TRAIN) {
         c->adam_t += 1;
@@ -760,6 +763,8 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     }
     else if (n == "n_global") c->n_global_opt = (int)value;
     else if (n == "n_offset") c->n_offset_opt = (int)value;
+    else if (n == "s_offset") c->s_offset_opt = (int)value;
+    else if (n == "s_world") c->s_world_opt = (int)value < 1 ? 1 : (int)value;
     else return set_err(DSDGP_ERR_INVALID, "unknown option '%s'", name);
     return DSDGP_OK;
 }

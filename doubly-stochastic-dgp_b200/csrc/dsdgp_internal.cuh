@@ -36,6 +36,7 @@ struct StepArgs {
     double lik_scale;      // num_data / (N_global * S_eff)
     double kl_weight;      // 1/world
     int N_global, n_offset;
+    int s_offset;          // first global sample index of this rank (S-sharded data parallelism), else 0
     // Adam
     double lr_t, beta1, beta2, eps;
 };

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_fwd(LayerDev P, FwdArgs a) {
     // mean function, variance, draw
     const float var0 = P.var[0], jit = a.jitter;
     const unsigned long long seed = a.sa->seed;
-    const int noff = a.sa->n_offset;
+    const int noff = a.sa->n_offset, soff = a.sa->s_offset;
     for (int e = tid; e < TR * D; e += DSDGP_NT) {
         int d = e % D, r = e / D, row = row0 + r;
         if (row >= R) continue;
@@ -221,13 +221,13 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_fwd(LayerDev P, FwdArgs a) {
             float sd = sqrtf(fmaxf(v + jit, 1e-30f));
             if (a.S_rep == 1) {
                 int s = row / a.N, n = row % a.N;
-                float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, s, n + noff, d);
+                float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, s + soff, n + noff, d);
                 if (a.z_out) a.z_out[(size_t)row * D + d] = z;
                 a.F[(size_t)row * D + d] = fmaf(z, sd, mean);
             } else {
                 for (int s = 0; s < a.S_rep; ++s) {
                     size_t o = ((size_t)s * a.N + row) * D + d;
-                    float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, s, row + noff, d);
+                    float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, s + soff, row + noff, d);
                     if (a.z_out) a.z_out[o] = z;
                     a.F[o] = fmaf(z, sd, mean);
                 }
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_bwd(LayerDev P, BwdArgs a) {
 
     const float jit = a.jitter;
     const unsigned long long seed = a.sa->seed;
-    const int noff = a.sa->n_offset;
+    const int noff = a.sa->n_offset, soff = a.sa->s_offset;
 
     // B1: mubar, vbar
     for (int e = tid; e < TR * D; e += DSDGP_NT) {
@@ -274,14 +274,14 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_bwd(LayerDev P, BwdArgs a) {
                 if (a.S_rep == 1) {
                     int s = row / a.N, n = row % a.N;
                     float fb = a.fbar[(size_t)row * D + d];
-                    float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, s, n + noff, d);
+                    float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, s + soff, n + noff, d);
                     m = fb; v = fb * z / (2.f * sd);
                 } else {
                     float sz = 0.f;
                     for (int s = 0; s < a.S_rep; ++s) {
                         size_t o = ((size_t)s * a.N + row) * D + d;
                         float fb = a.fbar[o];
-                        float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, s, row + noff, d);
+                        float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, s + soff, row + noff, d);
                         m += fb; sz = fmaf(fb, z, sz);
                     }
                     v = sz / (2.f * sd);

@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
         // ---- finalise: half h handles outputs d = h, h+2, ...
         const float jit = a.jitter;
         const unsigned long long seed = a.sa->seed;
-        const int noff = a.sa->n_offset;
+        const int noff = a.sa->n_offset, soff = a.sa->s_offset;
         const float bnt = part_s[t] + part_s[128 + t];
         if (valid) {
             for (int d = half; d < D; d += 2) {
@@ -400,13 +400,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
                     float sd = sqrtf(fmaxf(v + jit, 1e-30f));
                     if (a.S_rep == 1) {
                         int ss = row / a.N, n = row % a.N;
-                        float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, ss, n + noff, d);
+                        float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, ss + soff, n + noff, d);
                         if (a.z_out) a.z_out[(size_t)row * D + d] = z;
                         a.F[(size_t)row * D + d] = fmaf(z, sd, mean);
                     } else {
                         for (int ss = 0; ss < a.S_rep; ++ss) {
                             size_t o = ((size_t)ss * a.N + row) * D + d;
-                            float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, ss, row + noff, d);
+                            float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, ss + soff, row + noff, d);
                             if (a.z_out) a.z_out[o] = z;
                             a.F[o] = fmaf(z, sd, mean);
                         }

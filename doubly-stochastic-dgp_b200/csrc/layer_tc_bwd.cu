@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         const int c_lo = half ? NH : 0, c_hi = half ? NPAD : NH;
         const float jit = a.jitter;
         const unsigned long long seed = a.sa->seed;
-        const int noff = a.sa->n_offset;
+        const int noff = a.sa->n_offset, soff = a.sa->s_offset;
         const float var0 = P.var[0];
         const bool dbg = a.dbg && blockIdx.x == 0 && threadIdx.x == 0;
         int dbi = 0;
@@ -219,14 +219,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                     if (a.S_rep == 1) {
                         int ss = row / a.N, n = row % a.N;
                         float fb = a.fbar[(size_t)row * D + d];
-                        float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, ss, n + noff, d);
+                        float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, ss + soff, n + noff, d);
                         m = fb; v = fb * z / (2.f * sd);
                     } else {
                         float sz = 0.f;
                         for (int ss = 0; ss < a.S_rep; ++ss) {
                             size_t o = ((size_t)ss * a.N + row) * D + d;
                             float fb = a.fbar[o];
-                            float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, ss, row + noff, d);
+                            float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, ss + soff, row + noff, d);
                             m += fb; sz = fmaf(fb, z, sz);
                         }
                         v = sz / (2.f * sd);

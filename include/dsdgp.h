@@ -153,7 +153,9 @@ DSDGP_API int dsdgp_timer_stop(dsdgp_ctx* ctx, float* ms);
  * Fills up to n entries: [0] prep, [1] lik, [2] fin, [3] comm, [4] adam, then per layer l:
  * [5+3l] forward, [6+3l] backward rows, [7+3l] row reductions.  Returns the number of entries. */
 DSDGP_API int dsdgp_profile(dsdgp_ctx* ctx, float* ms, int n);
-/* Tuning / diagnostics knobs: "graph" (0/1), "profile" (0/1), "n_global", "n_offset". */
+/* Knobs: "graph" (0/1), "profile" (0/1), "path" (0 fp32 SIMT / 1 tcgen05), "overlap" (0/1);
+ * data-parallel layout: "n_global", "n_offset" (row sharding: this rank holds rows [n_offset, n_offset+N) of n_global),
+ * "s_world", "s_offset" (sample sharding: this rank draws samples [s_offset, s_offset+S) of s_world*S). */
 DSDGP_API int dsdgp_set_option(dsdgp_ctx* ctx, const char* name, double value);
 
 #ifdef __cplusplus

@@ -257,3 +257,24 @@ def test_tcgen05_forward_matches_simt_forward(white):
             sc = max(1.0, float(np.abs(ref).max()))
             assert_allclose(out[1][which][l], out[0][which][l], atol=1e-3 * sc, rtol=0, err_msg=f"tc vs simt {name} l={l}")
             assert_allclose(out[1][which][l], ref, atol=1e-3 * sc, rtol=0, err_msg=f"tc vs oracle {name} l={l}")
+
+
+def test_sample_sharding_is_exact():
+    """S-sharded data parallelism (options s_world / s_offset): two shards of S samples each, drawn from the global
+    Philox sample indices [0,S) and [S,2S), reproduce the single evaluation with 2S samples:
+    e_full = e_0 + e_1 + KL  (each shard's ELBO carries the likelihood/(2S) part and, without a communicator, a full KL)."""
+    prob = make_problem(seed=4321, dims=[4, 4, 1], N=96, M=24, S=3, inner_q_scale=0.3, num_data=960)
+    m = _model(prob)
+    ctx = m._ctx
+    N, S = prob['N'], prob['S']
+    e_full = ctx.elbo(prob['X'], prob['Y'], 2 * S, prob['num_data'], seed=99) if False else None
+    m2 = _model(prob)
+    c2 = m2._ensure_ctx(N, 2 * S)
+    e_full = c2.elbo(prob['X'], prob['Y'], 2 * S, prob['num_data'], seed=99)
+    kl = float(np.sum(c2.kl()))
+    ctx.set_option("s_world", 2)
+    parts = []
+    for r in range(2):
+        ctx.set_option("s_offset", r * S)
+        parts.append(ctx.elbo(prob['X'], prob['Y'], S, prob['num_data'], seed=99))
+    assert abs((parts[0] + parts[1] + kl) - e_full) <= 2e-6 * abs(e_full), (parts, kl, e_full)
