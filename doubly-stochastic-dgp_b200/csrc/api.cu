@@ -109,6 +109,7 @@ struct dsdgp_ctx {
     bool use_graph;
     int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
     int dbg_layer; long long* dbg_buf;
+    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain;
     float* wpack[DSDGP_MAX_LAYERS];
     std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, int, int, unsigned>, long long> graph_launches;
@@ -304,6 +305,9 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     c->s_offset_opt = 0; c->s_world_opt = 1;
     c->use_graph = true; c->nlaunch = 0; c->last_ms = 0.f; c->path = 1;
     c->dbg_layer = -1; CK(dmalloc(&c->dbg_buf, 64));
+    c->chain_max_tiles = (int)((Rmax + 127) / 128);
+    CK(dmalloc(&c->chain_flags, (size_t)2 * DSDGP_MAX_LAYERS * c->chain_max_tiles));
+    c->epoch = 0; c->chain = true;
     *out = c;
     return DSDGP_OK;
 }
@@ -316,6 +320,7 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     float* fl[] = {c->params, c->grads, c->free_, c->adam_m, c->adam_v, c->sm32, c->accf, c->Xd, c->Yd};
     for (float* p : fl) cudaFree(p);
+    cudaFree(c->chain_flags); cudaFree(c->dbg_buf);
     cudaFree(c->kinds); cudaFree(c->sm64); cudaFree(c->sa_dev); cudaFree(c->acc); cudaFree(c->result_dev);
     for (int l = 0; l < c->desc.L; ++l) {
         float* pl[] = {c->U[l], c->Fmean[l], c->Fvar[l], c->F[l], c->zs[l], c->xbar[l], c->meanW[l], c->meanB[l], c->wpack[l],
@@ -419,6 +424,9 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     if (any_tc) launch_pack_fwd(c->ls, st, nl);
     PROF_END(0);
     // forward
+    const bool chain = c->chain && c->path == 1 && !prof && mode != MODE_PROPAGATE && tc_chain_fwd_supported(c->ls);
+    FwdChain fc;
+    fc.L = L; fc.max_tiles = c->chain_max_tiles; fc.flags = c->chain_flags; fc.sa = c->sa_dev; fc.base[0] = 0;
     for (int l = 0; l < L; ++l) {
         FwdArgs a;
         a.Xin = (l == 0) ? c->Xd : c->F[l - 1];
@@ -431,11 +439,16 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         a.z = (zmask >> l) & 1u ? c->zs[l] : nullptr;
         a.z_out = (a.z == nullptr && a.F != nullptr && mode >= MODE_GRAD) ? c->zs[l] : nullptr;
         a.dbg = (c->dbg_layer == l) ? c->dbg_buf : nullptr;
+        if (chain) {
+            fc.a[l] = a; fc.tiles[l] = (a.R + 127) / 128; fc.base[l + 1] = fc.base[l] + fc.tiles[l];
+            continue;
+        }
         PROF_BEGIN(5 + 3 * l);
         if (c->path == 1 && tc_fwd_supported(c->ls.l[l])) launch_fwd_tc(c->ls.l[l], a, st, nl);
         else launch_fwd(c->ls.l[l], a, c->num_sms, st, nl);
         PROF_END(5 + 3 * l);
     }
+    if (chain) launch_chain_fwd_tc(c->ls, fc, c->num_sms, st, nl);
     if (mode == MODE_PROPAGATE) return DSDGP_OK;
     // likelihood
     const int Rlast = (L == 1) ? N : N * S;
@@ -529,6 +542,7 @@ static int run_step(dsdgp_ctx* c, int mode, int N, int S, double num_data, unsig
     sa.N_global = c->n_global_opt > 0 ? c->n_global_opt : N * c->world;
     sa.n_offset = c->n_offset_opt >= 0 ? c->n_offset_opt : N * c->rank;
     sa.s_offset = c->s_offset_opt;
+    sa.epoch = ++c->epoch;
     sa.lik_scale = num_data / ((double)sa.N_global * S_eff * (L == 1 ? 1 : c->s_world_opt));
     sa.kl_weight = 1.0 / c->world;
     if (mode == MODE_TRAIN) {
@@ -742,7 +756,11 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     std::string n(name);
     if (n == "graph") c->use_graph = value != 0;
     else if (n == "profile") c->profile = value != 0;
-    else if (n == "overlap") {
+    else if (n == "chain") {
+        c->chain = value != 0;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "overlap") {
         c->overlap = value != 0;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
@@ -751,6 +769,11 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
         c->dbg_layer = (int)value;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "dbg_prep") {
+        double h[8];
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpy(h, c->ls.l[0].scal, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "prepA cycles: gram %.0f  factor+inverse %.0f  outputs %.0f\n", h[5], h[6], h[7]);
     } else if (n == "dbg_dump") {
         long long h[64];
         CK(cudaStreamSynchronize(c->stream));

@@ -37,6 +37,7 @@ struct StepArgs {
     double kl_weight;      // 1/world
     int N_global, n_offset;
     int s_offset;          // first global sample index of this rank (S-sharded data parallelism), else 0
+    unsigned epoch;        // step counter (> 0): value of the per-tile "published" flags of the persistent chain kernels
     // Adam
     double lr_t, beta1, beta2, eps;
 };
@@ -152,6 +153,16 @@ struct FwdArgs {
     long long* dbg;       // optional clock64() stamps of CTA 0 (diagnostics), else NULL
 };
 
+// all layers' forward tiles as one persistent launch (layer_tc.cu k_chain_fwd_tc)
+struct FwdChain {
+    FwdArgs a[DSDGP_MAX_LAYERS];
+    int L, max_tiles;
+    int tiles[DSDGP_MAX_LAYERS];
+    int base[DSDGP_MAX_LAYERS + 1];      // first task number of each layer
+    unsigned* flags;                     // [L][max_tiles]
+    const StepArgs* sa;
+};
+
 struct BwdArgs {
     const float* Xin;     // (R, Din)
     int R, N, S_rep;
@@ -188,6 +199,8 @@ bool tc_fwd_supported(const LayerDev& P);
 size_t tc_fwd_pack_bytes(int M, int D, int white);
 void launch_pack_fwd(const LayerSet& ls, cudaStream_t st, long long* nlaunch);
 void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nlaunch);
+bool tc_chain_fwd_supported(const LayerSet& ls);
+void launch_chain_fwd_tc(const LayerSet& ls, const FwdChain& fc, int num_sms, cudaStream_t st, long long* nlaunch);
 cudaError_t layer_tc_bwd_init();
 bool tc_bwd_supported(const LayerDev& P);
 void launch_bwd_rows_tc(const LayerDev& P, const BwdArgs& a, cudaStream_t st, long long* nlaunch);

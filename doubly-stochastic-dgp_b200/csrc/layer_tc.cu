@@ -63,12 +63,12 @@ void launch_pack_fwd(const LayerSet& ls, cudaStream_t st, long long* nl) {
 // and split the accumulator columns / the inducing points between them), warp 8 = control (TMA + MMA issue).
 // ----------------------------------------------------------------------------------------------
 #define TC_ROWTHREADS 256
+// One 128-row tile of one layer.  `tile` = row-tile index; tmem = base of this CTA's 512 TMEM columns; reinit = the
+// mbarriers were used by a previous tile of this CTA (persistent chain kernel) and must be invalidated first.
 template <int DINP, int DOUTP>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdArgs a) {
+__device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& a, const int tile, const uint32_t sbase,
+                                              uint8_t* sgen, const uint32_t tmem, const bool reinit) {
     using namespace tc;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t A_hi = sbase, A_lo = sbase + 65536, Bring = sbase + 131072;
     const uint32_t slotb = tcp::slot_bytes(P.M);
     const uint32_t misc = Bring + TC_NSTAGE * slotb;
@@ -77,8 +77,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     const uint32_t bar_acc = bar_a + 24;                      // acc_full[2]
     const uint32_t bar_acc2f = bar_acc + 16;                  // acc2_full[2]
     const uint32_t bar_acc2e = bar_acc2f + 16;                // acc2_empty[2]
-    const uint32_t tmem_slot = bar_acc2e + 16;
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + (tmem_slot - sbase));
     float* part_s = reinterpret_cast<float*>(sgen + (misc + 256 - sbase));        // [2][128] |b|^2 partials
     float* Zs = part_s + 256;                                                       // [M][Din]
     float* qmu_s = Zs + ((P.M * P.Din + 3) & ~3);                                   // [M][D], 16-byte aligned
@@ -89,23 +87,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     const int M = P.M, Din = P.Din, D = P.Dout;
     const int nkb = (M + 31) / 32, NPAD = (M + 15) & ~15;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * TC_ROWS, R = a.R;
-    const uint32_t copy_bytes = (uint32_t)NPAD * 128u;
+    const int row0 = tile * TC_ROWS, R = a.R;
 
     if (threadIdx.x == 0) {
+        if (reinit)
+            for (int i = 0; i < 2 * TC_NSTAGE + 9; ++i) mbar_inval(misc + 8 * i);
         for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int i = 0; i < 3; ++i) mbar_init(bar_a + 8 * i, TC_ROWTHREADS);
         for (int i = 0; i < 2; ++i) { mbar_init(bar_acc + 8 * i, 1); mbar_init(bar_acc2f + 8 * i, 1); mbar_init(bar_acc2e + 8 * i, TC_ROWTHREADS); }
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
     for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) Zs[e] = P.Z[e];
     for (int e = threadIdx.x; e < M * D; e += TC_THREADS) qmu_s[e] = P.q_mu[e];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot_gen;
-    const uint32_t idesc = make_idesc_tf32(128, NPAD);
 
 
     if (warp == 8) {
@@ -186,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     } else {
         // ===================== row warps =====================
         const int t = threadIdx.x & 127, half = threadIdx.x >> 7, row = row0 + t;
-        const bool dbg = a.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+        const bool dbg = a.dbg && tile == 0 && threadIdx.x == 0;
         int dbi = 0;
 #define STAMP() do { if (dbg) a.dbg[dbi++] = clock64(); } while (0)
         STAMP();
@@ -215,7 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
         float x[DINP], il[DINP];
 #pragma unroll
         for (int q = 0; q < DINP; ++q) {
-            x[q] = (valid && q < Din) ? a.Xin[(size_t)row * Din + q] : 0.f;
+            x[q] = (valid && q < Din) ? __ldcg(&a.Xin[(size_t)row * Din + q]) : 0.f;
             il[q] = q < Din ? 1.0f / P.ls[P.ard ? q : 0] : 0.f;
         }
         const float var0 = P.var[0];
@@ -390,7 +386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
                 if (P.mean == DSDGP_MEAN_IDENTITY) mean += x[d < DINP ? d : 0];
                 else if (P.mean == DSDGP_MEAN_LINEAR) {
                     float ms = P.meanB[d];
-                    for (int q = 0; q < Din; ++q) ms = fmaf(a.Xin[(size_t)row * Din + q], __ldg(&P.meanW[q * D + d]), ms);
+                    for (int q = 0; q < Din; ++q) ms = fmaf(__ldcg(&a.Xin[(size_t)row * Din + q]), __ldg(&P.meanW[q * D + d]), ms);
                     mean += ms;
                 }
                 float v = var0 - bnt + csq_p[d * 128 + t] + csq_p[(D + d) * 128 + t];
@@ -415,9 +411,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
             }
         }
     }
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[40] = clock64();
+    if (a.dbg && tile == 0 && threadIdx.x == 0) a.dbg[40] = clock64();
     tc_fence_before();
     __syncthreads();
+}
+
+// ---- one layer, one tile per CTA
+template <int DINP, int DOUTP>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdArgs a) {
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    __shared__ uint32_t tmem_slot_s;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 8) tmem_alloc(smem_u32(&tmem_slot_s), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot_s;
+    fwd_tile_body<DINP, DOUTP>(P, a, blockIdx.x, sbase, sgen, tmem, false);
+    if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ---- all layers in ONE persistent kernel.  Tasks (layer l, tile t) are numbered layer-major; CTA c runs tasks
+// c, c+grid, c+2*grid, ... in increasing order and, before a task, spins until the tile(s) of the previous layer it
+// reads have been published (flag == epoch).  A task's dependency always has a smaller task number, and every CTA
+// runs its tasks in increasing order, so the smallest unfinished task is always runnable: no deadlock as long as
+// all CTAs are co-resident (grid <= number of SMs, 1 CTA/SM).  Rows are independent chains through the layers, so the
+// layer boundary costs no grid-wide wave quantisation: ceil(tasks/grid) tile latencies instead of 2 per layer.
+template <int DINP, int DOUTP>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_chain_fwd_tc(const __grid_constant__ LayerSet ls, const __grid_constant__ FwdChain fc) {
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    __shared__ uint32_t tmem_slot_s;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 8) tmem_alloc(smem_u32(&tmem_slot_s), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot_s;
+    const unsigned epoch = fc.sa->epoch;
+    bool first = true;
+    for (int q = blockIdx.x; q < fc.base[fc.L]; q += gridDim.x) {
+        int l = 0;
+        while (q >= fc.base[l + 1]) ++l;
+        const int t = q - fc.base[l];
+        if (l > 0 && threadIdx.x == 0) {
+            // dependency: the producer tile(s) of layer l-1
+            const unsigned* fl = fc.flags + (size_t)(l - 1) * fc.max_tiles;
+            if (fc.a[l - 1].S_rep > 1 || fc.tiles[l - 1] != fc.tiles[l]) {
+                for (int tt = 0; tt < fc.tiles[l - 1]; ++tt)
+                    while (ld_acquire_gpu(fl + tt) != epoch) {}
+            } else {
+                while (ld_acquire_gpu(fl + t) != epoch) {}
+            }
+        }
+        __syncthreads();
+        fwd_tile_body<DINP, DOUTP>(ls.l[l], fc.a[l], t, sbase, sgen, tmem, !first);
+        first = false;
+        if (threadIdx.x == 0) {                 // publish (all threads' global stores precede the barrier above)
+            __threadfence();
+            st_release_gpu(fc.flags + (size_t)l * fc.max_tiles + t, epoch);
+        }
+    }
     if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
@@ -425,14 +484,15 @@ static size_t tc_fwd_smem(int M, int Din, int D) { return 1024 + 131072 + TC_NST
 
 bool tc_fwd_supported(const LayerDev& P) {
     return P.M <= 128 && P.M >= 8 && P.Din <= 16 && P.Dout <= 32 && P.wpack_fwd != nullptr &&
-           tc_fwd_smem(P.M, P.Din, P.Dout) <= 227 * 1024;
+           tc_fwd_smem(P.M, P.Din, P.Dout) <= 226 * 1024;
 }
 
 #define TC_FWD_INSTANCES(X) X(8, 1) X(8, 8) X(8, 32) X(16, 1) X(16, 8) X(16, 32)
 
 cudaError_t layer_tc_init() {
     cudaError_t e;
-#define X(a, b) if ((e = cudaFuncSetAttribute(k_layer_fwd_tc<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))) return e;
+    if ((e = cudaFuncSetAttribute(k_chain_fwd_tc<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024))) return e;
+#define X(a, b) if ((e = cudaFuncSetAttribute(k_layer_fwd_tc<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024))) return e;
     TC_FWD_INSTANCES(X)
 #undef X
     return cudaSuccess;
@@ -441,6 +501,20 @@ cudaError_t layer_tc_init() {
 size_t tc_fwd_pack_bytes(int M, int D, int white) {
     (void)white;
     return (size_t)tcp::num_blocks(D) * tcp::slot_bytes(M);
+}
+
+bool tc_chain_fwd_supported(const LayerSet& ls) {
+    for (int l = 0; l < ls.L; ++l)
+        if (!tc_fwd_supported(ls.l[l]) || ls.l[l].Din > 8 || ls.l[l].Dout > 8 || ls.l[l].M != ls.l[0].M) return false;
+    return ls.L >= 2;      // (same M everywhere: the shared-memory carve-up, hence the mbarrier addresses, must not move)
+}
+
+void launch_chain_fwd_tc(const LayerSet& ls, const FwdChain& fc, int num_sms, cudaStream_t st, long long* nl) {
+    size_t sm = 0;
+    for (int l = 0; l < ls.L; ++l) sm = max(sm, tc_fwd_smem(ls.l[l].M, ls.l[l].Din, ls.l[l].Dout));
+    int grid = min(num_sms, fc.base[fc.L]);
+    k_chain_fwd_tc<8, 8><<<grid, TC_THREADS, sm, st>>>(ls, fc);
+    *nl += 1;
 }
 
 void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nl) {

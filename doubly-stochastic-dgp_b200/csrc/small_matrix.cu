@@ -16,11 +16,15 @@ __global__ void __launch_bounds__(1024) k_prepA(LayerSet ls, double jitter, Accu
     double* X = use_smem ? smd + (size_t)M * M : P.Linv64;
     const double var = (double)P.var[0];
 
+    long long t0 = clock64();
+    __shared__ double s_il[64];
+    for (int q = tid; q < min(Din, 64); q += nt) s_il[q] = 1.0 / (double)P.ls[P.ard ? q : 0];
+    __syncthreads();
     for (int idx = tid; idx < M * M; idx += nt) {
         int i = idx / M, j = idx % M;
         double r2 = 0.0;
         for (int q = 0; q < Din; ++q) {
-            double il = 1.0 / (double)P.ls[P.ard ? q : 0];
+            double il = q < 64 ? s_il[q] : 1.0 / (double)P.ls[P.ard ? q : 0];
             double d = ((double)P.Z[i * Din + q] - (double)P.Z[j * Din + q]) * il;
             r2 += d * d;
         }
@@ -33,28 +37,64 @@ __global__ void __launch_bounds__(1024) k_prepA(LayerSet ls, double jitter, Accu
     }
     __syncthreads();
 
+    long long t1 = clock64();
     __shared__ int s_fail;
+    __shared__ double s_piv[2];
     if (tid == 0) s_fail = 0;
     const int tx = tid & 31, ty = tid >> 5, nwarp = nt >> 5;
     for (int j = 0; j < M; ++j) {
         // phase A: scale column j of A (below the diagonal) and row j of X by 1/sqrt(A[j][j])
-        double piv = A[j * M + j];
-        if (!(piv > 0.0)) { if (tid == 0) s_fail = 1; piv = 1.0; }
-        double d = sqrt(piv), id = 1.0 / d;
-        __syncthreads();                      // everyone has read A[j][j]
-        for (int i = j + tid; i < M; i += nt) {
-            if (i == j) A[j * M + j] = d; else A[i * M + j] *= id;
+        // (the fp64 sqrt / reciprocal is done by one thread: replicated over 1024 threads it costs ~600 cycles of the
+        //  SM's fp64 throughput per column)
+        if (tid == 0) {
+            double piv = A[j * M + j];
+            if (!(piv > 0.0)) { s_fail = 1; piv = 1.0; }
+            const double d = sqrt(piv);
+            s_piv[0] = d; s_piv[1] = 1.0 / d;
+            A[j * M + j] = d;
         }
+        __syncthreads();
+        const double id = s_piv[1];
+        for (int i = j + 1 + tid; i < M; i += nt) A[i * M + j] *= id;
         for (int c = tid; c <= j; c += nt) X[j * M + c] *= id;
         __syncthreads();
-        // phase B: trailing update of A (lower triangle) and elimination step on X; one warp per row, lanes over columns
-        for (int i = j + 1 + ty; i < M; i += nwarp) {
-            const double lij = A[i * M + j];
-            for (int k = j + 1 + tx; k <= i; k += 32) A[i * M + k] -= lij * A[k * M + j];
-            for (int c = tx; c <= j; c += 32) X[i * M + c] -= lij * X[j * M + c];
+        // phase B: trailing update of A (lower triangle) and elimination step on X.  Thread (ty, tx) owns the elements
+        // (j+1+ty+32a, j+1+tx+32b) of A and (j+1+ty+32a, tx+32b) of X; the a/b loops are unrolled so that the loads of all
+        // of a thread's elements are in flight together (the loop is latency-, not throughput-bound).
+        {
+            const int n = M - j - 1;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int ii = ty + 32 * a;
+                if (ii < n) {
+                    const int i = j + 1 + ii;
+                    const double lij = A[i * M + j];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int kk = tx + 32 * b;
+                        if (kk <= ii) { const int k = j + 1 + kk; A[i * M + k] -= lij * A[k * M + j]; }
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int c = tx + 32 * b;
+                        if (c <= j) X[i * M + c] -= lij * X[j * M + c];
+                    }
+                }
+            }
+            // matrices larger than 128: remaining rows / columns (rare; generic strided loops)
+            if (M > 128) {
+                for (int i = j + 1 + ty; i < M; i += nwarp) {
+                    const double lij = A[i * M + j];
+                    for (int k = j + 1 + tx; k <= i; k += 32)
+                        if (i - (j + 1) >= 128 || k - (j + 1) >= 128) A[i * M + k] -= lij * A[k * M + j];
+                    for (int c = tx; c <= j; c += 32)
+                        if (i - (j + 1) >= 128 || c >= 128) X[i * M + c] -= lij * X[j * M + c];
+                }
+            }
         }
         __syncthreads();
     }
+    long long t2 = clock64();
     if (tid == 0 && s_fail) atomicExch(&acc->status, blockIdx.x + 1);
 
     // outputs
@@ -77,6 +117,7 @@ __global__ void __launch_bounds__(1024) k_prepA(LayerSet ls, double jitter, Accu
         double t = 0.0;
         for (int w = 0; w < (nt + 31) / 32; ++w) t += red[w];
         P.scal[0] = t; P.scal[2] = 0.0; P.scal[3] = 0.0;
+        P.scal[5] = (double)(t1 - t0); P.scal[6] = (double)(t2 - t1); P.scal[7] = (double)(clock64() - t2);
     }
 }
 

@@ -11,3 +11,6 @@ for layer in [int(a) for a in sys.argv[1:]]:
     for i in range(3): ctx.elbo_grad(prob['X'],prob['Y'],20,8192,seed=i)
     print("layer",layer,file=sys.stderr)
     ctx.set_option("dbg_dump",1)
+ctx.set_option("dbg_layer",-1)
+ctx.elbo_grad(prob['X'],prob['Y'],20,8192,seed=5)
+ctx.set_option("dbg_prep",1)
