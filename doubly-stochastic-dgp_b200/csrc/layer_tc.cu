@@ -12,7 +12,8 @@
 #include "tc_pack.cuh"
 
 #define TC_ROWS 128
-#define TC_NSTAGE 2          // weight ring: two slots of one band block each
+#define TC_NSTAGE 3          // weight ring slots (barriers): slots 0,1 in the ring area, slot 2 = the A_lo operand buffer
+                             // once the 3xTF32 projections are done (G2 streams 1.5x more bytes in flight)
 #define TC_CHUNK_BYTES 16384 // one [128 rows] x [32 k] activation k-block
 #define TC_THREADS 320
 
@@ -71,7 +72,9 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
     using namespace tc;
     const uint32_t A_hi = sbase, A_lo = sbase + 65536, Bring = sbase + 131072;
     const uint32_t slotb = tcp::slot_bytes(P.M);
-    const uint32_t misc = Bring + TC_NSTAGE * slotb;
+    const uint32_t misc = Bring + 2 * slotb;
+    const bool three = P.Dout <= 8 && slotb <= 40960;            // third slot + scratch fit into the 64 KB of A_lo
+    auto slot_addr = [&](int sl) { return sl == 2 ? A_lo : Bring + (uint32_t)sl * slotb; };
     const uint32_t bar_full = misc, bar_empty = misc + 8 * TC_NSTAGE;
     const uint32_t bar_a = bar_empty + 8 * TC_NSTAGE;        // a_ready[3]
     const uint32_t bar_acc = bar_a + 24;                      // acc_full[2]
@@ -81,7 +84,7 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
     float* Zs = part_s + 256;                                                       // [M][Din]
     float* qmu_s = Zs + ((P.M * P.Din + 3) & ~3);                                   // [M][D], 16-byte aligned
     // scratch aliased on A_lo once it is dead (G2 reads A_hi only): mean partials [2][128][D], |c_d|^2 partials [2][D][128]
-    float* mean_p = reinterpret_cast<float*>(sgen + (A_lo - sbase));
+    float* mean_p = reinterpret_cast<float*>(sgen + (A_lo - sbase) + (three ? 40960 : 0));
     float* csq_p = mean_p + 2 * 128 * P.Dout;
 
     const int M = P.M, Din = P.Din, D = P.Dout;
@@ -108,32 +111,35 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
         // ===================== TMA producer (one lane): streams the packed weight chunks through the ring ==========
         if (lane == 0) {
             const char* wsrc = reinterpret_cast<const char*>(P.wpack_fwd);
-            int s = 0;
-            uint32_t ph = 1;      // producer waits on the "previous" phase of empty[s] first
-            auto load = [&](int blk, int pat) {            // one band block = one bulk copy
+            int cnt[3] = {0, 0, 0};         // uses of each slot so far
+            auto load = [&](int blk, int pat, int sl) {            // one band block = one bulk copy
                 const uint32_t bytes = tcp::block_bytes(pat, M);
-                mbar_wait(bar_empty + 8 * s, ph);
-                mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
-                tma_bulk_g2s(Bring + s * slotb, wsrc + (size_t)blk * slotb, bytes, bar_full + 8 * s);
-                if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
+                mbar_wait(bar_empty + 8 * sl, ((cnt[sl] & 1) ^ 1));
+                mbar_arrive_expect_tx(bar_full + 8 * sl, bytes);
+                tma_bulk_g2s(slot_addr(sl), wsrc + (size_t)blk * slotb, bytes, bar_full + 8 * sl);
+                ++cnt[sl];
             };
-            load(tcp::blk_g1(0), tcp::PAT_LE); load(tcp::blk_g1(1), tcp::PAT_LE);
-            if (!P.white) { load(tcp::blk_g1p(0), tcp::PAT_GE); load(tcp::blk_g1p(1), tcp::PAT_GE); }
-            for (int d = 0; d < D; ++d) load(tcp::blk_g2(d), tcp::PAT_GE);
+            load(tcp::blk_g1(0), tcp::PAT_LE, 0); load(tcp::blk_g1(1), tcp::PAT_LE, 1);
+            if (!P.white) { load(tcp::blk_g1p(0), tcp::PAT_GE, 0); load(tcp::blk_g1p(1), tcp::PAT_GE, 1); }
+            for (int d = 0; d < D; ++d) {
+                const int sl = three ? (2 + d) % 3 : d & 1;
+                if (three && d == 0) mbar_wait(P.white ? bar_acc : bar_acc + 8, 0);      // A_lo is dead: projections done
+                load(tcp::blk_g2(d), tcp::PAT_GE, sl);
+            }
         }
     } else if (warp == 9) {
         // ===================== MMA issuer: whole warp runs the uniform control flow, one elected lane issues ==========
         {
-            int s = 0;
-            uint32_t ph = 0;
+            int cnt[3] = {0, 0, 0};
             const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             auto mkdesc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
             // one band block: D (+)= A * B^T over all k-blocks.  mode 0: A_hi and A_lo against this block (B_hi of a 3xTF32
             // product), 1: A_hi only, accumulating (B_lo), 2: A_hi only (1xTF32 product, fresh accumulator)
-            auto do_block = [&](uint32_t dcol, int pat, int mode) {
-                mbar_wait(bar_full + 8 * s, ph);
+            auto do_block = [&](uint32_t dcol, int pat, int mode, int sl) {
+                mbar_wait(bar_full + 8 * sl, cnt[sl] & 1);
+                ++cnt[sl];
                 tc_fence_after();
-                const uint32_t bslot = Bring + s * slotb;
+                const uint32_t bslot = slot_addr(sl);
                 bool first = mode != 1;
                 for (int q = 0; q < nkb; ++q) {
                     const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
@@ -151,23 +157,22 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
                     __syncwarp();
                     first = false;
                 }
-                if (elect_one()) mma_commit(bar_empty + 8 * s);
+                if (elect_one()) mma_commit(bar_empty + 8 * sl);
                 __syncwarp();
-                if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
             };
             auto commit = [&](uint32_t bar) { if (elect_one()) mma_commit(bar); __syncwarp(); };
             // G1: b = Linv k   (3xTF32)
             mbar_wait(bar_a, 0);
             tc_fence_after();
-            do_block(0u, tcp::PAT_LE, 0);
-            do_block(0u, tcp::PAT_LE, 1);
+            do_block(0u, tcp::PAT_LE, 0, 0);
+            do_block(0u, tcp::PAT_LE, 1, 1);
             commit(bar_acc);
             if (!P.white) {
                 // G1': u = Linv^T b   (3xTF32)
                 mbar_wait(bar_a + 8, 0);
                 tc_fence_after();
-                do_block(128u, tcp::PAT_GE, 0);
-                do_block(128u, tcp::PAT_GE, 1);
+                do_block(128u, tcp::PAT_GE, 0, 0);
+                do_block(128u, tcp::PAT_GE, 1, 1);
                 commit(bar_acc + 8);
             }
             // G2: c_d = L_d^T u   (1xTF32), accumulators double-buffered
@@ -175,7 +180,7 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
             tc_fence_after();
             for (int d = 0; d < D; ++d) {
                 if (d >= 2) { mbar_wait(bar_acc2e + 8 * (d & 1), ((d >> 1) - 1) & 1); tc_fence_after(); }
-                do_block(256u + 128u * (uint32_t)(d & 1), tcp::PAT_GE, 2);
+                do_block(256u + 128u * (uint32_t)(d & 1), tcp::PAT_GE, 2, three ? (2 + d) % 3 : d & 1);
                 commit(bar_acc2f + 8 * (d & 1));
             }
         }
@@ -480,7 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_chain_fwd_tc(const __grid_con
     if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-static size_t tc_fwd_smem(int M, int Din, int D) { return 1024 + 131072 + TC_NSTAGE * (size_t)tcp::slot_bytes(M) + 256 + 1024 + sizeof(float) * ((size_t)M * Din + (size_t)M * D + 8); }
+static size_t tc_fwd_smem(int M, int Din, int D) { return 1024 + 131072 + 2 * (size_t)tcp::slot_bytes(M) + 256 + 1024 + sizeof(float) * ((size_t)M * Din + (size_t)M * D + 8); }
 
 bool tc_fwd_supported(const LayerDev& P) {
     return P.M <= 128 && P.M >= 8 && P.Din <= 16 && P.Dout <= 32 && P.wpack_fwd != nullptr &&
