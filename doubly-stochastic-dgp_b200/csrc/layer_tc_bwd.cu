@@ -44,13 +44,16 @@ __host__ __device__ inline BwdSmem bwd_smem_plan(int M, int Din, int D) {
     return s;
 }
 
-template <int DINP, int DOUTP>
+// DINP == D_in and DOUTP == D_out exactly, kernel type and whitening are compile-time: the kernel is I-cache sensitive
+// (measured 21% "no instruction" stalls with the generic 13k-instruction body), other shapes use layer_simt.cu.
+template <int DINP, int DOUTP, int KERN, bool WHITE>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdArgs a) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw_b[];
     const uint32_t sbase = (smem_u32(smem_raw_b) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw_b + (sbase - smem_u32(smem_raw_b));
-    const int M = P.M, Din = P.Din, D = P.Dout;
+    const int M = P.M;
+    constexpr int Din = DINP, D = DOUTP;
     const BwdSmem sp = bwd_smem_plan(M, Din, D);
     const uint32_t A_u = sbase + sp.A_u, A_c = sbase + sp.A_c, Bring = sbase + sp.Bring, bars = sbase + sp.bars;
     const uint32_t bar_full = bars, bar_empty = bars + 32;
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             load(tcp::blk_g2(0), tcp::PAT_GE);
             if (D > 1) load(tcp::blk_g2(1), tcp::PAT_GE);
             for (int d = 0; d < D; ++d) { load(tcp::blk_g5(D, d), tcp::PAT_LE); if (d + 2 < D) load(tcp::blk_g2(d + 2), tcp::PAT_GE); }
-            if (!P.white) { load(tcp::blk_g1(0), tcp::PAT_LE); load(tcp::blk_g1(1), tcp::PAT_LE); }
+            if (!WHITE) { load(tcp::blk_g1(0), tcp::PAT_LE); load(tcp::blk_g1(1), tcp::PAT_LE); }
             load(tcp::blk_g1p(0), tcp::PAT_GE); load(tcp::blk_g1p(1), tcp::PAT_GE);
         }
     } else if (warp == 9) {
@@ -118,13 +121,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             mbar_wait(bar_full + 8 * s, ph);
             tc_fence_after();
             const uint32_t bslot = Bring + s * slotb;
+            uint32_t boff = 0;
+#pragma unroll 1
             for (int q = 0; q < nkb; ++q) {
                 const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
                 const int nks = min(4, (M - 32 * kb + 7) / 8);
-                const uint32_t bbase = bslot + tcp::band_offset(pat, M, kb), abase = kb * TC_CHUNK_BYTES;
-                const uint32_t id = make_idesc_tf32(128, tcp::band_rows(pat, M, kb));
+                const int nrows = tcp::band_rows(pat, M, kb);
+                const uint32_t bbase = bslot + boff, abase = kb * TC_CHUNK_BYTES;
+                boff += 128u * (uint32_t)nrows;
+                const uint32_t id = make_idesc_tf32(128, nrows);
                 const uint32_t dc = tmem + dcol + (uint32_t)tcp::band_row0(pat, kb);
                 if (tc::elect_one()) {
+#pragma unroll 1
                     for (int ks = 0; ks < nks; ++ks) {
                         const uint64_t bd = mkdesc(bbase + ks * 32);
                         mma_tf32(dc, mkdesc(Ahi + abase + ks * 32), bd, id, (fresh && q == 0 && ks == 0) ? 0u : 1u);
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             if (d == D - 1) commit(bar_ubar);
             if (d + 2 < D) g2(d + 2);
         }
-        if (!P.white) {
+        if (!WHITE) {
             mbar_wait(bar_s6, 0);
             tc_fence_after();
             do_block(0u, A_c, A_u, tcp::PAT_LE, true, true);
@@ -208,29 +216,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             il[q] = q < Din ? 1.0f / P.ls[P.ard ? q : 0] : 0.f;
             if (half == 0 && q < Din) xs_s[t * Din + q] = x[q];
         }
-#pragma unroll
-        for (int dd = 0; dd < (DOUTP + 1) / 2; ++dd) {
-            const int d = 2 * dd + half;
-            if (d >= D) continue;
+#pragma unroll 1
+        for (int d = half; d < D; d += 2) {
             float m = 0.f, v = 0.f;
             if (valid) {
                 if (a.fbar) {
-                    float sd = sqrtf(fmaxf(a.Fvar[(size_t)row * D + d] + jit, 1e-30f));
-                    if (a.S_rep == 1) {
-                        int ss = row / a.N, n = row % a.N;
-                        float fb = a.fbar[(size_t)row * D + d];
-                        float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, ss + soff, n + noff, d);
-                        m = fb; v = fb * z / (2.f * sd);
-                    } else {
-                        float sz = 0.f;
-                        for (int ss = 0; ss < a.S_rep; ++ss) {
-                            size_t o = ((size_t)ss * a.N + row) * D + d;
-                            float fb = a.fbar[o];
-                            float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, ss + soff, row + noff, d);
-                            m += fb; sz = fmaf(fb, z, sz);
-                        }
-                        v = sz / (2.f * sd);
+                    // z: the draws of the forward pass (injected, or the Philox draws it stored)
+                    const float sd = sqrtf(fmaxf(a.Fvar[(size_t)row * D + d] + jit, 1e-30f));
+                    float sz = 0.f;
+#pragma unroll 1
+                    for (int ss = 0; ss < a.S_rep; ++ss) {
+                        const size_t o = ((size_t)ss * a.N * (a.S_rep > 1) + row) * D + d;
+                        const float fb = a.fbar[o];
+                        m += fb; sz = fmaf(fb, a.z[o], sz);
                     }
+                    v = sz / (2.f * sd);
                     a.mubar[(size_t)row * D + d] = m;
                     a.vbar[(size_t)row * D + d] = v;
                 } else {
@@ -242,18 +242,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             mv_s[t * 2 * D + D + d] = v;
         }
         // ---- R1: u (this half's columns) -> A_u as the G2 operand; loads are issued four chunks ahead of their use
-        const bool vec4 = (M & 3) == 0;
+        constexpr bool vec4 = true;               // M % 4 == 0 (tc_bwd_supported)
         auto load_u4 = [&](int c0) -> float4 {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid && c0 < c_hi) {
-                if (vec4 && c0 + 4 <= M) v = *reinterpret_cast<const float4*>(a.U + (size_t)row * M + c0);
-                else {
-                    if (c0 < M) v.x = a.U[(size_t)row * M + c0];
-                    if (c0 + 1 < M) v.y = a.U[(size_t)row * M + c0 + 1];
-                    if (c0 + 2 < M) v.z = a.U[(size_t)row * M + c0 + 2];
-                    if (c0 + 3 < M) v.w = a.U[(size_t)row * M + c0 + 3];
-                }
-            }
+            if (valid && c0 < c_hi && c0 + 4 <= M) v = *reinterpret_cast<const float4*>(a.U + (size_t)row * M + c0);
             return v;
         };
         {
@@ -290,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         // ---- R2 (deferred, interleaved below): r2_i for this half's inducing points -> TMEM scratch columns 384+
         auto gram_chunk = [&](int c0) {
             float r2[8];
-            if (Din == DINP) {
+            {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int i = min(c0 + u, M - 1);
@@ -302,20 +294,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                         float d0 = (x[4 * q4] - zv.x) * il[4 * q4], d1 = (x[4 * q4 + 1] - zv.y) * il[4 * q4 + 1];
                         float d2 = (x[4 * q4 + 2] - zv.z) * il[4 * q4 + 2], d3 = (x[4 * q4 + 3] - zv.w) * il[4 * q4 + 3];
                         s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d2, d2, s); s = fmaf(d3, d3, s);
-                    }
-                    r2[u] = s;
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int i = min(c0 + u, M - 1);
-                    float s = 0.f;
-#pragma unroll
-                    for (int q = 0; q < DINP; ++q) {
-                        if (q < Din) {
-                            float dd = (x[q] - Zs[i * Din + q]) * il[q];
-                            s = fmaf(dd, dd, s);
-                        }
                     }
                     r2[u] = s;
                 }
@@ -355,12 +333,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         tc_fence_after();
         BSTAMP();   // 27: Ubar ready
         {
-            float4 ua = P.white ? load_u4(c_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 ub4 = P.white ? load_u4(c_lo + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ua = WHITE ? load_u4(c_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ub4 = WHITE ? load_u4(c_lo + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
             for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
                 float4 na = ua, nb4 = ub4;
-                if (P.white) { na = load_u4(c0 + 8); nb4 = load_u4(c0 + 12); }
+                if (WHITE) { na = load_u4(c0 + 8); nb4 = load_u4(c0 + 12); }
                 float ub[8], r2[8];
                 __syncwarp();
                 tmem_ld8(lane_addr + 256 + c0, ub);
@@ -390,10 +368,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
 #pragma unroll
                             for (int d = 0; d < DOUTP; ++d) if (d < D) acc = fmaf(mub[d], qmu_s[i * D + d], acc);
                         }
-                        if (P.white) acc -= 2.f * vs * uloc[u];
+                        if (WHITE) acc -= 2.f * vs * uloc[u];
                         else {
                             float k, kp;
-                            kern_eval_fast(P.kern, r2[u], var0, k, kp);
+                            kern_eval_fast(KERN, r2[u], var0, k, kp);
                             acc -= vs * k;
                         }
                     }
@@ -406,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         }
         tc_fence_before();
         fence_proxy_async();
-        if (!P.white) {
+        if (!WHITE) {
             mbar_arrive(bar_s6);
             BSTAMP();   // 28: R4 done
             // ---- R5: t = Linv ubar -> operands of the second triangular product
@@ -432,12 +410,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         float s2 = 0.f;
         const float inv_var = 1.0f / var0;
         {
-            float4 ua = !P.white ? load_u4(c_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 ub4 = !P.white ? load_u4(c_lo + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ua = !WHITE ? load_u4(c_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ub4 = !WHITE ? load_u4(c_lo + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
             for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
                 float4 na = ua, nb4 = ub4;
-                if (!P.white) { na = load_u4(c0 + 8); nb4 = load_u4(c0 + 12); }
+                if (!WHITE) { na = load_u4(c0 + 8); nb4 = load_u4(c0 + 12); }
                 float w[8], r2[8];
                 __syncwarp();
                 tmem_ld8(lane_addr + 128 + c0, w);
@@ -459,9 +437,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                     const int i = c0 + u;
                     if (i < M) {
                         float kb_ = w[u];
-                        if (!P.white) kb_ -= vs * uloc[u];
+                        if (!WHITE) kb_ -= vs * uloc[u];
                         float k, kp;
-                        kern_eval_fast(P.kern, r2[u], var0, k, kp);
+                        kern_eval_fast(KERN, r2[u], var0, k, kp);
                         s2 = fmaf(kb_ * k, inv_var, s2);
                         g_s[t * MP + i] = 2.f * kb_ * kp;
                     }
@@ -487,7 +465,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             float accq[DINP];
 #pragma unroll
             for (int q = 0; q < DINP; ++q) accq[q] = 0.f;
-            if (Din == DINP) {
+            {
 #pragma unroll 4
                 for (int i = 0; i < M; ++i) {
                     const float g = g_s[t * MP + i];
@@ -502,13 +480,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                             if ((q & 1) == half) accq[q] = fmaf(g, x[q] - zz[e], accq[q]);
                         }
                     }
-                }
-            } else {
-                for (int i = 0; i < M; ++i) {
-                    const float g = g_s[t * MP + i];
-#pragma unroll
-                    for (int q = 0; q < DINP; ++q)
-                        if (q < Din && (q & 1) == half) accq[q] = fmaf(g, x[q] - Zs[i * Din + q], accq[q]);
                 }
             }
 #pragma unroll
@@ -535,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                 float zi[DINP];
 #pragma unroll
                 for (int q = 0; q < DINP; ++q) { sa[q] = 0.f; sb[q] = 0.f; zi[q] = q < Din ? Zs[i * Din + q] : 0.f; }
-                if (Din == DINP) {
+                {
 #pragma unroll 4
                     for (int r = rh * 64; r < rh * 64 + 64; ++r) {
                         const float g = g_s[r * MP + i];
@@ -549,18 +520,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                                 const float dd = xx[e] - zi[4 * q4 + e];
                                 sa[4 * q4 + e] = fmaf(g, dd, sa[4 * q4 + e]);
                                 sb[4 * q4 + e] = fmaf(g * dd, dd, sb[4 * q4 + e]);
-                            }
-                        }
-                    }
-                } else {
-                    for (int r = rh * 64; r < rh * 64 + 64; ++r) {
-                        const float g = g_s[r * MP + i];
-#pragma unroll
-                        for (int q = 0; q < DINP; ++q) {
-                            if (q < Din) {
-                                const float dd = xs_s[r * Din + q] - zi[q];
-                                sa[q] = fmaf(g, dd, sa[q]);
-                                sb[q] = fmaf(g * dd, dd, sb[q]);
                             }
                         }
                     }
@@ -599,17 +558,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-#define TC_BWD_INSTANCES(X) X(8, 1) X(8, 8) X(16, 1) X(16, 8)
+// (DINP, DOUTP, KERN, WHITE) instances
+#define TC_BWD_INSTANCES(X) \
+    X(8, 1, 0, false) X(8, 1, 0, true) X(8, 1, 1, false) X(8, 1, 1, true) \
+    X(8, 8, 0, false) X(8, 8, 0, true) X(8, 8, 1, false) X(8, 8, 1, true)
 
 bool tc_bwd_supported(const LayerDev& P) {
-    if (!(P.M <= 128 && P.M >= 8 && P.Din <= 16 && P.Dout <= 8 && P.wpack_fwd != nullptr)) return false;
-    if (P.ard && P.Din > 32) return false;
+    if (!(P.M <= 128 && P.M >= 8 && (P.M & 3) == 0 && P.wpack_fwd != nullptr)) return false;
+    if (P.Din != 8 || !(P.Dout == 1 || P.Dout == 8)) return false;      // compile-time shapes (see the kernel comment)
     return bwd_smem_plan(P.M, P.Din, P.Dout).total + 1024 <= 227 * 1024;
 }
 
 cudaError_t layer_tc_bwd_init() {
     cudaError_t e;
-#define X(a_, b_) if ((e = cudaFuncSetAttribute(k_layer_bwd_tc<a_, b_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))) return e;
+#define X(a_, b_, k_, w_) if ((e = cudaFuncSetAttribute(k_layer_bwd_tc<a_, b_, k_, w_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))) return e;
     TC_BWD_INSTANCES(X)
 #undef X
     return cudaSuccess;
@@ -618,8 +580,8 @@ cudaError_t layer_tc_bwd_init() {
 void launch_bwd_rows_tc(const LayerDev& P, const BwdArgs& a, cudaStream_t st, long long* nl) {
     int grid = (a.R + TC_ROWS - 1) / TC_ROWS;
     size_t sm = bwd_smem_plan(P.M, P.Din, P.Dout).total + 1024;
-    int dinp = P.Din <= 8 ? 8 : 16, doutp = P.Dout <= 1 ? 1 : 8;
-#define X(a_, b_) if (dinp == a_ && doutp == b_) k_layer_bwd_tc<a_, b_><<<grid, TC_THREADS, sm, st>>>(P, a);
+    const bool wh = P.white != 0;
+#define X(a_, b_, k_, w_) if (P.Din == a_ && P.Dout == b_ && P.kern == k_ && wh == w_) k_layer_bwd_tc<a_, b_, k_, w_><<<grid, TC_THREADS, sm, st>>>(P, a);
     TC_BWD_INSTANCES(X)
 #undef X
     *nl += 1;
