@@ -424,7 +424,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     if (any_tc) launch_pack_fwd(c->ls, st, nl);
     PROF_END(0);
     // forward
-    const bool chain = c->chain && c->path == 1 && !prof && mode != MODE_PROPAGATE && tc_chain_fwd_supported(c->ls);
+    const bool chain = c->chain && c->path == 1 && mode != MODE_PROPAGATE && tc_chain_fwd_supported(c->ls);
     FwdChain fc;
     fc.L = L; fc.max_tiles = c->chain_max_tiles; fc.flags = c->chain_flags; fc.sa = c->sa_dev; fc.base[0] = 0;
     for (int l = 0; l < L; ++l) {
@@ -448,7 +448,11 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         else launch_fwd(c->ls.l[l], a, c->num_sms, st, nl);
         PROF_END(5 + 3 * l);
     }
-    if (chain) launch_chain_fwd_tc(c->ls, fc, c->num_sms, st, nl);
+    if (chain) {          // profile mode: the whole chain is reported in the first layer's forward slot
+        PROF_BEGIN(5);
+        launch_chain_fwd_tc(c->ls, fc, c->num_sms, st, nl);
+        PROF_END(5);
+    }
     if (mode == MODE_PROPAGATE) return DSDGP_OK;
     // likelihood
     const int Rlast = (L == 1) ? N : N * S;

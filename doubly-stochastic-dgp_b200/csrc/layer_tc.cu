@@ -141,13 +141,18 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
                 tc_fence_after();
                 const uint32_t bslot = slot_addr(sl);
                 bool first = mode != 1;
+                uint32_t boff = 0;
+#pragma unroll 1
                 for (int q = 0; q < nkb; ++q) {
                     const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
                     const int nks = min(4, (M - 32 * kb + 7) / 8);
-                    const uint32_t bbase = bslot + tcp::band_offset(pat, M, kb), abase = kb * TC_CHUNK_BYTES;
-                    const uint32_t id = make_idesc_tf32(128, tcp::band_rows(pat, M, kb));
+                    const int nrows = tcp::band_rows(pat, M, kb);
+                    const uint32_t bbase = bslot + boff, abase = kb * TC_CHUNK_BYTES;
+                    boff += 128u * (uint32_t)nrows;
+                    const uint32_t id = make_idesc_tf32(128, nrows);
                     const uint32_t dc = tmem + dcol + (uint32_t)tcp::band_row0(pat, kb);
                     if (elect_one()) {
+#pragma unroll 1
                         for (int ks = 0; ks < nks; ++ks) {
                             const uint64_t bd = mkdesc(bbase + ks * 32), ah = mkdesc(A_hi + abase + ks * 32);
                             mma_tf32(dc, ah, bd, id, (first && ks == 0) ? 0u : 1u);
