@@ -69,6 +69,9 @@ struct dsdgp_ctx {
     size_t n_params;                 // trainables + lik variance slot
     float *params, *grads /* n_params + 2 */, *free_, *adam_m, *adam_v;
     unsigned char* kinds;
+    std::vector<unsigned char> kinds_base;   // structural kinds (host); device kinds = base, or 4 where set untrainable
+    std::vector<unsigned char> kinds_host;
+    double* ng_ws; size_t ng_ws_n; int* ng_status;   // natural-gradient workspace (lazily sized)
     std::vector<LayerOff> off;
     size_t off_likvar;
     float* meanW[DSDGP_MAX_LAYERS];
@@ -198,6 +201,9 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     CK(layer_tc_bwd_init());
     CK(rowred_tc_init());
     CK(small_matrix_init());
+    CK(natgrad_init());
+    c->ng_ws = nullptr; c->ng_ws_n = 0;
+    CK(dmalloc(&c->ng_status, 1));
 
     const int L = desc->L;
     // ---- parameter layout
@@ -239,6 +245,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
         }
         kinds[c->off_likvar] = desc->likelihood == DSDGP_LIK_GAUSSIAN ? 1 : 4;
         init[c->off_likvar] = 1.f;
+        c->kinds_base = kinds; c->kinds_host = kinds;
         CK(cudaMemcpy(c->kinds, kinds.data(), n, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->params, init.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -320,7 +327,7 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     float* fl[] = {c->params, c->grads, c->free_, c->adam_m, c->adam_v, c->sm32, c->accf, c->Xd, c->Yd};
     for (float* p : fl) cudaFree(p);
-    cudaFree(c->chain_flags); cudaFree(c->dbg_buf);
+    cudaFree(c->chain_flags); cudaFree(c->dbg_buf); cudaFree(c->ng_ws); cudaFree(c->ng_status);
     cudaFree(c->kinds); cudaFree(c->sm64); cudaFree(c->sa_dev); cudaFree(c->acc); cudaFree(c->result_dev);
     for (int l = 0; l < c->desc.L; ++l) {
         float* pl[] = {c->U[l], c->Fmean[l], c->Fvar[l], c->F[l], c->zs[l], c->xbar[l], c->meanW[l], c->meanB[l], c->wpack[l],
@@ -672,6 +679,75 @@ int dsdgp_train_step(dsdgp_ctx* c, const float* X, const float* Y, int N, int S,
                      const float* const* zs, uint64_t seed, unsigned flags, double* elbo) {
     return elbo_common(c, MODE_TRAIN, X, Y, N, S, num_data, zs, seed, flags, elbo);
 }
+int dsdgp_set_trainable(dsdgp_ctx* c, int layer, int field, int trainable) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    if (field == DSDGP_F_MEAN_W || field == DSDGP_F_MEAN_B) {
+        if (trainable) return set_err(DSDGP_ERR_UNSUPPORTED, "mean function parameters are fixed (layer_initializations.py:41-42)");
+        return DSDGP_OK;
+    }
+    if (field != DSDGP_F_LIK_VARIANCE && (layer < 0 || layer >= c->desc.L)) return set_err(DSDGP_ERR_INVALID, "layer %d out of range", layer);
+    if (field < 0 || field > DSDGP_F_LIK_VARIANCE) return set_err(DSDGP_ERR_INVALID, "field %d unknown", field);
+    if (field == DSDGP_F_LIK_VARIANCE && c->desc.likelihood != DSDGP_LIK_GAUSSIAN) return DSDGP_OK;
+    CK(cudaSetDevice(c->desc.device));
+    const size_t o = (size_t)field_offset(c, layer, field), n = field_count(c, layer, field);
+    for (size_t i = 0; i < n; ++i) c->kinds_host[o + i] = trainable ? c->kinds_base[o + i] : (c->kinds_base[o + i] == 3 ? 3 : 4);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(c->kinds + o, c->kinds_host.data() + o, n, cudaMemcpyHostToDevice));
+    // re-derive the unconstrained copy of this field from its current value when it becomes trainable (again)
+    if (trainable) c->free_dirty = true;
+    return DSDGP_OK;
+}
+
+int dsdgp_natgrad_step(dsdgp_ctx* c, const float* X, const float* Y, int N, int S, double num_data, const float* const* zs,
+                       uint64_t seed, unsigned flags, const int* layers, int n_layers, double gamma, double* elbo) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    if (!layers || n_layers < 1) return set_err(DSDGP_ERR_INVALID, "natgrad: empty layer list");
+    if (!(gamma > 0.0) || !(gamma <= 1.0)) return set_err(DSDGP_ERR_INVALID, "natgrad: gamma=%g outside (0, 1]", gamma);
+    size_t need = 0;
+    for (int i = 0; i < n_layers; ++i) {
+        if (layers[i] < 0 || layers[i] >= c->desc.L) return set_err(DSDGP_ERR_INVALID, "natgrad: layer %d out of range", layers[i]);
+        for (int k = 0; k < i; ++k) if (layers[k] == layers[i]) return set_err(DSDGP_ERR_INVALID, "natgrad: layer %d listed twice", layers[i]);
+        const dsdgp_layer_desc& d = c->desc.layers[layers[i]];
+        need = max(need, natgrad_ws_doubles(d.M, d.D_out));
+    }
+    CK(cudaSetDevice(c->desc.device));
+    if (need > c->ng_ws_n) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->ng_ws) CK(cudaFree(c->ng_ws));
+        c->ng_ws = nullptr; c->ng_ws_n = 0;
+        CK(dmalloc(&c->ng_ws, need));
+        c->ng_ws_n = need;
+    }
+    // ELBO + gradient pass: fills the row-reduced accumulators P_d, qmubar (and Kinv) the update is built from
+    double e = 0.0;
+    int rc = elbo_common(c, MODE_GRAD, X, Y, N, S, num_data, zs, seed, flags, &e);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(c->ng_status, 0, sizeof(int), c->stream));
+    for (int i = 0; i < n_layers; ++i) {
+        const int l = layers[i];
+        const LayerDev& P = c->ls.l[l];
+        const dsdgp_layer_desc& d = c->desc.layers[l];
+        const size_t mm = (size_t)d.M * d.M;
+        if (c->comm) {      // accumulators are per-rank partial sums over this rank's rows: [P_d | G | qmubar] is one block
+            int e2 = g_nccl.AllReduce(P.Pd, P.Pd, (size_t)d.D_out * mm + mm + (size_t)d.M * d.D_out, NCCL_FLOAT, NCCL_SUM, c->comm, c->stream);
+            if (e2) return set_err(DSDGP_ERR_NCCL, "natgrad ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e2) : "?");
+        }
+        launch_natgrad_layer(P, gamma, c->ng_ws, c->ng_status, c->params + c->off[l].q_mu, c->params + c->off[l].q_sqrt,
+                             c->stream, &c->nlaunch);
+        if (c->adam_on) {   // keep Adam's unconstrained copy of these (identity-transformed) fields in step
+            CK(cudaMemcpyAsync(c->free_ + c->off[l].q_mu, c->params + c->off[l].q_mu, (size_t)d.M * d.D_out * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->free_ + c->off[l].q_sqrt, c->params + c->off[l].q_sqrt, (size_t)d.D_out * mm * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
+    CK(cudaGetLastError());
+    int st_host = 0;
+    CK(cudaMemcpyAsync(&st_host, c->ng_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (st_host) return set_err(DSDGP_ERR_NOT_PD, "natgrad: a natural-parameter precision (or S) was not positive definite; (q_mu, q_sqrt) of the affected layer were left unchanged (gamma=%g too large for a non-conjugate layer?)", gamma);
+    if (elbo) *elbo = e;
+    return DSDGP_OK;
+}
+
 int dsdgp_timer_start(dsdgp_ctx* c) {
     if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
     CK(cudaSetDevice(c->desc.device));

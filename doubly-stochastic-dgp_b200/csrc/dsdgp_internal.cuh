@@ -212,5 +212,9 @@ void launch_adam(float* params, float* free_, float* m, float* v, const float* g
                  const int* tril_m, size_t n, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
 void launch_constrain_init(const float* params, float* free_, const unsigned char* kinds, size_t n, cudaStream_t st,
                            long long* nlaunch);
+cudaError_t natgrad_init();
+size_t natgrad_ws_doubles(int M, int D);
+void launch_natgrad_layer(const LayerDev& P, double gamma, double* ws, int* status, float* q_mu, float* q_sqrt,
+                          cudaStream_t st, long long* nlaunch);
 size_t fwd_smem_bytes(int M, int Din, int TR);
 size_t bwd_smem_bytes(int M, int Din, int TR);

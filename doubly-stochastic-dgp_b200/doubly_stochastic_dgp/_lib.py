@@ -37,7 +37,7 @@ SYMBOLS = ["dsdgp_last_error", "dsdgp_version", "dsdgp_create", "dsdgp_destroy",
            "dsdgp_get_param", "dsdgp_get_grad", "dsdgp_propagate", "dsdgp_elbo", "dsdgp_elbo_grad",
            "dsdgp_adam_init", "dsdgp_train_step", "dsdgp_kl", "dsdgp_comm_unique_id", "dsdgp_comm_init", "dsdgp_sync",
            "dsdgp_launch_count", "dsdgp_last_step_ms", "dsdgp_set_option", "dsdgp_timer_start",
-           "dsdgp_timer_stop", "dsdgp_profile"]
+           "dsdgp_timer_stop", "dsdgp_profile", "dsdgp_set_trainable", "dsdgp_natgrad_step"]
 
 
 def lib_path():
@@ -67,6 +67,9 @@ def load():
     lib.dsdgp_adam_init.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.dsdgp_train_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                      C.c_uint64, C.c_uint, DP]
+    lib.dsdgp_set_trainable.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.dsdgp_natgrad_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                       C.c_uint64, C.c_uint, C.POINTER(C.c_int), C.c_int, C.c_double, DP]
     lib.dsdgp_timer_start.argtypes = [C.c_void_p]
     lib.dsdgp_timer_stop.argtypes = [C.c_void_p, FP]
     lib.dsdgp_profile.argtypes = [C.c_void_p, FP, C.c_int]
@@ -199,6 +202,19 @@ class Context:
         check(self.lib.dsdgp_train_step(self.h, _ptr(X), _ptr(Y), N, S, float(num_data), zarr, seed, flags,
                                         C.byref(e) if want_elbo else None))
         return e.value if want_elbo else None
+
+    def set_trainable(self, layer, field, flag):
+        check(self.lib.dsdgp_set_trainable(self.h, layer, field, int(bool(flag))))
+
+    def natgrad_step(self, X, Y, N, S, num_data, seed, layers, gamma, flags=0, zs=None):
+        """ELBO + gradient pass, then the natural-gradient update of (q_mu, q_sqrt) of `layers`; returns the ELBO."""
+        e = C.c_double()
+        zs32 = None if zs is None else [None if z is None else (z if isinstance(z, int) else f32(z)) for z in zs]
+        zarr, _ = _ptr_array(zs32, self.L)
+        ids = (C.c_int * len(layers))(*[int(l) for l in layers])
+        check(self.lib.dsdgp_natgrad_step(self.h, _ptr(X), _ptr(Y), N, S, float(num_data), zarr, seed, flags, ids,
+                                          len(layers), float(gamma), C.byref(e)))
+        return e.value
 
     def timer_start(self):
         check(self.lib.dsdgp_timer_start(self.h))

@@ -55,6 +55,7 @@ class DGP_Base(Parameterized):
         self._device = device
         self._ctx = None
         self._host_dirty = True
+        self._trainable_dirty = True
         self._device_newer = False
         self._seed = 0x5D6A1
         self._adam = None
@@ -78,6 +79,20 @@ class DGP_Base(Parameterized):
 
     def _mark_host_dirty(self):
         self._host_dirty = True
+
+    def _mark_trainable_dirty(self):
+        self._trainable_dirty = True
+
+    def _param_fields(self):
+        """(layer index, C-ABI field, Parameter) of every trainable-capable parameter."""
+        out = []
+        for i, l in enumerate(self.layers):
+            out += [(i, _lib.F_Z, l.feature.Z), (i, _lib.F_Q_MU, l.q_mu), (i, _lib.F_Q_SQRT, l.q_sqrt),
+                    (i, _lib.F_LENGTHSCALES, l.kern.lengthscales), (i, _lib.F_VARIANCE, l.kern.variance)]
+        lik = self.likelihood.likelihood
+        if isinstance(lik, Gaussian):
+            out.append((-1, _lib.F_LIK_VARIANCE, lik.variance))
+        return out
 
     def _refresh_from_device(self):
         if not self._device_newer or self._ctx is None:
@@ -122,6 +137,7 @@ class DGP_Base(Parameterized):
             S_max = max(S, self.num_samples, 8)
             self._ctx = _lib.Context(self._layer_descs(), lik.code, K, D_y, float(settings.jitter), N_max, S_max,
                                      device=self._device)
+            self._trainable_dirty = True
             if self._comm is not None:
                 self._ctx.comm_init(*self._comm)
             self._host_dirty = True
@@ -140,6 +156,10 @@ class DGP_Base(Parameterized):
             if isinstance(lik, Gaussian):
                 c.set_param(-1, _lib.F_LIK_VARIANCE, lik.variance._value)
             self._host_dirty = False
+        if self._trainable_dirty:
+            for i, field, p in self._param_fields():
+                self._ctx.set_trainable(i, field, p.trainable)
+            self._trainable_dirty = False
         return self._ctx
 
     def _next_seed(self):
@@ -234,6 +254,32 @@ class DGP_Base(Parameterized):
                            zs=zs)
         self._device_newer = True
         return e
+
+    def natgrad_step(self, var_list=None, gamma=1.0, X=None, Y=None, zs=None):
+        """NatGradOptimizer(gamma).minimize(model, var_list=var_list, maxiter=1) (tests/test_collapsed.py:99-100):
+        one ELBO+gradient pass on the (next) minibatch, then the natural-gradient update of every [q_mu, q_sqrt] pair
+        in var_list (default: the last layer's).  Returns the ELBO before the update."""
+        ids = self._natgrad_layers(var_list)
+        if X is None:
+            X, Y = self._minibatch()
+        ctx = self._ensure_ctx(X.shape[0], self.num_samples)
+        e = ctx.natgrad_step(_lib.f32(X), _lib.f32(Y), X.shape[0], self.num_samples, self.num_data, self._next_seed(),
+                             ids, gamma, zs=zs)
+        self._device_newer = True
+        return e
+
+    def _natgrad_layers(self, var_list):
+        if var_list is None:
+            return [len(self.layers) - 1]
+        ids = []
+        for pair in var_list:
+            if len(pair) != 2:
+                raise ValueError("var_list entries must be [q_mu, q_sqrt] pairs")
+            hit = [i for i, l in enumerate(self.layers) if pair[0] is l.q_mu and pair[1] is l.q_sqrt]
+            if not hit:
+                raise ValueError("var_list entry is not the (q_mu, q_sqrt) of a layer of this model")
+            ids.append(hit[0])
+        return ids
 
     def minimize(self, maxiter=1000, lr=0.01):
         if self._adam is None:

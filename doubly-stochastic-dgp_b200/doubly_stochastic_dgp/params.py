@@ -37,7 +37,11 @@ class Parameter:
             self._owner._mark_host_dirty()
 
     def set_trainable(self, flag):
+        """gpflow Parameter.set_trainable: an untrainable parameter is left alone by AdamOptimizer
+        (demos/using_natural_gradients.ipynb takes the NatGrad-managed q_mu, q_sqrt away from Adam this way)."""
         self.trainable = bool(flag)
+        if self._owner is not None:
+            self._owner._mark_trainable_dirty()
 
     def __array__(self, dtype=None, copy=None):
         v = self.read_value()

@@ -133,6 +133,19 @@ DSDGP_API int dsdgp_adam_init(dsdgp_ctx* ctx, double lr, double beta1, double be
 DSDGP_API int dsdgp_train_step(dsdgp_ctx* ctx, const float* X, const float* Y, int N, int S, double num_data,
                      const float* const* zs, uint64_t seed, unsigned flags, double* elbo);
 
+/* param.set_trainable(flag) (demos/using_natural_gradients.ipynb: the NatGrad-managed q_mu, q_sqrt are taken away
+ * from Adam): an untrainable field is skipped by dsdgp_train_step's Adam update; its gradient is still computed. */
+DSDGP_API int dsdgp_set_trainable(dsdgp_ctx* ctx, int layer, int field, int trainable);
+
+/* gpflow.training.NatGradOptimizer(gamma).minimize(model, var_list=[[q_mu, q_sqrt] of each listed layer], maxiter=1)
+ * (tests/test_collapsed.py:99-100, demos/demo_regression_UCI.ipynb:357-366): one ELBO+gradient pass on the minibatch,
+ * then theta <- theta - gamma * d(-ELBO)/d eta in natural parameters (default XiNat), fp64, for every output dimension
+ * of the n_layers layers listed in layers[].  elbo = the value before the update.  0 < gamma <= 1.
+ * DSDGP_ERR_NOT_PD: the updated precision was not positive definite (that layer's q is left unchanged). */
+DSDGP_API int dsdgp_natgrad_step(dsdgp_ctx* ctx, const float* X, const float* Y, int N, int S, double num_data,
+                       const float* const* zs, uint64_t seed, unsigned flags, const int* layers, int n_layers,
+                       double gamma, double* elbo);
+
 /* NCCL communicator for row-sharded data parallelism (no counterpart in the reference).
  * id = 128-byte ncclUniqueId produced by dsdgp_comm_unique_id on rank 0 and broadcast by the host. */
 DSDGP_API int dsdgp_comm_unique_id(void* id128);

@@ -574,3 +574,58 @@ class AdamState:
                 else:
                     p.copy_(self.free[i])
         return elbo
+
+
+# ----------------------------------------------------------------------------
+# Natural-gradient step on (q_mu, q_sqrt) of chosen layers.  The reference calls
+# gpflow.training.NatGradOptimizer(gamma).minimize(model, var_list=[[q_mu, q_sqrt]], maxiter=1)
+# (tests/test_collapsed.py:99-100, demos/using_natural_gradients.ipynb "ng_action",
+# demos/demo_regression_UCI.ipynb:357-366).  GPflow 1.1.1 is not in /root/reference; this is a
+# restatement of its published algorithm (training/natgrad_optimizer.py, default XiNat
+# parameterisation; Salimbeni, Eleftheriadis & Hensman 2018, "Natural gradients in practice"):
+#   eta = (m, S + m m^T),  theta = (S^-1 m, -1/2 S^-1)
+#   dL/d eta  by back-propagating (dL/dq_mu, dL/dq_sqrt) through eta -> (eta1, chol(eta2 - eta1 eta1^T))
+#   theta <- theta - gamma dL/d eta           (L = -ELBO)
+#   (q_mu, q_sqrt) <- natural_to_meanvarsqrt(theta): C = chol(-2 theta2), V = C^-1, S = V^T V,
+#                      m = S theta1, q_sqrt = chol(S)
+# Pinned by identity I6 (gamma = 1 on a Gaussian-likelihood last layer lands on the SGPR optimum,
+# tests/test_collapsed.py:57-104) in tests/test_oracle_identities.py / tests/test_natgrad_cpu.py.
+# ----------------------------------------------------------------------------
+def natgrad_step(model, layer_ids, gamma, X=None, Y=None, zs=None):
+    """One NatGrad step on the listed layers; returns the ELBO before the update."""
+    elbo, grads = model.elbo_and_grad(X, Y, zs)
+    ps = model.parameters()
+    for li in layer_ids:
+        layer = model.layers[li]
+        i_mu = next(i for i, p in enumerate(ps) if p is layer.q_mu)
+        i_sq = next(i for i, p in enumerate(ps) if p is layer.q_sqrt)
+        dL_dmean = -grads[i_mu]                        # (M, D)
+        dL_dsqrt = -torch.tril(grads[i_sq])            # (D, M, M)  LowerTriangular transform: packed lower triangle
+        q_mu = layer.q_mu.detach()
+        q_sqrt = torch.tril(layer.q_sqrt.detach())
+        D, M = q_sqrt.shape[0], q_sqrt.shape[1]
+        new_mu = torch.empty_like(q_mu)
+        new_sqrt = torch.empty_like(q_sqrt)
+        for d in range(D):
+            m = q_mu[:, d:d + 1]
+            Lq = q_sqrt[d]
+            S = Lq @ Lq.T
+            eta1 = m.clone().requires_grad_(True)
+            eta2 = (S + m @ m.T).clone().requires_grad_(True)
+            mean = eta1
+            varsqrt = torch.linalg.cholesky(eta2 - eta1 @ eta1.T)
+            g1, g2 = torch.autograd.grad([mean, varsqrt], [eta1, eta2],
+                                         grad_outputs=[dL_dmean[:, d:d + 1], dL_dsqrt[d]])
+            g2 = 0.5 * (g2 + g2.T)
+            Sinv = torch.cholesky_inverse(torch.linalg.cholesky(S))
+            nat1 = Sinv @ m - gamma * g1
+            nat2 = -0.5 * Sinv - gamma * g2
+            C = torch.linalg.cholesky(-2.0 * nat2)
+            V = torch.linalg.solve_triangular(C, torch.eye(M, dtype=DT), upper=False)
+            S_new = V.T @ V
+            new_mu[:, d:d + 1] = S_new @ nat1
+            new_sqrt[d] = torch.linalg.cholesky(S_new)
+        with torch.no_grad():
+            layer.q_mu.copy_(new_mu)
+            layer.q_sqrt.copy_(new_sqrt)
+    return elbo

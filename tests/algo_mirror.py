@@ -168,7 +168,7 @@ def gaussian_lik(mean, var, Y, lik_var, c):
     return c * np.sum(ve), mubar, vbar, lvbar
 
 
-def elbo_and_grad(layers, X, Y, lik_var, S, zs, num_data, jitter, n_global=None, klw=1.0):
+def elbo_and_grad(layers, X, Y, lik_var, S, zs, num_data, jitter, n_global=None, klw=1.0, aux=None):
     """Full step in the kernels' order.  X (N,D), zs[l] (S,N,Dout_l).  Layer 1 is evaluated on the N
     distinct rows only (the reference's tile, dgp.py:63, makes its conditional S-fold redundant).
     n_global / klw: the row-sharded data-parallel protocol of csrc/api.cu -- this rank holds N of n_global minibatch
@@ -209,6 +209,8 @@ def elbo_and_grad(layers, X, Y, lik_var, S, zs, num_data, jitter, n_global=None,
         Xl, mean, var, u, sd = acts[l]
         xbar, w, Zb, lsb, s2b = layer_bwdA(P, Linv, Xl, u, mubar, vbar)
         Pd, G, qmub = layer_bwdB(u, w, mubar, vbar)
+        if aux is not None:                   # row-reduced accumulators, as csrc/natgrad.cu reads them
+            aux[l] = dict(Pd=Pd, qmubar=qmub, Kinv=Linv.T @ Linv)
         KL, gq_mu, gq_sqrt, Zb2, lsb2, s2b2 = layer_fin(P, K, Lu, Linv, Pd, G, qmub, klw=klw)
         KLs += KL
         lsg = lsb + lsb2
@@ -226,3 +228,36 @@ def elbo_and_grad(layers, X, Y, lik_var, S, zs, num_data, jitter, n_global=None,
                 mubar = fbar
                 vbar = fbar * zs[l - 1].reshape(S * N, -1) / (2.0 * psd)
     return Lval - klw * KLs, grads, lvbar
+
+
+def natgrad_update(P, Kinv, Pd, qmubar, gamma):
+    """csrc/natgrad.cu: natural-gradient step on (q_mu, q_sqrt) of one layer straight from the row-reduced
+    accumulators of the backward pass (summed over ranks), SURVEY App. B last paragraph:
+      dELBO/dS_d = P_d - 1/2 Prior^-1 + 1/2 S_d^-1 ,  dELBO/dm_d = qmubar_d - Prior^-1 m_d     (Prior = K, or I if white)
+      => -2 theta2' = (1-gamma) S^-1 + gamma (Prior^-1 - 2 P_d)
+            theta1' = (1-gamma) S^-1 m + gamma (qmubar_d - 2 P_d m)
+      then GPflow's natural_to_meanvarsqrt: C = chol(-2 theta2'), V = C^-1, S' = V^T V, m' = S' theta1', q_sqrt' = chol S'.
+    With gamma == 1 the old S drops out exactly (no S^-1 is formed)."""
+    M, D = P.M, P.Dout
+    prior_inv = np.eye(M) if P.white else Kinv
+    new_mu = np.empty_like(P.q_mu)
+    new_sqrt = np.empty_like(P.q_sqrt)
+    for d in range(D):
+        m = P.q_mu[:, d]
+        P2 = Pd[d] + Pd[d].T                   # 2 P_d, symmetrised as the kernel does (atomics)
+        if gamma == 1.0:
+            prec = prior_inv - P2
+            t1 = qmubar[:, d] - P2 @ m
+        else:
+            S = P.q_sqrt[d] @ P.q_sqrt[d].T
+            Ls = np.linalg.cholesky(S)
+            Li = np.linalg.inv(Ls)
+            Sinv = Li.T @ Li
+            prec = (1.0 - gamma) * Sinv + gamma * (prior_inv - P2)
+            t1 = (1.0 - gamma) * (Sinv @ m) + gamma * (qmubar[:, d] - P2 @ m)
+        C = np.linalg.cholesky(prec)
+        V = np.linalg.inv(C)
+        S_new = V.T @ V
+        new_mu[:, d] = S_new @ t1
+        new_sqrt[d] = np.linalg.cholesky(S_new)
+    return new_mu, new_sqrt

@@ -73,3 +73,45 @@ def test_uneven_shards_need_explicit_n_global():
                                   [z[:, lo:hi] for z in prob['zs']], prob['num_data'], prob['jitter'], n_global=11, klw=0.5)
         acc += e
     np.testing.assert_allclose(acc, full[0], rtol=1e-10)
+
+
+def _ng_worker(rank, world, port, kw, out):
+    """dsdgp_natgrad_step with a communicator: each rank all-reduces the layer's [P_d | G | qmubar] block (partial sums over
+    its rows; the KL part of the natural gradient is analytic and not reduced), then applies the update locally."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    prob = make_problem(**kw)
+    N = prob['N']
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    layers = _layers(prob)
+    aux = {}
+    A.elbo_and_grad(layers, prob['X'][lo:hi], prob['Y'][lo:hi], prob['lik_var'], prob['S'], [z[:, lo:hi] for z in prob['zs']],
+                    prob['num_data'], prob['jitter'], n_global=N, klw=1.0 / world, aux=aux)
+    l = len(layers) - 1
+    Pd, qb = torch.from_numpy(aux[l]['Pd'].copy()), torch.from_numpy(aux[l]['qmubar'].copy())
+    dist.all_reduce(Pd, op=dist.ReduceOp.SUM)
+    dist.all_reduce(qb, op=dist.ReduceOp.SUM)
+    mu, sq = A.natgrad_update(layers[l], aux[l]['Kinv'], Pd.numpy(), qb.numpy(), 1.0)
+    np.savez(f"{out}.{rank}.npz", mu=mu, sq=sq)
+    dist.destroy_process_group()
+
+
+def test_natgrad_on_allreduced_accumulators_matches_single_process(tmp_path):
+    kw = dict(seed=79, dims=[3, 3, 1], N=24, M=6, S=3, inner_q_scale=0.3, num_data=240)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "ng")
+    mp.spawn(_ng_worker, args=(2, port, kw, out), nprocs=2, join=True)
+    prob = make_problem(**kw)
+    layers = _layers(prob)
+    aux = {}
+    A.elbo_and_grad(layers, prob['X'], prob['Y'], prob['lik_var'], prob['S'], prob['zs'], prob['num_data'], prob['jitter'],
+                    aux=aux)
+    l = len(layers) - 1
+    mu, sq = A.natgrad_update(layers[l], aux[l]['Kinv'], aux[l]['Pd'], aux[l]['qmubar'], 1.0)
+    for rank in range(2):
+        got = np.load(f"{out}.{rank}.npz")
+        np.testing.assert_allclose(got['mu'], mu, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(got['sq'], sq, rtol=1e-8, atol=1e-10)
