@@ -633,6 +633,53 @@ int dsdgp_propagate(dsdgp_ctx* c, const float* X, int N, int S, const float* con
     return fetch_result(c, nullptr);
 }
 
+// DGP_Base.predict_y / predict_density (dgp.py:116-126): propagate, then the likelihood epilogue on the device.
+static int predict_common(dsdgp_ctx* c, const float* X, const float* Y, int N, int S, const float* const* zs, uint64_t seed,
+                          unsigned flags, float* out0, float* out1, bool density) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    if (!out0 || (!density && !out1)) return set_err(DSDGP_ERR_INVALID, "null output pointer");
+    if (density && !Y) return set_err(DSDGP_ERR_INVALID, "Y is null");
+    CK(cudaSetDevice(c->desc.device));
+    unsigned zmask;
+    int rc = stage_inputs(c, X, Y, N, S, zs, flags, &zmask);
+    if (rc) return rc;
+    rc = run_step(c, MODE_PROPAGATE, N, S, 1.0, zmask, seed);
+    if (rc) return rc;
+    const int L = c->desc.L, D = c->desc.layers[L - 1].D_out;
+    const bool dedup = (L == 1);                 // single layer: conditional evaluated on the N distinct rows (dgp.py:63)
+    const int R = dedup ? N : N * S;
+    const size_t per = (size_t)N * D;
+    cudaMemcpyKind kind = (flags & DSDGP_FLAG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const float* likvar = c->params + c->off_likvar;
+    if (!density) {
+        // mubar / vbar of the last layer are free in propagate mode: (R, D) scratch for the epilogue's outputs
+        launch_predict_y(c->desc.likelihood, c->Fmean[L - 1], c->Fvar[L - 1], R, D, likvar, c->mubar[L - 1], c->vbar[L - 1],
+                         c->stream, &c->nlaunch);
+        for (int which = 0; which < 2; ++which) {
+            float* dst = which ? out1 : out0;
+            const float* src = which ? c->vbar[L - 1] : c->mubar[L - 1];
+            if (dedup) for (int s = 0; s < S; ++s) CK(cudaMemcpyAsync(dst + (size_t)s * per, src, per * sizeof(float), kind, c->stream));
+            else CK(cudaMemcpyAsync(dst, src, (size_t)S * per * sizeof(float), kind, c->stream));
+        }
+    } else {
+        const int Do = c->desc.likelihood == DSDGP_LIK_GAUSSIAN ? D : 1;
+        launch_predict_density(c->desc.likelihood, c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, S, N, D, dedup ? 1 : 0, likvar,
+                               c->mubar[L - 1], c->stream, &c->nlaunch);
+        CK(cudaMemcpyAsync(out0, c->mubar[L - 1], (size_t)N * Do * sizeof(float), kind, c->stream));
+    }
+    CK(cudaGetLastError());
+    launch_result(c->acc, c->grads + c->n_params, 0, c->result_dev, c->stream, &c->nlaunch);
+    return fetch_result(c, nullptr);
+}
+int dsdgp_predict_y(dsdgp_ctx* c, const float* X, int N, int S, const float* const* zs, uint64_t seed, float* mean, float* var,
+                    unsigned flags) {
+    return predict_common(c, X, nullptr, N, S, zs, seed, flags, mean, var, false);
+}
+int dsdgp_predict_density(dsdgp_ctx* c, const float* X, const float* Y, int N, int S, const float* const* zs, uint64_t seed,
+                          float* out, unsigned flags) {
+    return predict_common(c, X, Y, N, S, zs, seed, flags, out, nullptr, true);
+}
+
 static int elbo_common(dsdgp_ctx* c, int mode, const float* X, const float* Y, int N, int S, double num_data,
                        const float* const* zs, uint64_t seed, unsigned flags, double* elbo) {
     if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");

@@ -212,6 +212,10 @@ void launch_adam(float* params, float* free_, float* m, float* v, const float* g
                  const int* tril_m, size_t n, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
 void launch_constrain_init(const float* params, float* free_, const unsigned char* kinds, size_t n, cudaStream_t st,
                            long long* nlaunch);
+void launch_predict_y(int lik, const float* Fmean, const float* Fvar, int R, int D, const float* lik_var, float* mean,
+                      float* var, cudaStream_t st, long long* nlaunch);
+void launch_predict_density(int lik, const float* Fmean, const float* Fvar, const float* Y, int S, int N, int D, int dedup,
+                            const float* lik_var, float* out, cudaStream_t st, long long* nlaunch);
 cudaError_t natgrad_init();
 size_t natgrad_ws_doubles(int M, int D);
 void launch_natgrad_layer(const LayerDev& P, double gamma, double* ws, int* status, float* q_mu, float* q_sqrt,

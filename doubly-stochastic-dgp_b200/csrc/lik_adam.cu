@@ -1,4 +1,4 @@
-// Likelihood expectations (+ their adjoints) and the optimiser step.
+// Likelihood expectations (+ their adjoints), the prediction-side likelihood epilogues, and the optimiser step.
 // Reference: utils.py:88-93 (BroadcastingLikelihood.variational_expectations -> gpflow Gaussian / MultiClass
 // RobustMax), dgp.py:88-98 (mean over S, sum, scale); Adam = tf.train.AdamOptimizer on GPflow's
 // unconstrained variables.
@@ -116,6 +116,107 @@ __global__ void k_lik_multiclass(const float* __restrict__ Fmean, const float* _
 void launch_lik_multiclass(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int K, float* mubar,
                            float* vbar, Accum* acc, const StepArgs* sa, int want_grad, cudaStream_t st, long long* nl) {
     k_lik_multiclass<<<(R + 127) / 128, 128, 0, st>>>(Fmean, Fvar, Y, R, N, K, mubar, vbar, acc, sa, want_grad);
+    *nl += 1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Prediction epilogues (dgp.py:116-126): likelihood.predict_mean_and_var / predict_density broadcast over the S samples
+// (utils.py:110-121), and the log-mean-exp over S of predict_density (dgp.py:124-126).  Rows r = s*N + n; when `dedup`
+// (single-layer model: the conditional was evaluated on the N distinct rows only) every s reads row n.
+// GPflow: Gaussian.predict_mean_and_var = (Fmu, Fvar + s2), predict_density = log N(Y; Fmu, Fvar + s2);
+// MultiClass(RobustMax): mean_k = P(k is largest), var = mean - mean^2, density = log(p (1-eps) + (1-p) eps/(K-1)).
+// ----------------------------------------------------------------------------------------------
+__device__ double mc_prob_is_largest(const float* __restrict__ mu_r, const float* __restrict__ var_r, int K, int y) {
+    double mu[MC_MAXK], sd[MC_MAXK];
+    for (int k = 0; k < K; ++k) {
+        double v = var_r[k];
+        if (v < 1e-10) v = 1e-10;
+        mu[k] = mu_r[k]; sd[k] = sqrt(v);
+    }
+    const double s2y = sqrt(2.0) * sd[y];
+    double p = 0.0;
+    for (int h = 0; h < 20; ++h) {
+        const double x = mu[y] + s2y * c_gh_x[h];
+        double prod = 1.0;
+        for (int k = 0; k < K; ++k) {
+            if (k == y) continue;
+            const double t = (x - mu[k]) / sd[k];
+            prod *= 0.5 * (1.0 + erf(t * 0.70710678118654752)) * (1.0 - 2e-4) + 1e-4;
+        }
+        p += c_gh_w[h] * 0.56418958354775628 * prod;
+    }
+    return p;
+}
+
+__global__ void k_predict_y_gaussian(const float* __restrict__ Fmean, const float* __restrict__ Fvar, size_t total,
+                                     const float* __restrict__ lik_var, float* __restrict__ mean, float* __restrict__ var) {
+    const float s2 = lik_var[0];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        mean[i] = Fmean[i];
+        var[i] = Fvar[i] + s2;
+    }
+}
+// one thread per (row, class)
+__global__ void k_predict_y_multiclass(const float* __restrict__ Fmean, const float* __restrict__ Fvar, int R, int K,
+                                       float* __restrict__ mean, float* __restrict__ var) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)R * K) return;
+    const int r = (int)(i / K), k = (int)(i % K);
+    const double p = mc_prob_is_largest(Fmean + (size_t)r * K, Fvar + (size_t)r * K, K, k);
+    mean[i] = (float)p;
+    var[i] = (float)(p - p * p);
+}
+// out (N, Dy): logsumexp_s(log N(y; mu_s, v_s + s2) - log S), streaming over s
+__global__ void k_density_gaussian(const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
+                                   int S, int N, int Dy, int dedup, const float* __restrict__ lik_var, float* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * Dy) return;
+    const double s2 = (double)lik_var[0], y = Y[i], lS = log((double)S);
+    double mx = -INFINITY, acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const size_t j = dedup ? i : (size_t)s * N * Dy + i;
+        const double v = (double)Fvar[j] + s2, e = y - (double)Fmean[j];
+        const double l = -0.5 * 1.8378770664093453 - 0.5 * log(v) - 0.5 * e * e / v - lS;
+        if (l > mx) { acc = acc * exp(mx - l) + 1.0; mx = l; }
+        else acc += exp(l - mx);
+    }
+    out[i] = (float)(mx + log(acc));
+}
+// out (N, 1)
+__global__ void k_density_multiclass(const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
+                                     int S, int N, int K, int dedup, float* __restrict__ out) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int y = (int)(Y[n] + 0.5f);
+    const double eps = 1e-3, lS = log((double)S);
+    double mx = -INFINITY, acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const size_t r = dedup ? (size_t)n : (size_t)s * N + n;
+        const double p = mc_prob_is_largest(Fmean + r * K, Fvar + r * K, K, y);
+        const double l = log(p * (1.0 - eps) + (1.0 - p) * (eps / (K - 1.0))) - lS;
+        if (l > mx) { acc = acc * exp(mx - l) + 1.0; mx = l; }
+        else acc += exp(l - mx);
+    }
+    out[n] = (float)(mx + log(acc));
+}
+
+void launch_predict_y(int lik, const float* Fmean, const float* Fvar, int R, int D, const float* lik_var, float* mean,
+                      float* var, cudaStream_t st, long long* nl) {
+    const size_t total = (size_t)R * D;
+    if (lik == DSDGP_LIK_GAUSSIAN) {
+        int nb = (int)min((size_t)1184, (total + 255) / 256);
+        k_predict_y_gaussian<<<nb, 256, 0, st>>>(Fmean, Fvar, total, lik_var, mean, var);
+    } else {
+        k_predict_y_multiclass<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(Fmean, Fvar, R, D, mean, var);
+    }
+    *nl += 1;
+}
+void launch_predict_density(int lik, const float* Fmean, const float* Fvar, const float* Y, int S, int N, int D, int dedup,
+                            const float* lik_var, float* out, cudaStream_t st, long long* nl) {
+    if (lik == DSDGP_LIK_GAUSSIAN)
+        k_density_gaussian<<<(unsigned)(((size_t)N * D + 127) / 128), 128, 0, st>>>(Fmean, Fvar, Y, S, N, D, dedup, lik_var, out);
+    else
+        k_density_multiclass<<<(N + 127) / 128, 128, 0, st>>>(Fmean, Fvar, Y, S, N, D, dedup, out);
     *nl += 1;
 }
 

@@ -37,7 +37,8 @@ SYMBOLS = ["dsdgp_last_error", "dsdgp_version", "dsdgp_create", "dsdgp_destroy",
            "dsdgp_get_param", "dsdgp_get_grad", "dsdgp_propagate", "dsdgp_elbo", "dsdgp_elbo_grad",
            "dsdgp_adam_init", "dsdgp_train_step", "dsdgp_kl", "dsdgp_comm_unique_id", "dsdgp_comm_init", "dsdgp_sync",
            "dsdgp_launch_count", "dsdgp_last_step_ms", "dsdgp_set_option", "dsdgp_timer_start",
-           "dsdgp_timer_stop", "dsdgp_profile", "dsdgp_set_trainable", "dsdgp_natgrad_step"]
+           "dsdgp_timer_stop", "dsdgp_profile", "dsdgp_set_trainable", "dsdgp_natgrad_step", "dsdgp_predict_y",
+           "dsdgp_predict_density"]
 
 
 def lib_path():
@@ -67,6 +68,10 @@ def load():
     lib.dsdgp_adam_init.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.dsdgp_train_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                      C.c_uint64, C.c_uint, DP]
+    lib.dsdgp_predict_y.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
+                                    C.c_void_p, C.c_uint]
+    lib.dsdgp_predict_density.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
+                                          C.c_void_p, C.c_uint]
     lib.dsdgp_set_trainable.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.dsdgp_natgrad_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                        C.c_uint64, C.c_uint, C.POINTER(C.c_int), C.c_int, C.c_double, DP]
@@ -174,6 +179,30 @@ class Context:
             outs.append(o); arrs.append(a)
         check(self.lib.dsdgp_propagate(self.h, _ptr(X), N, S, zarr, seed, arrs[0], arrs[1], arrs[2], flags))
         return outs
+
+    def _zs(self, zs):
+        zs32 = None if zs is None else [None if z is None else f32(z) for z in zs]
+        zarr, _ = _ptr_array(zs32, self.L)
+        return zarr, zs32
+
+    def predict_y(self, X, S, zs=None, seed=0):
+        """likelihood.predict_mean_and_var of the last layer, per sample: two (S,N,D_last) arrays."""
+        X = f32(X)
+        N, D = X.shape[0], self.desc.layers[self.L - 1].D_out
+        zarr, keep = self._zs(zs)
+        mean, var = np.empty((S, N, D), dtype=np.float32), np.empty((S, N, D), dtype=np.float32)
+        check(self.lib.dsdgp_predict_y(self.h, _ptr(X), N, S, zarr, seed, _ptr(mean), _ptr(var), 0))
+        return mean, var
+
+    def predict_density(self, X, Y, S, zs=None, seed=0):
+        """logsumexp_S(likelihood.predict_density - log S): (N,D_y) Gaussian, (N,1) MultiClass."""
+        X, Y = f32(X), f32(Y)
+        N = X.shape[0]
+        Do = self.desc.D_y if self.desc.likelihood == 0 else 1
+        zarr, keep = self._zs(zs)
+        out = np.empty((N, Do), dtype=np.float32)
+        check(self.lib.dsdgp_predict_density(self.h, _ptr(X), _ptr(Y), N, S, zarr, seed, _ptr(out), 0))
+        return out
 
     def _elbo(self, fn, X, Y, S, num_data, zs, seed, flags):
         if isinstance(X, int):

@@ -225,16 +225,20 @@ class DGP_Base(Parameterized):
     def predict_all_layers_full_cov(self, Xnew, num_samples):
         return self.propagate(Xnew, full_cov=True, S=num_samples)
 
-    def predict_y(self, Xnew, num_samples):
-        Fmean, Fvar = self._build_predict(Xnew, full_cov=False, S=num_samples)
-        return self.likelihood.predict_mean_and_var(Fmean, Fvar)
+    def predict_y(self, Xnew, num_samples, zs=None):
+        """dgp.py:116-119: likelihood.predict_mean_and_var of the last layer's marginals, (S,N,D) each; the likelihood
+        epilogue runs on the device (csrc/lik_adam.cu)."""
+        Xnew = np.asarray(Xnew, dtype=np.float64)
+        ctx = self._ensure_ctx(Xnew.shape[0], num_samples)
+        mean, var = ctx.predict_y(Xnew, num_samples, zs=zs, seed=self._next_seed())
+        return mean.astype(np.float64), var.astype(np.float64)
 
-    def predict_density(self, Xnew, Ynew, num_samples):
-        Fmean, Fvar = self._build_predict(Xnew, full_cov=False, S=num_samples)
-        l = self.likelihood.predict_density(Fmean, Fvar, np.asarray(Ynew, dtype=np.float64))
-        a = l - np.log(num_samples)
-        mx = a.max(0)
-        return mx + np.log(np.exp(a - mx).sum(0))          # tf.reduce_logsumexp(axis=0), dgp.py:124-126
+    def predict_density(self, Xnew, Ynew, num_samples, zs=None):
+        """dgp.py:121-126: logsumexp_S(likelihood.predict_density(Fmean, Fvar, Ynew) - log S), on the device."""
+        Xnew = np.asarray(Xnew, dtype=np.float64)
+        ctx = self._ensure_ctx(Xnew.shape[0], num_samples)
+        out = ctx.predict_density(Xnew, np.asarray(Ynew, dtype=np.float64), num_samples, zs=zs, seed=self._next_seed())
+        return out.astype(np.float64)
 
     # ------------------------------------------------------------------ training (AdamOptimizer.minimize)
     def adam_init(self, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):

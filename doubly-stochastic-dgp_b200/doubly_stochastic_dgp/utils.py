@@ -39,7 +39,8 @@ class BroadcastingLikelihood(Parameterized):
         return self.likelihood.parameters()
 
     def predict_mean_and_var(self, Fmu, Fvar):
-        return self.likelihood.predict_mean_and_var(Fmu, Fvar)
+        raise NotImplementedError("the likelihood epilogues run on the device: use model.predict_y(Xnew, num_samples)")
 
     def predict_density(self, Fmu, Fvar, Y):
-        return self.likelihood.predict_density(Fmu, Fvar, np.asarray(Y)[None])
+        raise NotImplementedError("the likelihood epilogues run on the device: use "
+                                  "model.predict_density(Xnew, Ynew, num_samples)")

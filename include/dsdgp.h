@@ -116,6 +116,16 @@ DSDGP_API int dsdgp_propagate(dsdgp_ctx* ctx, const float* X, int N, int S, cons
                     uint64_t seed, float* const* Fs, float* const* Fmeans, float* const* Fvars,
                     unsigned flags);
 
+/* DGP_Base.predict_y (dgp.py:116-119): likelihood.predict_mean_and_var (utils.py:110-114) of the last layer's
+ * marginals, per sample.  mean, var: (S,N,D_last) float32.  Gaussian: (Fmean, Fvar + variance); MultiClass: class
+ * probabilities p_k and p_k - p_k^2. */
+DSDGP_API int dsdgp_predict_y(dsdgp_ctx* ctx, const float* X, int N, int S, const float* const* zs, uint64_t seed,
+                    float* mean, float* var, unsigned flags);
+/* DGP_Base.predict_density (dgp.py:121-126): logsumexp over the S samples of likelihood.predict_density - log S.
+ * Y: (N,D_y) (class ids (N,1) for MultiClass); out: (N,D_y) Gaussian, (N,1) MultiClass. */
+DSDGP_API int dsdgp_predict_density(dsdgp_ctx* ctx, const float* X, const float* Y, int N, int S, const float* const* zs,
+                          uint64_t seed, float* out, unsigned flags);
+
 /* DGP_Base._build_likelihood (dgp.py:92-98) == compute_log_likelihood(): ELBO scalar. */
 DSDGP_API int dsdgp_elbo(dsdgp_ctx* ctx, const float* X, const float* Y, int N, int S, double num_data,
                const float* const* zs, uint64_t seed, unsigned flags, double* elbo);
