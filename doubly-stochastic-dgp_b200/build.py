@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdsdgp.so")
-SOURCES = ["api.cu", "small_matrix.cu", "layer_simt.cu", "lik_adam.cu", "layer_tc.cu", "layer_tc_bwd.cu", "rowred_tc.cu", "natgrad.cu"]
+SOURCES = ["api.cu", "small_matrix.cu", "layer_simt.cu", "lik_adam.cu", "layer_tc.cu", "layer_tc_bwd.cu", "rowred_tc.cu", "natgrad.cu", "full_cov.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -72,6 +72,7 @@ struct dsdgp_ctx {
     std::vector<unsigned char> kinds_base;   // structural kinds (host); device kinds = base, or 4 where set untrainable
     std::vector<unsigned char> kinds_host;
     double* ng_ws; size_t ng_ws_n; int* ng_status;   // natural-gradient workspace (lazily sized)
+    double* fc_ws; size_t fc_ws_n; float* fc_out; size_t fc_out_n;   // full_cov path: fp64 workspace, fp32 output staging
     std::vector<LayerOff> off;
     size_t off_likvar;
     float* meanW[DSDGP_MAX_LAYERS];
@@ -202,7 +203,9 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     CK(rowred_tc_init());
     CK(small_matrix_init());
     CK(natgrad_init());
+    CK(full_cov_init());
     c->ng_ws = nullptr; c->ng_ws_n = 0;
+    c->fc_ws = nullptr; c->fc_ws_n = 0; c->fc_out = nullptr; c->fc_out_n = 0;
     CK(dmalloc(&c->ng_status, 1));
 
     const int L = desc->L;
@@ -327,7 +330,7 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     float* fl[] = {c->params, c->grads, c->free_, c->adam_m, c->adam_v, c->sm32, c->accf, c->Xd, c->Yd};
     for (float* p : fl) cudaFree(p);
-    cudaFree(c->chain_flags); cudaFree(c->dbg_buf); cudaFree(c->ng_ws); cudaFree(c->ng_status);
+    cudaFree(c->chain_flags); cudaFree(c->dbg_buf); cudaFree(c->ng_ws); cudaFree(c->ng_status); cudaFree(c->fc_ws); cudaFree(c->fc_out);
     cudaFree(c->kinds); cudaFree(c->sm64); cudaFree(c->sa_dev); cudaFree(c->acc); cudaFree(c->result_dev);
     for (int l = 0; l < c->desc.L; ++l) {
         float* pl[] = {c->U[l], c->Fmean[l], c->Fvar[l], c->F[l], c->zs[l], c->xbar[l], c->meanW[l], c->meanB[l], c->wpack[l],
@@ -540,9 +543,9 @@ static int stage_inputs(dsdgp_ctx* c, const float* X, const float* Y, int N, int
     return DSDGP_OK;
 }
 
-static int run_step(dsdgp_ctx* c, int mode, int N, int S, double num_data, unsigned zmask, uint64_t seed) {
+// Upload this step's scalars (pinned StepArgs ring: a slot is reused only after the copy that read it has completed).
+static int push_step_args(dsdgp_ctx* c, int mode, int N, int S, double num_data, uint64_t seed) {
     const int L = c->desc.L;
-    // pinned StepArgs ring: a slot is reused only after the copy that read it has completed
     const int slot = c->sa_slot;
     c->sa_slot = (c->sa_slot + 1) % 16;
     if (c->sa_used[slot]) CK(cudaEventSynchronize(c->sa_ev[slot]));
@@ -564,6 +567,12 @@ static int run_step(dsdgp_ctx* c, int mode, int N, int S, double num_data, unsig
     CK(cudaMemcpyAsync(c->sa_dev, &sa, sizeof(StepArgs), cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->sa_ev[slot], c->stream));
     c->sa_used[slot] = true;
+    return DSDGP_OK;
+}
+
+static int run_step(dsdgp_ctx* c, int mode, int N, int S, double num_data, unsigned zmask, uint64_t seed) {
+    int rc0 = push_step_args(c, mode, N, S, num_data, seed);
+    if (rc0) return rc0;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (!c->use_graph || c->profile) {
         long long nl = 0;
@@ -631,6 +640,74 @@ int dsdgp_propagate(dsdgp_ctx* c, const float* X, int N, int S, const float* con
     // status check (Cholesky) -- accumulators are valid in propagate mode too
     launch_result(c->acc, c->grads + c->n_params, 0, c->result_dev, c->stream, &c->nlaunch);
     return fetch_result(c, nullptr);
+}
+
+// DGP_Base.propagate(full_cov=True) (dgp.py:61-76 through layers.py:66-69,206-217 and utils.py:43-51): float64 pipeline of
+// csrc/full_cov.cu, layer by layer; outputs leave as float32 in the reference's layouts.
+int dsdgp_propagate_full_cov(dsdgp_ctx* c, const float* X, int N, int S, const float* const* zs, uint64_t seed,
+                             float* const* Fs, float* const* Fmeans, float* const* Fvars, unsigned flags) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    CK(cudaSetDevice(c->desc.device));
+    const int L = c->desc.L;
+    size_t need = 0, need_out = 0;
+    int Dio = c->desc.layers[0].D_in;
+    for (int l = 0; l < L; ++l) Dio = max(Dio, c->desc.layers[l].D_out);
+    for (int l = 0; l < L; ++l) {
+        const dsdgp_layer_desc& d = c->desc.layers[l];
+        if ((long long)S * d.D_out > 65535) return set_err(DSDGP_ERR_UNSUPPORTED, "full_cov: S*D_out=%lld > 65535", (long long)S * d.D_out);
+        need = max(need, full_cov_ws_doubles(d.M, d.D_out, Dio, N, S));
+        need_out = max(need_out, (size_t)S * N * N * d.D_out + 2 * (size_t)S * N * d.D_out);
+    }
+    if (N > 16384) return set_err(DSDGP_ERR_UNSUPPORTED, "full_cov: N=%d > 16384", N);
+    if (need > ((size_t)1 << 32)) return set_err(DSDGP_ERR_UNSUPPORTED, "full_cov: workspace of %zu MB exceeds the 32 GB cap (N=%d, S=%d)", need >> 17, N, S);
+    unsigned zmask;
+    int rc = stage_inputs(c, X, nullptr, N, S, zs, flags, &zmask);
+    if (rc) return rc;
+    if (need > c->fc_ws_n) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->fc_ws) CK(cudaFree(c->fc_ws));
+        c->fc_ws = nullptr; c->fc_ws_n = 0;
+        CK(dmalloc(&c->fc_ws, need));
+        c->fc_ws_n = need;
+    }
+    if (need_out > c->fc_out_n) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->fc_out) CK(cudaFree(c->fc_out));
+        c->fc_out = nullptr; c->fc_out_n = 0;
+        CK(dmalloc(&c->fc_out, need_out));
+        c->fc_out_n = need_out;
+    }
+    rc = push_step_args(c, MODE_PROPAGATE, N, S, 1.0, seed);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    CK(cudaMemsetAsync(c->acc, 0, sizeof(Accum), st));
+    CK(cudaMemsetAsync(c->ng_status, 0, sizeof(int), st));
+    launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, st, st, c->ev_dag[0], &c->nlaunch);     // K64, Lu, Linv, Kinv (fp64)
+    // the two activation buffers sit at the end of the workspace
+    double* act[2] = {c->fc_ws + c->fc_ws_n - 2 * (size_t)S * N * Dio, c->fc_ws + c->fc_ws_n - (size_t)S * N * Dio};
+    launch_full_cov_x64(c->Xd, (size_t)N * c->desc.layers[0].D_in, act[0], st, &c->nlaunch);
+    cudaMemcpyKind kind = (flags & DSDGP_FLAG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int l = 0; l < L; ++l) {
+        const dsdgp_layer_desc& d = c->desc.layers[l];
+        const size_t nF = (size_t)S * N * d.D_out, nV = (size_t)S * N * N * d.D_out;
+        float* var32 = c->fc_out;
+        float* F32 = c->fc_out + nV;
+        float* mean32 = F32 + nF;
+        launch_full_cov_layer(c->ls.l[l], act[l & 1], l == 0 ? 0 : (size_t)N * d.D_in, N, S, c->desc.jitter,
+                              (zmask >> l) & 1u ? c->zs[l] : nullptr, c->sa_dev, c->fc_ws, act[(l + 1) & 1], F32, mean32, var32,
+                              c->ng_status, st, &c->nlaunch);
+        if (Fs && Fs[l]) CK(cudaMemcpyAsync(Fs[l], F32, nF * sizeof(float), kind, st));
+        if (Fmeans && Fmeans[l]) CK(cudaMemcpyAsync(Fmeans[l], mean32, nF * sizeof(float), kind, st));
+        if (Fvars && Fvars[l]) CK(cudaMemcpyAsync(Fvars[l], var32, nV * sizeof(float), kind, st));
+    }
+    CK(cudaGetLastError());
+    int st_host = 0;
+    CK(cudaMemcpyAsync(&st_host, c->ng_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    launch_result(c->acc, c->grads + c->n_params, 0, c->result_dev, st, &c->nlaunch);
+    rc = fetch_result(c, nullptr);
+    if (rc) return rc;
+    if (st_host) return set_err(DSDGP_ERR_NOT_PD, "full_cov: a conditional covariance + jitter*I was not positive definite (tf.cholesky would raise, utils.py:47)");
+    return DSDGP_OK;
 }
 
 // DGP_Base.predict_y / predict_density (dgp.py:116-126): propagate, then the likelihood epilogue on the device.
@@ -761,7 +838,9 @@ int dsdgp_natgrad_step(dsdgp_ctx* c, const float* X, const float* Y, int N, int 
     if (need > c->ng_ws_n) {
         CK(cudaStreamSynchronize(c->stream));
         if (c->ng_ws) CK(cudaFree(c->ng_ws));
-        c->ng_ws = nullptr; c->ng_ws_n = 0;
+        CK(full_cov_init());
+    c->ng_ws = nullptr; c->ng_ws_n = 0;
+    c->fc_ws = nullptr; c->fc_ws_n = 0; c->fc_out = nullptr; c->fc_out_n = 0;
         CK(dmalloc(&c->ng_ws, need));
         c->ng_ws_n = need;
     }

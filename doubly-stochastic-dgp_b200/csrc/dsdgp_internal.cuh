@@ -216,6 +216,12 @@ void launch_predict_y(int lik, const float* Fmean, const float* Fvar, int R, int
                       float* var, cudaStream_t st, long long* nlaunch);
 void launch_predict_density(int lik, const float* Fmean, const float* Fvar, const float* Y, int S, int N, int D, int dedup,
                             const float* lik_var, float* out, cudaStream_t st, long long* nlaunch);
+cudaError_t full_cov_init();
+size_t full_cov_ws_doubles(int M, int D, int Dmax_io, int N, int S);
+void launch_full_cov_x64(const float* X, size_t n, double* X64, cudaStream_t st, long long* nlaunch);
+void launch_full_cov_layer(const LayerDev& P, const double* Xin, size_t xs, int N, int S, double jitter, const float* z,
+                           const StepArgs* sa, double* ws, double* Fnext, float* F_out, float* mean_out, float* var_out,
+                           int* status, cudaStream_t st, long long* nlaunch);
 cudaError_t natgrad_init();
 size_t natgrad_ws_doubles(int M, int D);
 void launch_natgrad_layer(const LayerDev& P, double gamma, double* ws, int* status, float* q_mu, float* q_sqrt,

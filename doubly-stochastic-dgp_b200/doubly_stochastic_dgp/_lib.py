@@ -38,7 +38,7 @@ SYMBOLS = ["dsdgp_last_error", "dsdgp_version", "dsdgp_create", "dsdgp_destroy",
            "dsdgp_adam_init", "dsdgp_train_step", "dsdgp_kl", "dsdgp_comm_unique_id", "dsdgp_comm_init", "dsdgp_sync",
            "dsdgp_launch_count", "dsdgp_last_step_ms", "dsdgp_set_option", "dsdgp_timer_start",
            "dsdgp_timer_stop", "dsdgp_profile", "dsdgp_set_trainable", "dsdgp_natgrad_step", "dsdgp_predict_y",
-           "dsdgp_predict_density"]
+           "dsdgp_predict_density", "dsdgp_propagate_full_cov"]
 
 
 def lib_path():
@@ -68,6 +68,7 @@ def load():
     lib.dsdgp_adam_init.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.dsdgp_train_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                      C.c_uint64, C.c_uint, DP]
+    lib.dsdgp_propagate_full_cov.argtypes = lib.dsdgp_propagate.argtypes
     lib.dsdgp_predict_y.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
                                     C.c_void_p, C.c_uint]
     lib.dsdgp_predict_density.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
@@ -179,6 +180,19 @@ class Context:
             outs.append(o); arrs.append(a)
         check(self.lib.dsdgp_propagate(self.h, _ptr(X), N, S, zarr, seed, arrs[0], arrs[1], arrs[2], flags))
         return outs
+
+    def propagate_full_cov(self, X, S, zs=None, seed=0):
+        """full_cov=True propagate: Fs, Fmeans lists of (S,N,D_l); Fvars list of (S,N,N,D_l)."""
+        X = f32(X)
+        N, L = X.shape[0], self.L
+        douts = [self.desc.layers[l].D_out for l in range(L)]
+        zarr, keep = self._zs(zs)
+        Fs = [np.empty((S, N, d), dtype=np.float32) for d in douts]
+        Fm = [np.empty((S, N, d), dtype=np.float32) for d in douts]
+        Fv = [np.empty((S, N, N, d), dtype=np.float32) for d in douts]
+        a0, a1, a2 = _ptr_array(Fs, L)[0], _ptr_array(Fm, L)[0], _ptr_array(Fv, L)[0]
+        check(self.lib.dsdgp_propagate_full_cov(self.h, _ptr(X), N, S, zarr, seed, a0, a1, a2, 0))
+        return Fs, Fm, Fv
 
     def _zs(self, zs):
         zs32 = None if zs is None else [None if z is None else f32(z) for z in zs]

@@ -174,11 +174,12 @@ class DGP_Base(Parameterized):
     # ------------------------------------------------------------------ reference API
     def propagate(self, X, full_cov=False, S=1, zs=None):
         """dgp.py:61-76 -> (Fs, Fmeans, Fvars), lists of (S,N,D_l) float64 arrays."""
-        if full_cov:
-            raise NotImplementedError("full_cov=True is not on the accelerated path yet (SURVEY.md 8(f) rank 3)")
         X = np.asarray(X, dtype=np.float64)
         ctx = self._ensure_ctx(X.shape[0], S)
-        Fs, Fmeans, Fvars = ctx.propagate(X, S, zs=zs, seed=self._next_seed())
+        if full_cov:      # Fvars[l] is (S,N,N,D_l): float64 device pipeline of csrc/full_cov.cu
+            Fs, Fmeans, Fvars = ctx.propagate_full_cov(X, S, zs=zs, seed=self._next_seed())
+        else:
+            Fs, Fmeans, Fvars = ctx.propagate(X, S, zs=zs, seed=self._next_seed())
         f64 = lambda lst: [a.astype(np.float64) for a in lst]
         return f64(Fs), f64(Fmeans), f64(Fvars)
 
@@ -302,8 +303,11 @@ class DGP_Base(Parameterized):
             self._ctx.comm_init(id_bytes, rank, world)
 
     # ------------------------------------------------------------------ per-layer services for layers.py
-    def _layer_conditional(self, layer, X):
+    def _layer_conditional(self, layer, X, full_cov=False):
         raise NotImplementedError("layer.conditional_ND on a layer inside a model: use model.propagate")
+
+    def _layer_propagate(self, layer, X, **kw):
+        raise NotImplementedError("layer.sample_from_conditional on a layer inside a model: use model.propagate")
 
     def _layer_KL(self, layer):
         ctx = self._ensure_ctx(1, 1)
@@ -321,9 +325,12 @@ class DGP(DGP_Base):
 
 class _SingleLayer(DGP_Base):
     """Private one-layer model so that a stand-alone SVGP_Layer can evaluate conditional_ND / KL on the device."""
-    def _layer_conditional(self, layer, X):
-        Fs, Fmeans, Fvars = self.propagate(X, S=1)
+    def _layer_conditional(self, layer, X, full_cov=False):
+        Fs, Fmeans, Fvars = self.propagate(X, S=1, full_cov=full_cov)
         return Fmeans[0][0], Fvars[0][0]
+
+    def _layer_propagate(self, layer, X, **kw):
+        return self.propagate(X, **kw)
 
 
 def _single_layer_model(layer):

@@ -53,25 +53,33 @@ class SVGP_Layer(Layer):
         return self._model
 
     def conditional_ND(self, X, full_cov=False):
-        """layers.py:178-219: mean, var of q(f(X)), both (N, num_outputs)."""
-        if full_cov:
-            raise NotImplementedError("full_cov=True is not on the accelerated path yet (SURVEY.md 8(f) rank 3)")
-        return self._ctx_model()._layer_conditional(self, np.asarray(X))
+        """layers.py:178-219: mean (N, num_outputs) and var (N, num_outputs), or (N, N, num_outputs) with full_cov."""
+        return self._ctx_model()._layer_conditional(self, np.asarray(X), full_cov=full_cov)
 
     def conditional_SND(self, X, full_cov=False):
-        """layers.py:52-74."""
+        """layers.py:52-74: independent over the S samples; var is (S,N,D_out), or (S,N,N,D_out) with full_cov."""
         X = np.asarray(X)
         S, N, D = X.shape
-        m, v = self.conditional_ND(X.reshape(S * N, D), full_cov=full_cov)
+        if full_cov:        # tf.map_fn over the samples (layers.py:66-69)
+            ms, vs = zip(*[self.conditional_ND(X[s], full_cov=True) for s in range(S)])
+            return np.stack(ms), np.stack(vs)
+        m, v = self.conditional_ND(X.reshape(S * N, D))
         return m.reshape(S, N, self.num_outputs), v.reshape(S, N, self.num_outputs)
 
     def sample_from_conditional(self, X, z=None, full_cov=False):
-        """layers.py:76-119: returns samples, mean, var, each (S,N,num_outputs)."""
-        mean, var = self.conditional_SND(X, full_cov=full_cov)
-        if z is None:
-            z = np.random.randn(*mean.shape)
-        from .utils import reparameterize
-        return reparameterize(mean, var, np.asarray(z)), mean, var
+        """layers.py:76-119: returns samples, mean (S,N,num_outputs) and var (S,N,num_outputs) or (S,N,N,num_outputs);
+        conditional and draw both run on the device (z=None: host standard normals handed to the kernel)."""
+        X = np.asarray(X)
+        S, N, D = X.shape
+        Do = self.num_outputs
+        z = np.random.randn(S, N, Do) if z is None else np.asarray(z, dtype=np.float64).reshape(S, N, Do)
+        model = self._ctx_model()
+        if full_cov:
+            outs = [model._layer_propagate(self, X[s], S=1, full_cov=True, zs=[z[s][None]]) for s in range(S)]
+            return (np.concatenate([o[0][0] for o in outs]), np.concatenate([o[1][0] for o in outs]),
+                    np.concatenate([o[2][0] for o in outs]))
+        Fs, Fm, Fv = model._layer_propagate(self, X.reshape(S * N, D), S=1, zs=[z.reshape(1, S * N, Do)])
+        return Fs[0].reshape(S, N, Do), Fm[0].reshape(S, N, Do), Fv[0].reshape(S, N, Do)
 
     def KL(self):
         """layers.py:221-246."""

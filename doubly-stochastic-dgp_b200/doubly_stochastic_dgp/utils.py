@@ -1,6 +1,8 @@
-"""Host mirror of doubly_stochastic_dgp/utils.py (reference).  `reparameterize` (utils.py:22-41, diagonal
-branch) is fused into the forward kernel's epilogue on the device (csrc/layer_simt.cu); the function here
-is the same formula for host-side use on returned arrays.  `BroadcastingLikelihood` (utils.py:54-121)
+"""Host mirror of doubly_stochastic_dgp/utils.py (reference).  `reparameterize` (utils.py:22-51) runs on the device:
+the diagonal branch is fused into the forward kernels' epilogue (csrc/layer_simt.cu, csrc/layer_tc.cu), the full_cov
+branch is the batched Cholesky draw of csrc/full_cov.cu (k_fc_chol_draw); both are reached through
+`model.propagate(..., zs=...)` / `layer.sample_from_conditional(X, z)`.  The function here is the diagonal formula as a
+convenience on host arrays that were already returned (it is not called by any product path).  `BroadcastingLikelihood` (utils.py:54-121)
 keeps the wrapper object so that `model.likelihood.likelihood.variance` (and the reference demo's
 `model.likelihood.variance`) both work."""
 import numpy as np
@@ -14,8 +16,8 @@ def reparameterize(mean, var, z, full_cov=False):
     if var is None:
         return mean
     if full_cov:
-        raise NotImplementedError("full_cov reparameterisation is not on the accelerated path yet "
-                                  "(SURVEY.md section 8(f) rank 3)")
+        raise NotImplementedError("the full_cov draw runs on the device: use model.propagate(X, full_cov=True, zs=...) or "
+                                  "layer.sample_from_conditional(X, z, full_cov=True)")
     return mean + z * (var + settings.jitter) ** 0.5
 
 

@@ -116,6 +116,13 @@ DSDGP_API int dsdgp_propagate(dsdgp_ctx* ctx, const float* X, int N, int S, cons
                     uint64_t seed, float* const* Fs, float* const* Fmeans, float* const* Fvars,
                     unsigned flags);
 
+/* DGP_Base.propagate with full_cov=True (dgp.py:61-76; layers.py:66-69,206-217; utils.py:43-51) -- behind
+ * predict_f_full_cov / predict_all_layers_full_cov (dgp.py:104-114).  Per sample and output dimension the N x N
+ * conditional covariance and a joint draw f = mean + chol(var + jitter I) z; float64 on the device (layers.py:68), float32
+ * at the boundary.  Fs, Fmeans: (S,N,D_l); Fvars: (S,N,N,D_l).  zs as in dsdgp_propagate. */
+DSDGP_API int dsdgp_propagate_full_cov(dsdgp_ctx* ctx, const float* X, int N, int S, const float* const* zs, uint64_t seed,
+                             float* const* Fs, float* const* Fmeans, float* const* Fvars, unsigned flags);
+
 /* DGP_Base.predict_y (dgp.py:116-119): likelihood.predict_mean_and_var (utils.py:110-114) of the last layer's
  * marginals, per sample.  mean, var: (S,N,D_last) float32.  Gaussian: (Fmean, Fvar + variance); MultiClass: class
  * probabilities p_k and p_k - p_k^2. */

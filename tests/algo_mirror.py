@@ -261,3 +261,32 @@ def natgrad_update(P, Kinv, Pd, qmubar, gamma):
         new_mu[:, d] = S_new @ t1
         new_sqrt[d] = np.linalg.cholesky(S_new)
     return new_mu, new_sqrt
+
+
+def full_cov_propagate(layers, X, S, zs, jitter):
+    """csrc/full_cov.cu, kernel by kernel (float64): per layer and sample, Kuf/Kff (k_fc_gram), A = Kuu^-1 Kuf or Lu^-1 Kuf
+    (k_fc_A), SK_d (k_fc_SK), B_d = SK_d A (k_fc_B), var_d = Kff + A^T B_d (k_fc_cov), mean (k_fc_mean),
+    f = mean + chol(var_d + jitter I) z (k_fc_chol_draw).  Returns lists Fs, Fmeans (S,N,D) and Fvars (S,N,N,D)."""
+    N = X.shape[0]
+    Fs, Fms, Fvs = [], [], []
+    Xin = np.broadcast_to(X[None], (S,) + X.shape)
+    for l, P in enumerate(layers):
+        K, Lu, Linv = prepA(P, jitter)
+        W = Linv if P.white else Linv.T @ Linv
+        M, D = P.M, P.Dout
+        F = np.empty((S, N, D)); Fm = np.empty((S, N, D)); Fv = np.empty((S, N, N, D))
+        for s in range(S):
+            Xs = Xin[s]
+            Kuf, _ = kern_eval(P.kind, r2_mat(P.Z, Xs, P.ls), P.var)        # (M, N)
+            Kff, _ = kern_eval(P.kind, r2_mat(Xs, Xs, P.ls), P.var)
+            A = W @ Kuf
+            Fm[s] = A.T @ P.q_mu + meanfn(P, Xs)
+            for d in range(D):
+                SK = P.q_sqrt[d] @ P.q_sqrt[d].T - (np.eye(M) if P.white else K)
+                cov = Kff + A.T @ (SK @ A)
+                Fv[s, :, :, d] = cov
+                C = np.linalg.cholesky(cov + jitter * np.eye(N))
+                F[s, :, d] = Fm[s, :, d] + C @ zs[l][s, :, d]
+        Fs.append(F); Fms.append(Fm); Fvs.append(Fv)
+        Xin = F
+    return Fs, Fms, Fvs
