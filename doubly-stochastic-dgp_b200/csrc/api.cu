@@ -72,6 +72,7 @@ struct dsdgp_ctx {
     std::vector<unsigned char> kinds_base;   // structural kinds (host); device kinds = base, or 4 where set untrainable
     std::vector<unsigned char> kinds_host;
     double* ng_ws; size_t ng_ws_n; int* ng_status;   // natural-gradient workspace (lazily sized)
+    float* sw_dev; int sw_n;                          // per-sample likelihood weights (DGP_Quad), sw_n == 0: uniform
     double* fc_ws; size_t fc_ws_n; float* fc_out; size_t fc_out_n;   // full_cov path: fp64 workspace, fp32 output staging
     std::vector<LayerOff> off;
     size_t off_likvar;
@@ -205,6 +206,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     CK(natgrad_init());
     CK(full_cov_init());
     c->ng_ws = nullptr; c->ng_ws_n = 0;
+    CK(dmalloc(&c->sw_dev, (size_t)desc->S_max)); c->sw_n = 0;
     c->fc_ws = nullptr; c->fc_ws_n = 0; c->fc_out = nullptr; c->fc_out_n = 0;
     CK(dmalloc(&c->ng_status, 1));
 
@@ -330,7 +332,7 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     float* fl[] = {c->params, c->grads, c->free_, c->adam_m, c->adam_v, c->sm32, c->accf, c->Xd, c->Yd};
     for (float* p : fl) cudaFree(p);
-    cudaFree(c->chain_flags); cudaFree(c->dbg_buf); cudaFree(c->ng_ws); cudaFree(c->ng_status); cudaFree(c->fc_ws); cudaFree(c->fc_out);
+    cudaFree(c->chain_flags); cudaFree(c->dbg_buf); cudaFree(c->ng_ws); cudaFree(c->ng_status); cudaFree(c->fc_ws); cudaFree(c->fc_out); cudaFree(c->sw_dev);
     cudaFree(c->kinds); cudaFree(c->sm64); cudaFree(c->sa_dev); cudaFree(c->acc); cudaFree(c->result_dev);
     for (int l = 0; l < c->desc.L; ++l) {
         float* pl[] = {c->U[l], c->Fmean[l], c->Fvar[l], c->F[l], c->zs[l], c->xbar[l], c->meanW[l], c->meanB[l], c->wpack[l],
@@ -466,13 +468,14 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     if (mode == MODE_PROPAGATE) return DSDGP_OK;
     // likelihood
     const int Rlast = (L == 1) ? N : N * S;
+    const float* sw = (c->sw_n > 0 && L > 1) ? c->sw_dev : nullptr;
     PROF_BEGIN(1);
     if (c->desc.likelihood == DSDGP_LIK_GAUSSIAN)
         launch_lik_gaussian(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.D_y, c->params + c->off_likvar,
-                            c->mubar[L - 1], c->vbar[L - 1], c->acc, c->sa_dev, grad, st, nl);
+                            c->mubar[L - 1], c->vbar[L - 1], c->acc, c->sa_dev, grad, sw, st, nl);
     else
         launch_lik_multiclass(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.num_classes, c->mubar[L - 1],
-                              c->vbar[L - 1], c->acc, c->sa_dev, grad, st, nl);
+                              c->vbar[L - 1], c->acc, c->sa_dev, grad, sw, st, nl);
     PROF_END(1);
     if (grad) {
         for (int l = L - 1; l >= 0; --l) {
@@ -580,7 +583,7 @@ static int run_step(dsdgp_ctx* c, int mode, int N, int S, double num_data, unsig
         if (rc) return rc;
         c->nlaunch += nl;
     } else {
-        auto key = std::make_tuple(mode, N, S, zmask);
+        auto key = std::make_tuple(mode + (c->sw_n > 0 ? 16 : 0), N, S, zmask);
         auto it = c->graphs.find(key);
         if (it == c->graphs.end()) {
             long long nl = 0;
@@ -666,7 +669,7 @@ int dsdgp_propagate_full_cov(dsdgp_ctx* c, const float* X, int N, int S, const f
     if (need > c->fc_ws_n) {
         CK(cudaStreamSynchronize(c->stream));
         if (c->fc_ws) CK(cudaFree(c->fc_ws));
-        c->fc_ws = nullptr; c->fc_ws_n = 0;
+    c->fc_ws = nullptr; c->fc_ws_n = 0;
         CK(dmalloc(&c->fc_ws, need));
         c->fc_ws_n = need;
     }
@@ -766,6 +769,7 @@ static int elbo_common(dsdgp_ctx* c, int mode, const float* X, const float* Y, i
     unsigned zmask;
     int rc = stage_inputs(c, X, Y, N, S, zs, flags, &zmask);
     if (rc) return rc;
+    if (c->sw_n > 0 && c->sw_n != S) return set_err(DSDGP_ERR_INVALID, "sample weights were set for S=%d, call has S=%d", c->sw_n, S);
     if (mode == MODE_TRAIN) {
         if (!c->adam_on) return set_err(DSDGP_ERR_INVALID, "call dsdgp_adam_init first");
         if (c->free_dirty) {
@@ -803,6 +807,19 @@ int dsdgp_train_step(dsdgp_ctx* c, const float* X, const float* Y, int N, int S,
                      const float* const* zs, uint64_t seed, unsigned flags, double* elbo) {
     return elbo_common(c, MODE_TRAIN, X, Y, N, S, num_data, zs, seed, flags, elbo);
 }
+int dsdgp_set_sample_weights(dsdgp_ctx* c, const double* w, int S) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    CK(cudaSetDevice(c->desc.device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (!w || S == 0) { c->sw_n = 0; return DSDGP_OK; }
+    if (S < 1 || S > c->desc.S_max) return set_err(DSDGP_ERR_INVALID, "sample weights: S=%d outside [1, S_max=%d]", S, c->desc.S_max);
+    std::vector<float> tmp(S);
+    for (int i = 0; i < S; ++i) tmp[i] = (float)(w[i] * S);      // kernels scale the uniform 1/S weight: store w_s / (1/S)
+    CK(cudaMemcpy(c->sw_dev, tmp.data(), S * sizeof(float), cudaMemcpyHostToDevice));
+    c->sw_n = S;
+    return DSDGP_OK;
+}
+
 int dsdgp_set_trainable(dsdgp_ctx* c, int layer, int field, int trainable) {
     if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
     if (field == DSDGP_F_MEAN_W || field == DSDGP_F_MEAN_B) {
@@ -838,9 +855,7 @@ int dsdgp_natgrad_step(dsdgp_ctx* c, const float* X, const float* Y, int N, int 
     if (need > c->ng_ws_n) {
         CK(cudaStreamSynchronize(c->stream));
         if (c->ng_ws) CK(cudaFree(c->ng_ws));
-        CK(full_cov_init());
-    c->ng_ws = nullptr; c->ng_ws_n = 0;
-    c->fc_ws = nullptr; c->fc_ws_n = 0; c->fc_out = nullptr; c->fc_out_n = 0;
+        c->ng_ws = nullptr; c->ng_ws_n = 0;
         CK(dmalloc(&c->ng_ws, need));
         c->ng_ws_n = need;
     }

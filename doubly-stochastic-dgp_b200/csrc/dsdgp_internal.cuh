@@ -187,10 +187,10 @@ void launch_bwd_rowred(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStr
 void launch_fin(const LayerSet& ls, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
 void launch_lik_gaussian(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy,
                          const float* lik_var, float* mubar, float* vbar, Accum* acc, const StepArgs* sa,
-                         int want_grad, cudaStream_t st, long long* nlaunch);
+                         int want_grad, const float* sample_w, cudaStream_t st, long long* nlaunch);
 void launch_lik_multiclass(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int K,
                            float* mubar, float* vbar, Accum* acc, const StepArgs* sa, int want_grad,
-                           cudaStream_t st, long long* nlaunch);
+                           const float* sample_w, cudaStream_t st, long long* nlaunch);
 void launch_elbo_finish(Accum* acc, const StepArgs* sa, float* glikvar, float* elbo_hi_lo, cudaStream_t st, long long* nlaunch);
 void launch_result(const Accum* acc, const float* elbo_hi_lo, int use_hi_lo, double* result, cudaStream_t st, long long* nlaunch);
 cudaError_t layer_kernels_init();

@@ -19,35 +19,38 @@ __constant__ double c_gh_w[20] = {
 // Gaussian: VE = -1/2 log 2pi - 1/2 log s2 - 1/2 ((y-mu)^2 + v)/s2 ; rows r = s*N + n share y_n (utils.py:72-73)
 __global__ void k_lik_gaussian(const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
                                int R, int N, int Dy, const float* __restrict__ lik_var, float* __restrict__ mubar,
-                               float* __restrict__ vbar, Accum* acc, const StepArgs* sa, int want_grad) {
-    const double s2 = (double)lik_var[0], c = sa->lik_scale;
+                               float* __restrict__ vbar, Accum* acc, const StepArgs* sa, int want_grad,
+                               const float* __restrict__ sw) {
+    // sw (optional): per-sample weights relative to the uniform 1/S (DGP_Quad's Gauss-Hermite weights, dgp.py:159-166)
+    const double s2 = (double)lik_var[0], c0 = sa->lik_scale;
     const double base = -0.5 * 1.8378770664093453 - 0.5 * log(s2);
     double ve = 0.0, gl = 0.0;
     size_t total = (size_t)R * Dy;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int r = idx / Dy, d = idx % Dy, n = r % N;
+        const double c = sw ? c0 * (double)sw[r / N] : c0;
         double y = Y[(size_t)n * Dy + d], mu = Fmean[idx], v = Fvar[idx];
         double e2 = (y - mu) * (y - mu) + v;
-        ve += base - 0.5 * e2 / s2;
+        ve += c * (base - 0.5 * e2 / s2);
         if (want_grad) {
             mubar[idx] = (float)(c * (y - mu) / s2);
             vbar[idx] = (float)(-0.5 * c / s2);
-            gl += -0.5 / s2 + 0.5 * e2 / (s2 * s2);
+            gl += c * (-0.5 / s2 + 0.5 * e2 / (s2 * s2));
         }
     }
     ve = warp_sum_d(ve); gl = warp_sum_d(gl);
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&acc->lik, c * ve);
-        if (want_grad) atomicAdd(&acc->glikvar, c * gl);
+        atomicAdd(&acc->lik, ve);
+        if (want_grad) atomicAdd(&acc->glikvar, gl);
     }
 }
 
 void launch_lik_gaussian(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy, const float* lik_var,
-                         float* mubar, float* vbar, Accum* acc, const StepArgs* sa, int want_grad, cudaStream_t st,
-                         long long* nl) {
+                         float* mubar, float* vbar, Accum* acc, const StepArgs* sa, int want_grad, const float* sw,
+                         cudaStream_t st, long long* nl) {
     size_t total = (size_t)R * Dy;
     int nb = (int)min((size_t)1024, (total + 255) / 256);
-    k_lik_gaussian<<<nb, 256, 0, st>>>(Fmean, Fvar, Y, R, N, Dy, lik_var, mubar, vbar, acc, sa, want_grad);
+    k_lik_gaussian<<<nb, 256, 0, st>>>(Fmean, Fvar, Y, R, N, Dy, lik_var, mubar, vbar, acc, sa, want_grad, sw);
     *nl += 1;
 }
 
@@ -55,13 +58,15 @@ void launch_lik_gaussian(const float* Fmean, const float* Fvar, const float* Y, 
 #define MC_MAXK 32
 __global__ void k_lik_multiclass(const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
                                  int R, int N, int K, float* __restrict__ mubar, float* __restrict__ vbar, Accum* acc,
-                                 const StepArgs* sa, int want_grad) {
-    const double c = sa->lik_scale, eps = 1e-3;
+                                 const StepArgs* sa, int want_grad, const float* __restrict__ sw) {
+    const double eps = 1e-3;
+    double c = sa->lik_scale;
     const double l1 = log(1.0 - eps), l0 = log(eps / (K - 1.0));
     double ve = 0.0;
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < R) {
         int n = r % N;
+        if (sw) c *= (double)sw[r / N];
         int y = (int)(Y[n] + 0.5f);
         double mu[MC_MAXK], sd[MC_MAXK], gm[MC_MAXK], gv[MC_MAXK];
         bool clipped[MC_MAXK];
@@ -100,7 +105,7 @@ __global__ void k_lik_multiclass(const float* __restrict__ Fmean, const float* _
                 if (!clipped[y]) gv[y] += dPdx * c_gh_x[h] / (s2y);       // dx/dv_y = gh/(sqrt(2) sd_y)
             }
         }
-        ve = p * l1 + (1.0 - p) * l0;
+        ve = c * (p * l1 + (1.0 - p) * l0);
         if (want_grad) {
             double f = c * (l1 - l0);
             for (int k = 0; k < K; ++k) {
@@ -110,12 +115,13 @@ __global__ void k_lik_multiclass(const float* __restrict__ Fmean, const float* _
         }
     }
     ve = warp_sum_d(ve);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&acc->lik, c * ve);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&acc->lik, ve);
 }
 
 void launch_lik_multiclass(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int K, float* mubar,
-                           float* vbar, Accum* acc, const StepArgs* sa, int want_grad, cudaStream_t st, long long* nl) {
-    k_lik_multiclass<<<(R + 127) / 128, 128, 0, st>>>(Fmean, Fvar, Y, R, N, K, mubar, vbar, acc, sa, want_grad);
+                           float* vbar, Accum* acc, const StepArgs* sa, int want_grad, const float* sw, cudaStream_t st,
+                           long long* nl) {
+    k_lik_multiclass<<<(R + 127) / 128, 128, 0, st>>>(Fmean, Fvar, Y, R, N, K, mubar, vbar, acc, sa, want_grad, sw);
     *nl += 1;
 }
 

@@ -38,7 +38,7 @@ SYMBOLS = ["dsdgp_last_error", "dsdgp_version", "dsdgp_create", "dsdgp_destroy",
            "dsdgp_adam_init", "dsdgp_train_step", "dsdgp_kl", "dsdgp_comm_unique_id", "dsdgp_comm_init", "dsdgp_sync",
            "dsdgp_launch_count", "dsdgp_last_step_ms", "dsdgp_set_option", "dsdgp_timer_start",
            "dsdgp_timer_stop", "dsdgp_profile", "dsdgp_set_trainable", "dsdgp_natgrad_step", "dsdgp_predict_y",
-           "dsdgp_predict_density", "dsdgp_propagate_full_cov"]
+           "dsdgp_predict_density", "dsdgp_propagate_full_cov", "dsdgp_set_sample_weights"]
 
 
 def lib_path():
@@ -73,6 +73,7 @@ def load():
                                     C.c_void_p, C.c_uint]
     lib.dsdgp_predict_density.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
                                           C.c_void_p, C.c_uint]
+    lib.dsdgp_set_sample_weights.argtypes = [C.c_void_p, DP, C.c_int]
     lib.dsdgp_set_trainable.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.dsdgp_natgrad_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                        C.c_uint64, C.c_uint, C.POINTER(C.c_int), C.c_int, C.c_double, DP]
@@ -245,6 +246,14 @@ class Context:
         check(self.lib.dsdgp_train_step(self.h, _ptr(X), _ptr(Y), N, S, float(num_data), zarr, seed, flags,
                                         C.byref(e) if want_elbo else None))
         return e.value if want_elbo else None
+
+    def set_sample_weights(self, w):
+        """w: S weights summing to 1 (DGP_Quad), or None for the Monte-Carlo mean."""
+        if w is None:
+            check(self.lib.dsdgp_set_sample_weights(self.h, None, 0))
+        else:
+            w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1)
+            check(self.lib.dsdgp_set_sample_weights(self.h, w.ctypes.data_as(DP), w.size))
 
     def set_trainable(self, layer, field, flag):
         check(self.lib.dsdgp_set_trainable(self.h, layer, field, int(bool(flag))))

@@ -166,6 +166,10 @@ class DGP_Base(Parameterized):
         self._seed = (self._seed * 6364136223846793005 + 1442695040888963407) % (1 << 64)
         return self._seed
 
+    def _default_zs(self, N):
+        """Draws used when the caller passes zs=None: None = in-kernel Philox normals (DGP_Quad overrides this)."""
+        return None
+
     def _minibatch(self):
         if self.minibatch_size:
             return self._Xmb.next(), self._Ymb.next()
@@ -194,6 +198,7 @@ class DGP_Base(Parameterized):
         if X is None:
             X, Y = self._minibatch()
         ctx = self._ensure_ctx(X.shape[0], self.num_samples)
+        zs = self._default_zs(X.shape[0]) if zs is None else zs
         return ctx.elbo(X, Y, self.num_samples, self.num_data, zs=zs, seed=self._next_seed())
 
     def compute_log_likelihood_and_grad(self, zs=None, X=None, Y=None):
@@ -201,6 +206,7 @@ class DGP_Base(Parameterized):
         if X is None:
             X, Y = self._minibatch()
         ctx = self._ensure_ctx(X.shape[0], self.num_samples)
+        zs = self._default_zs(X.shape[0]) if zs is None else zs
         e = ctx.elbo_grad(X, Y, self.num_samples, self.num_data, zs=zs, seed=self._next_seed())
         grads = []
         for i, l in enumerate(self.layers):
@@ -255,6 +261,7 @@ class DGP_Base(Parameterized):
         if X is None:
             X, Y = self._minibatch()
         ctx = self._ensure_ctx(X.shape[0], self.num_samples)
+        zs = self._default_zs(X.shape[0]) if zs is None else zs
         e = ctx.train_step(_lib.f32(X), _lib.f32(Y), X.shape[0], self.num_samples, self.num_data, self._next_seed(),
                            zs=zs)
         self._device_newer = True
@@ -268,6 +275,7 @@ class DGP_Base(Parameterized):
         if X is None:
             X, Y = self._minibatch()
         ctx = self._ensure_ctx(X.shape[0], self.num_samples)
+        zs = self._default_zs(X.shape[0]) if zs is None else zs
         e = ctx.natgrad_step(_lib.f32(X), _lib.f32(Y), X.shape[0], self.num_samples, self.num_data, self._next_seed(),
                              ids, gamma, zs=zs)
         self._device_newer = True
@@ -312,6 +320,51 @@ class DGP_Base(Parameterized):
     def _layer_KL(self, layer):
         ctx = self._ensure_ctx(1, 1)
         return ctx.kl()[self.layers.index(layer)]
+
+
+def mvhermgauss(H, D):
+    """gpflow.quadrature.mvhermgauss: tensor-product Gauss-Hermite nodes (H**D, D) and weights (H**D,) (dgp.py:143).
+    Construction-time constants (host), like the reference."""
+    import itertools
+    gh_x, gh_w = np.polynomial.hermite.hermgauss(H)
+    x = np.array(list(itertools.product(*(gh_x,) * D))).reshape(H ** D, D)
+    w = np.prod(np.array(list(itertools.product(*(gh_w,) * D))).reshape(H ** D, D), 1)
+    return x, w
+
+
+class DGP_Quad(DGP_Base):
+    """dgp.py:129-166: Gauss-Hermite quadrature over the inner layers' whitened draws instead of Monte-Carlo samples.
+    The H**D_quad nodes are handed to the device as the layers' z (dsdgp_* `zs`), the node weights as per-sample
+    likelihood weights (dsdgp_set_sample_weights); everything else is the DGP_Base hot path."""
+    def __init__(self, *args, H=100, **kwargs):
+        DGP_Base.__init__(self, *args, **kwargs)
+        self.H = H
+        self.D_quad = sum(l.q_mu.shape[1] for l in self.layers[:-1])                    # dgp.py:142
+        gh_x, gh_w = mvhermgauss(H, self.D_quad)
+        gh_x = gh_x * 2. ** 0.5                                                          # dgp.py:144
+        self.gh_w = gh_w * np.pi ** (-0.5 * self.D_quad)                                 # dgp.py:145
+        self.gh_x, s = [], 0
+        for l in self.layers[:-1]:                                                       # dgp.py:149-154
+            e = s + l.q_mu.shape[1]
+            self.gh_x.append(gh_x[:, None, s:e])
+            s = e
+        self.gh_x.append(None)            # the final layer is never sampled (dgp.py:156-157)
+        self.num_samples = H ** self.D_quad                                              # dgp.py:164 S=H**D_quad
+        self._zs_cache = {}
+        self._weights_ctx = None
+
+    def _ensure_ctx(self, N, S):
+        ctx = DGP_Base._ensure_ctx(self, N, S)
+        if self._weights_ctx is not ctx:
+            ctx.set_sample_weights(self.gh_w)
+            self._weights_ctx = ctx
+        return ctx
+
+    def _default_zs(self, N):
+        if N not in self._zs_cache:       # (S,1,D) nodes broadcast over the N rows (dgp.py:147-148)
+            self._zs_cache = {N: [None if g is None else np.ascontiguousarray(
+                np.broadcast_to(g, (g.shape[0], N, g.shape[2])), dtype=np.float32) for g in self.gh_x]}
+        return self._zs_cache[N]
 
 
 class DGP(DGP_Base):

@@ -150,6 +150,11 @@ DSDGP_API int dsdgp_adam_init(dsdgp_ctx* ctx, double lr, double beta1, double be
 DSDGP_API int dsdgp_train_step(dsdgp_ctx* ctx, const float* X, const float* Y, int N, int S, double num_data,
                      const float* const* zs, uint64_t seed, unsigned flags, double* elbo);
 
+/* DGP_Quad (dgp.py:129-166): the S "samples" are Gauss-Hermite nodes (passed as zs) and the likelihood term is
+ * sum_s w_s VE_s instead of the Monte-Carlo mean.  w: S weights summing to 1 (host float64), applied by the likelihood
+ * kernels to sample s of every following elbo / elbo_grad / train_step / natgrad_step call with that S; NULL: back to 1/S. */
+DSDGP_API int dsdgp_set_sample_weights(dsdgp_ctx* ctx, const double* w, int S);
+
 /* param.set_trainable(flag) (demos/using_natural_gradients.ipynb: the NatGrad-managed q_mu, q_sqrt are taken away
  * from Adam): an untrainable field is skipped by dsdgp_train_step's Adam update; its gradient is still computed. */
 DSDGP_API int dsdgp_set_trainable(dsdgp_ctx* ctx, int layer, int field, int trainable);

@@ -510,6 +510,40 @@ class DGP_Base:
             return torch.logsumexp(l - math.log(num_samples), 0)
 
 
+def mvhermgauss(H, D):
+    """gpflow.quadrature.mvhermgauss (GPflow 1.1.1, restated): tensor-product Gauss-Hermite nodes (H**D, D) and
+    weights (H**D,).  Call site dgp.py:143."""
+    import itertools
+    gh_x, gh_w = np.polynomial.hermite.hermgauss(H)
+    x = np.array(list(itertools.product(*(gh_x,) * D)))
+    w = np.prod(np.array(list(itertools.product(*(gh_w,) * D))), 1)
+    return x, w
+
+
+class DGP_Quad(DGP_Base):
+    """dgp.py:129-166: quadrature over the inner layers' whitened draws instead of Monte-Carlo sampling."""
+    def __init__(self, *args, H=100, **kwargs):
+        DGP_Base.__init__(self, *args, **kwargs)
+        self.H = H
+        self.D_quad = sum(layer.q_mu.shape[1] for layer in self.layers[:-1])           # dgp.py:142
+        gh_x, gh_w = mvhermgauss(H, self.D_quad)
+        gh_x = gh_x * 2. ** 0.5                                                          # dgp.py:144
+        self.gh_w = _t(gh_w * np.pi ** (-0.5 * self.D_quad))                             # dgp.py:145
+        s, e = 0, 0
+        self.gh_x = []
+        for layer in self.layers[:-1]:                                                   # dgp.py:149-154
+            e += layer.q_mu.shape[1]
+            self.gh_x.append(_t(gh_x[:, None, s:e]))
+            s += layer.q_mu.shape[1]
+        self.gh_x.append(torch.zeros(1, 1, 1, dtype=DT))                                 # dgp.py:157
+
+    def E_log_p_Y(self, X, Y, zs=None):
+        """dgp.py:159-166."""
+        _, Fmeans, Fvars = self.propagate(X, zs=self.gh_x, full_cov=False, S=self.H ** self.D_quad)
+        var_exp = self.likelihood.variational_expectations(Fmeans[-1], Fvars[-1], _t(Y))
+        return torch.sum(var_exp * self.gh_w[:, None, None], 0)
+
+
 class DGP(DGP_Base):
     """dgp.py:169-192."""
     def __init__(self, X, Y, Z, kernels, likelihood, num_outputs=None, mean_function=None,
