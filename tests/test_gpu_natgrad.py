@@ -4,8 +4,8 @@ the closed-form SGPR optimum (identity I6, reference tests/test_collapsed.py:57-
 
 Tolerances: the update is fp64 arithmetic on fp32 / TF32 row-reduced accumulators.  Accumulator noise of relative size
 delta moves (q_mu, q_sqrt) by ~delta*cond but the ELBO only by ~delta^2-ish (it is a stationary point for gamma=1), see
-the CPU calibration in DESIGN.md "NatGrad": ELBO after the step within 2e-4 (fp32 path) / 1e-3 (TF32 path) relative,
-parameters within 5e-2 / 1e-1 of their scale; the measured errors are appended to gpurun_out/parity_errors.jsonl."""
+the CPU calibration in DESIGN.md "NatGrad": ELBO after the step within 1e-4 relative on both paths, parameters within
+1e-3 (fp32 path) / 5e-3 (TF32 path) of their scale; the measured errors are appended to gpurun_out/parity_errors.jsonl."""
 import numpy as np
 import pytest
 from numpy.testing import assert_allclose
@@ -27,14 +27,18 @@ def _check_against_oracle(prob, ids, gamma, path, tol_elbo=None, tol_par=None):
     from oracle import reference_dgp as R
     from tests.gpu_common import record, rel_err
     # fp32 SIMT accumulators (path 0) / TF32 tensor-core accumulators (path 1)
-    tol_elbo = tol_elbo or (2e-4 if path == 0 else 1e-3)
-    tol_par = tol_par or (5e-2 if path == 0 else 1e-1)
+    # measured on B200 (gpurun_out/parity_errors.jsonl, summarised in DESIGN.md): ELBO after the step <= 1.5e-5 relative,
+    # parameters <= 6e-5 (fp32 path) / 4e-4 (TF32 path) of their scale
+    tol_elbo = tol_elbo or 1e-4
+    tol_par = tol_par or (1e-3 if path == 0 else 5e-3)
     m = _model(prob, path)
     var_list = [[m.layers[l].q_mu, m.layers[l].q_sqrt] for l in ids]
     e0 = m.natgrad_step(var_list=var_list, gamma=gamma, zs=prob['zs'], X=prob['X'], Y=prob['Y'])
     o = build_oracle(prob)
     e0_ref = R.natgrad_step(o, ids, gamma, zs=prob['zs'])
-    assert abs(e0 - e0_ref) <= 1e-4 * abs(e0_ref)              # value before the update
+    # value before the update.  TF32 path: with the synthetic q_sqrt = 0.3 I on top of an ill-conditioned Kuu the variance is
+    # dominated by |L_d^T u|^2, the one GEMM that is single-pass TF32 (DESIGN.md "TF32 passes"): 1.6e-4 measured there
+    assert abs(e0 - e0_ref) <= (1e-4 if path == 0 else 5e-4) * abs(e0_ref), (e0, e0_ref)
     e1 = m.compute_log_likelihood(zs=prob['zs'], X=prob['X'], Y=prob['Y'])
     e1_ref = o.compute_log_likelihood(zs=prob['zs'])
     assert abs(e1 - e1_ref) <= tol_elbo * abs(e1_ref), (e1, e1_ref)
@@ -63,13 +67,13 @@ def test_I6_gamma1_single_layer_reaches_sgpr_optimum(white, path):
         m_opt, S_opt = cf.optimal_q_gaussian('rbf', lay['var'], lay['ls'], lay['Z'], prob['X'], prob['Y'], prob['lik_var'],
                                              prob['jitter'])
         sq = m.layers[0].q_sqrt.value[0]
-        assert_allclose(m.layers[0].q_mu.value, m_opt, atol=1e-1 * np.abs(m_opt).max(), rtol=0)
-        assert_allclose(sq @ sq.T, S_opt, atol=1e-1 * np.abs(S_opt).max(), rtol=0)
+        assert_allclose(m.layers[0].q_mu.value, m_opt, atol=1e-2 * np.abs(m_opt).max(), rtol=0)
+        assert_allclose(sq @ sq.T, S_opt, atol=1e-2 * np.abs(S_opt).max(), rtol=0)
     # a second gamma=1 step is a fixed point: the ELBO does not move
     e_before = m.compute_log_likelihood(zs=prob['zs'], X=prob['X'], Y=prob['Y'])
     m.natgrad_step(gamma=1.0, zs=prob['zs'], X=prob['X'], Y=prob['Y'])
     e_after = m.compute_log_likelihood(zs=prob['zs'], X=prob['X'], Y=prob['Y'])
-    assert abs(e_after - e_before) <= 1e-3 * abs(e_before)
+    assert abs(e_after - e_before) <= 1e-4 * abs(e_before)
 
 
 @pytest.mark.parametrize("path", [0, 1])
