@@ -98,6 +98,7 @@ struct dsdgp_ctx {
     cudaStream_t stream2;                       // side branch of the step DAG (KL prep, row reductions)
     cudaEvent_t ev_dag[2 * DSDGP_MAX_LAYERS + 4];
     bool overlap;
+    bool fin_per_layer;
     // step scalars
     StepArgs* sa_dev; StepArgs* sa_host;   // pinned ring of SA_RING slots (steps may be in flight)
     cudaEvent_t sa_ev[16]; bool sa_used[16]; int sa_slot;
@@ -273,7 +274,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     CK(dmalloc(&c->Yd, (size_t)desc->N_max * desc->D_y));
     CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_dag[i], cudaEventDisableTiming));
-    c->overlap = true;
+    c->overlap = true; c->fin_per_layer = true;
     (void)Dmax; (void)Mmax;
     {
         double* p64 = c->sm64; float* p32 = c->sm32; float* pa = c->accf;
@@ -502,10 +503,13 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             if (c->path == 1 && tc_rowred_supported(c->ls.l[l])) launch_bwd_rowred_tc(c->ls.l[l], b, c->num_sms, sr, nl);
             else launch_bwd_rowred(c->ls.l[l], b, c->num_sms, sr, nl);
             PROF_END(7 + 3 * l);
+            // gradient assembly of layer l needs only this layer's accumulators and the KL preparation (same side branch):
+            // it runs behind the row reductions, off the critical path, instead of for all layers at the end of the step
+            if (side && c->fin_per_layer) launch_fin(c->ls, l, l + 1, c->acc, c->sa_dev, sr, nl);
         }
         if (side) { CK(cudaEventRecord(c->ev_dag[1], c->stream2)); CK(cudaStreamWaitEvent(st, c->ev_dag[1], 0)); }
         PROF_BEGIN(2);
-        launch_fin(c->ls, c->acc, c->sa_dev, st, nl);
+        if (!(side && c->fin_per_layer)) launch_fin(c->ls, 0, L, c->acc, c->sa_dev, st, nl);
         PROF_END(2);
     }
     launch_elbo_finish(c->acc, c->sa_dev, grad ? c->grads + c->off_likvar : nullptr, c->grads + c->n_params, st, nl);
@@ -981,6 +985,10 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
         c->chain = value != 0;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "fin_per_layer") {
+        c->fin_per_layer = value != 0;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
     } else if (n == "overlap") {
         c->overlap = value != 0;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
@@ -1002,6 +1010,16 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
         for (int i = 0; i < 41; ++i) if (h[i]) fprintf(stderr, "dbg[%d] = %lld (+%lld)\n", i, h[i] - h[0], i ? h[i] - h[i - 1] : 0);
     } else if (n == "path") {
         c->path = (int)value;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    }
+    else if (n == "fin_algo") {
+        small_matrix_set_fin_algo((int)value);
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    }
+    else if (n == "prep_algo" || n == "prep_threads") {      // library-wide tuning knobs of the fp64 prep kernels
+        small_matrix_set_tuning(n == "prep_algo" ? (int)value : -1, n == "prep_threads" ? (int)value : -1);
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     }

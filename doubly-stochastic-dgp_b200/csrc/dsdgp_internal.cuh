@@ -184,7 +184,7 @@ void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* 
 void launch_fwd(const LayerDev& P, const FwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
 void launch_bwd_rows(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
 void launch_bwd_rowred(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
-void launch_fin(const LayerSet& ls, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
+void launch_fin(const LayerSet& ls, int l0, int l1, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
 void launch_lik_gaussian(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy,
                          const float* lik_var, float* mubar, float* vbar, Accum* acc, const StepArgs* sa,
                          int want_grad, const float* sample_w, cudaStream_t st, long long* nlaunch);
@@ -208,6 +208,8 @@ cudaError_t rowred_tc_init();
 bool tc_rowred_supported(const LayerDev& P);
 void launch_bwd_rowred_tc(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
 cudaError_t small_matrix_init();
+void small_matrix_set_tuning(int prep_algo, int prep_threads);   // -1: leave as is
+void small_matrix_set_fin_algo(int algo);
 void launch_adam(float* params, float* free_, float* m, float* v, const float* grads, const unsigned char* kinds,
                  const int* tril_m, size_t n, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
 void launch_constrain_init(const float* params, float* free_, const unsigned char* kinds, size_t n, cudaStream_t st,

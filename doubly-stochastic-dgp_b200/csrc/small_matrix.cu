@@ -121,6 +121,124 @@ __global__ void __launch_bounds__(1024) k_prepA(LayerSet ls, double jitter, Accu
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// prepA, fast path (M <= 111: both working matrices in shared memory).  Same results as k_prepA, restructured around the
+// latency of the pivot loop, which is what bounds it (measured: 2.9k cycles per pivot in k_prepA, 147 us of a 1.2 ms step):
+//   * square-root-free elimination: K = Lt D Lt^T is factored with the pivot d_j read by every thread (one fp64 reciprocal
+//     each, no designated thread, no broadcast) -> ONE __syncthreads per pivot instead of three; Lu = Lt D^1/2 and
+//     Lu^-1 = D^-1/2 Lt^-1 are formed once at the end (M square roots in parallel);
+//   * the factor is held transposed, B[j][i] = A_j[i][j] (i >= j): the pivot column is a contiguous row, so with lanes
+//     walking i every shared-memory access is stride-1 (the row-major form reads the pivot column with stride M: 8-way
+//     bank conflicts on fp64); each lane keeps its slice of the pivot row (and of row j of the inverse) in registers for all
+//     the rows its warp updates;
+//   * the Gram matrix is evaluated on the lower triangle only (fp64 exp is the cost) and mirrored.
+// ----------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) k_prepA_ldl(LayerSet ls, double jitter, Accum* acc) {
+    const LayerDev& P = ls.l[blockIdx.x];
+    const int M = P.M, Din = P.Din, tid = threadIdx.x, MS = M | 1;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    extern __shared__ double smd[];
+    double* B = smd;                          // [M][MS]  upper: B[j][i], i >= j
+    double* X = smd + (size_t)M * MS;         // [M][MS]  lower: X[i][c], c <= i  (unit-lower inverse of Lt)
+    __shared__ double s_il[64];
+    __shared__ double s_rsq[128];
+    __shared__ int s_fail;
+    const double var = (double)P.var[0];
+
+    long long t0 = clock64();
+    if (tid == 0) s_fail = 0;
+    for (int q = tid; q < min(Din, 64); q += NT) s_il[q] = 1.0 / (double)P.ls[P.ard ? q : 0];
+    for (int idx = tid; idx < M * MS; idx += NT) { X[idx] = (idx / MS == idx % MS) ? 1.0 : 0.0; B[idx] = 0.0; }
+    __syncthreads();
+    // Gram on i >= j: rows p and M-1-p folded into one line of M+1 entries so that all threads carry the same load
+    {
+        const int H = (M + 1) / 2, W = M + 1;
+        for (int idx = tid; idx < H * W; idx += NT) {
+            const int p = idx / W, q = idx % W;
+            int i, j;
+            if (q <= p) { i = p; j = q; }
+            else { i = M - 1 - p; j = q - p - 1; if (i == p) continue; }        // odd M: the middle row is not folded twice
+            double r2 = 0.0;
+            for (int qq = 0; qq < Din; ++qq) {
+                const double il = qq < 64 ? s_il[qq] : 1.0 / (double)P.ls[P.ard ? qq : 0];
+                const double d = ((double)P.Z[i * Din + qq] - (double)P.Z[j * Din + qq]) * il;
+                r2 += d * d;
+            }
+            double k, kp;
+            kern_eval_d(P.kern, r2, var, k, kp);
+            if (i == j) k += jitter;
+            P.K64[i * M + j] = k;
+            P.K64[j * M + i] = k;
+            B[j * MS + i] = k;
+        }
+    }
+    long long t1 = clock64();
+    // elimination: one barrier per pivot
+    for (int j = 0; j < M; ++j) {
+        __syncthreads();
+        double piv = B[j * MS + j];
+        if (!(piv > 0.0)) { if (tid == 0) s_fail = 1; piv = 1.0; }
+        const double r = 1.0 / piv;
+        // this lane's slice of the pivot row (columns i = j+1+lane+32b) and of row j of X (columns c = lane+32b <= j)
+        double pr[4], xr[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = j + 1 + lane + 32 * b, c = lane + 32 * b;
+            pr[b] = (i < M) ? B[j * MS + i] : 0.0;
+            xr[b] = (c <= j) ? X[j * MS + c] : 0.0;
+        }
+        for (int k = j + 1 + warp; k < M; k += NW) {
+            const double t = B[j * MS + k] * r;            // Lt[k][j]
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int i = j + 1 + lane + 32 * b, c = lane + 32 * b;
+                if (i >= k && i < M) B[k * MS + i] -= t * pr[b];
+                if (c <= j) X[k * MS + c] -= t * xr[b];
+            }
+        }
+    }
+    __syncthreads();
+    long long t2 = clock64();
+    if (tid == 0 && s_fail) atomicExch(&acc->status, blockIdx.x + 1);
+    for (int i = tid; i < M; i += NT) s_rsq[i] = rsqrt(B[i * MS + i]);
+    __syncthreads();
+    // outputs (row-major global, coalesced): Lu = Lt D^1/2, Linv = D^-1/2 Lt^-1 (fp64, fp32, fp32 transposed)
+    for (int idx = tid; idx < M * M; idx += NT) {
+        const int i = idx / M, j = idx % M;
+        double l = 0.0, x = 0.0;
+        if (j <= i) {
+            l = (i == j) ? 1.0 / s_rsq[j] : B[j * MS + i] * s_rsq[j];
+            x = X[i * MS + j] * s_rsq[i];
+        }
+        P.Lu64[idx] = l; P.Linv64[idx] = x;
+        P.Linv32[idx] = (float)x;
+        // transposed copy, written coalesced: element (i, j) of LinvT is Linv[j][i]
+        P.LinvT32[idx] = (i <= j) ? (float)(X[j * MS + i] * s_rsq[j]) : 0.f;
+    }
+    double s = 0.0;
+    for (int i = tid; i < M; i += NT) s -= log(s_rsq[i]);          // sum log diag Lu = -sum log d^-1/2
+    s = warp_sum_d(s);
+    __shared__ double red[32];
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < NW; ++w) t += red[w];
+        P.scal[0] = t; P.scal[2] = 0.0; P.scal[3] = 0.0;
+        P.scal[5] = (double)(t1 - t0); P.scal[6] = (double)(t2 - t1); P.scal[7] = (double)(clock64() - t2);
+    }
+}
+
+// tuning knobs (dsdgp_set_option "prep_algo" / "prep_threads"): 1 = k_prepA_ldl (default where it fits), 0 = k_prepA
+static int g_prep_algo = 1, g_prep_threads = 512;
+void small_matrix_set_tuning(int algo, int threads) {
+    if (algo >= 0) g_prep_algo = algo;
+    if (threads == 256 || threads == 512 || threads == 1024) g_prep_threads = threads;
+}
+
 // q_sqrtT[d][j][i] = q_sqrt[d][i][j]; scal[1] = sum log diag^2 ; scal[4] = sum q_sqrt^2 + sum q_mu^2
 __global__ void k_qsqrtT(LayerSet ls) {
     const LayerDev& P = ls.l[blockIdx.y];
@@ -226,7 +344,13 @@ void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* 
     for (int l = 0; l < ls.L; ++l) { Mmax = max(Mmax, ls.l[l].M); Dmax = max(Dmax, ls.l[l].Dout); }
     size_t sm = 2 * (size_t)Mmax * Mmax * sizeof(double);
     int use_smem = sm <= 200 * 1024;
-    k_prepA<<<ls.L, 1024, use_smem ? sm : 0, st>>>(ls, jitter, acc, use_smem);
+    const size_t sm_ldl = 2 * (size_t)Mmax * (Mmax | 1) * sizeof(double);
+    if (g_prep_algo == 1 && Mmax <= 128 && sm_ldl <= 200 * 1024) {
+        if (g_prep_threads == 256) k_prepA_ldl<256><<<ls.L, 256, sm_ldl, st>>>(ls, jitter, acc);
+        else if (g_prep_threads == 1024) k_prepA_ldl<1024><<<ls.L, 1024, sm_ldl, st>>>(ls, jitter, acc);
+        else k_prepA_ldl<512><<<ls.L, 512, sm_ldl, st>>>(ls, jitter, acc);
+    } else
+        k_prepA<<<ls.L, 1024, use_smem ? sm : 0, st>>>(ls, jitter, acc, use_smem);
     if (st_kl != st) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(st_kl, ev_fork, 0); }
     st = st_kl;
     k_zero_scal<<<ls.L, 32, 0, st>>>(ls);
@@ -250,8 +374,8 @@ void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* 
 // fin: parameter gradients from the row-reduced accumulators (tests/algo_mirror.py::layer_fin)
 // ----------------------------------------------------------------------------------------------
 // gq_sqrt[d] = tril((2 P_d - klw*Kinv) L_d) + klw*diag(1/L_d,ii)     (white: Kinv -> I)
-__global__ void k_fin_qsqrt(LayerSet ls, const StepArgs* sa) {
-    const LayerDev& P = ls.l[blockIdx.z];
+__global__ void k_fin_qsqrt(LayerSet ls, const StepArgs* sa, int lbase) {
+    const LayerDev& P = ls.l[lbase + blockIdx.z];
     const int M = P.M, d = blockIdx.y;
     if (d >= P.Dout) return;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,8 +399,8 @@ __global__ void k_fin_qsqrt(LayerSet ls, const StepArgs* sa) {
 }
 
 // gq_mu = qmubar - klw * Kinv q_mu   (white: - klw q_mu)
-__global__ void k_fin_qmu(LayerSet ls, const StepArgs* sa) {
-    const LayerDev& P = ls.l[blockIdx.y];
+__global__ void k_fin_qmu(LayerSet ls, const StepArgs* sa, int lbase) {
+    const LayerDev& P = ls.l[lbase + blockIdx.y];
     const int M = P.M, D = P.Dout;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * D) return;
@@ -294,8 +418,8 @@ __global__ void k_fin_qmu(LayerSet ls, const StepArgs* sa) {
 
 // white: Phi = tril(Lu^T tril(-G)) with halved diagonal -> T1 ; then T1 <- Phi Linv (into Ssum64) ;
 // Kbar = sym(Linv^T (Phi Linv))
-__global__ void k_fin_w1(LayerSet ls) {
-    const LayerDev& P = ls.l[blockIdx.y];
+__global__ void k_fin_w1(LayerSet ls, int lbase) {
+    const LayerDev& P = ls.l[lbase + blockIdx.y];
     if (!P.white) return;
     const int M = P.M;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,8 +432,8 @@ __global__ void k_fin_w1(LayerSet ls) {
     }
     P.T1[idx] = s;
 }
-__global__ void k_fin_w2(LayerSet ls) {
-    const LayerDev& P = ls.l[blockIdx.y];
+__global__ void k_fin_w2(LayerSet ls, int lbase) {
+    const LayerDev& P = ls.l[lbase + blockIdx.y];
     if (!P.white) return;
     const int M = P.M;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,8 +443,8 @@ __global__ void k_fin_w2(LayerSet ls) {
     for (int k = j; k <= i; ++k) s += P.T1[i * M + k] * P.Linv64[k * M + j];
     P.Ssum64[idx] = s;
 }
-__global__ void k_fin_w3(LayerSet ls) {
-    const LayerDev& P = ls.l[blockIdx.y];
+__global__ void k_fin_w3(LayerSet ls, int lbase) {
+    const LayerDev& P = ls.l[lbase + blockIdx.y];
     if (!P.white) return;
     const int M = P.M;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -332,8 +456,8 @@ __global__ void k_fin_w3(LayerSet ls) {
 }
 
 // g_ij = Kbar_ij * dk/dr2_ij  (Kbar symmetric)  -> Gsym ; gvar += sum Kbar o k / var
-__global__ void k_fin_kbar(LayerSet ls, const StepArgs* sa) {
-    const LayerDev& P = ls.l[blockIdx.y];
+__global__ void k_fin_kbar(LayerSet ls, const StepArgs* sa, int lbase) {
+    const LayerDev& P = ls.l[lbase + blockIdx.y];
     const int M = P.M, Din = P.Din;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     double s2 = 0.0;
@@ -358,8 +482,8 @@ __global__ void k_fin_kbar(LayerSet ls, const StepArgs* sa) {
 }
 
 // Zbar_iq += 4/l_q^2 sum_j g_ij (z_iq - z_jq) ; lsbar_q += -2/l_q^3 sum_ij g_ij (z_iq - z_jq)^2
-__global__ void k_fin_kuu(LayerSet ls) {
-    const LayerDev& P = ls.l[blockIdx.y];
+__global__ void k_fin_kuu(LayerSet ls, int lbase) {
+    const LayerDev& P = ls.l[lbase + blockIdx.y];
     const int M = P.M, Din = P.Din;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * Din) return;
@@ -374,6 +498,123 @@ __global__ void k_fin_kuu(LayerSet ls) {
     atomicAdd(&P.gls[P.ard ? q : 0], (float)(-2.0 * b / (l * l * l)));
 }
 
+
+// ---- tiled / warp-per-output versions of the three long fin kernels (same arithmetic, fp64).  The one-thread-per-element
+// forms above walk a dependent 100-iteration fp64 chain per thread out of L2 (57 + 17 + 17 us of a 1.2 ms step at the
+// north-star shape, all of it on the tail of the critical path); these keep operands in shared memory / registers.
+#define FT 32
+// gq_sqrt[d] tile (ti >= tj): sum over k-tiles kt >= tj of A[ti,kt] L[kt,tj],  A = P_d + P_d^T - klw Kinv (white: no Kinv)
+__global__ void __launch_bounds__(256) k_fin_qsqrt_t(LayerSet ls, const StepArgs* sa, int lbase) {
+    const LayerDev& P = ls.l[lbase + blockIdx.z];
+    const int M = P.M, d = blockIdx.y;
+    if (d >= P.Dout) return;
+    const int nt = (M + FT - 1) / FT;
+    int ti = 0, rem = blockIdx.x;                  // blockIdx.x enumerates the lower-triangular tile pairs row by row
+    while (rem > ti) { rem -= ti + 1; ++ti; }
+    const int tj = rem;
+    if (ti >= nt) return;
+    __shared__ double As[FT][FT + 1], Ls[FT][FT + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const double klw = sa->kl_weight;
+    const float* Ld = P.q_sqrt + (size_t)d * M * M;
+    const float* Pd = P.Pd + (size_t)d * M * M;
+    const int i0 = ti * FT, j0 = tj * FT;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int kt = tj; kt < nt; ++kt) {
+        const int k0 = kt * FT;
+        for (int e = threadIdx.x; e < FT * FT; e += 256) {
+            const int r = e / FT, c = e % FT;
+            const int i = i0 + r, k = k0 + c;                 // A[i][k]
+            double a = 0.0;
+            if (i < M && k < M) {
+                a = (double)Pd[i * M + k] + (double)Pd[k * M + i];
+                if (!P.white) a -= klw * P.Kinv64[i * M + k];
+            }
+            As[r][c] = a;
+            const int kk = k0 + r, j = j0 + c;                // L[kk][j], lower triangular
+            Ls[r][c] = (kk < M && j < M && j <= kk) ? (double)Ld[kk * M + j] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < FT; ++kk) {
+            const double a0 = As[ty][kk], a1 = As[ty + 16][kk], l0 = Ls[kk][tx], l1 = Ls[kk][tx + 16];
+            acc[0][0] += a0 * l0; acc[0][1] += a0 * l1; acc[1][0] += a1 * l0; acc[1][1] += a1 * l1;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+            if (i >= M || j >= M) continue;
+            double g = 0.0;
+            if (j <= i) {
+                g = acc[a][b];
+                if (P.white) g -= klw * (double)Ld[i * M + j];
+                if (i == j) g += klw / (double)Ld[i * M + i];
+            }
+            P.gq_sqrt[(size_t)d * M * M + i * M + j] = (float)g;      // (strictly-upper tiles stay at the step's memset zero)
+        }
+}
+
+// gq_mu: one warp per output (i, d), lanes over k
+__global__ void __launch_bounds__(256) k_fin_qmu_w(LayerSet ls, const StepArgs* sa, int lbase) {
+    const LayerDev& P = ls.l[lbase + blockIdx.y];
+    const int M = P.M, D = P.Dout;
+    const int idx = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (idx >= M * D) return;
+    const int i = idx / D, d = idx % D;
+    const double klw = sa->kl_weight;
+    double s = 0.0;
+    if (!P.white)
+        for (int k = lane; k < M; k += 32) s += P.Kinv64[i * M + k] * (double)P.q_mu[k * D + d];
+    s = warp_sum_d(s);
+    if (lane == 0) {
+        double g = (double)P.qmubar[idx];
+        g -= P.white ? klw * (double)P.q_mu[idx] : klw * s;
+        P.gq_mu[idx] = (float)g;
+    }
+}
+
+// Zbar / lsbar from Gsym: one warp per inducing point i, lanes over j, input dimensions in chunks of 8
+__global__ void __launch_bounds__(256) k_fin_kuu_w(LayerSet ls, int lbase) {
+    const LayerDev& P = ls.l[lbase + blockIdx.y];
+    const int M = P.M, Din = P.Din;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= M) return;
+    double ls_acc = 0.0;                                   // non-ARD: all dimensions share one lengthscale
+    for (int q0 = 0; q0 < Din; q0 += 8) {
+        const int nq = min(8, Din - q0);
+        double a[8], b[8], zi[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { a[q] = 0.0; b[q] = 0.0; zi[q] = q < nq ? (double)P.Z[i * Din + q0 + q] : 0.0; }
+        for (int j = lane; j < M; j += 32) {
+            const double g = P.Gsym[i * M + j];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < nq) {
+                    const double dd = zi[q] - (double)P.Z[j * Din + q0 + q];
+                    a[q] += g * dd; b[q] += g * dd * dd;
+                }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const double as = warp_sum_d(a[q]), bs = warp_sum_d(b[q]);
+            if (lane == 0 && q < nq) {
+                const double l = (double)P.ls[P.ard ? q0 + q : 0];
+                atomicAdd(&P.gZ[i * Din + q0 + q], (float)(4.0 * as / (l * l)));
+                if (P.ard) atomicAdd(&P.gls[q0 + q], (float)(-2.0 * bs / (l * l * l)));
+                else ls_acc += -2.0 * bs / (l * l * l);
+            }
+        }
+    }
+    if (lane == 0 && !P.ard) atomicAdd(&P.gls[0], (float)ls_acc);
+}
+
+static int g_fin_algo = 1;         // dsdgp_set_option "fin_algo": 1 = the tiled kernels, 0 = one thread per element
+void small_matrix_set_fin_algo(int a) { g_fin_algo = a; }
+
 __global__ void k_elbo_finish(Accum* acc, const StepArgs* sa, float* glikvar, float* elbo_hi_lo) {
     double e = acc->lik - sa->kl_weight * acc->kl;
     acc->elbo = e;
@@ -385,26 +626,36 @@ __global__ void k_elbo_finish(Accum* acc, const StepArgs* sa, float* glikvar, fl
     }
 }
 
-void launch_fin(const LayerSet& ls, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nl) {
+// layers [l0, l1): everything here depends only on that layer's accumulators and on the KL preparation, so the step DAG
+// runs it per layer on the side branch right behind the layer's row reductions (api.cu)
+void launch_fin(const LayerSet& ls, int l0, int l1, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nl) {
     int Mmax = 0, Dmax = 0, MDmax = 0, MDin = 0;
     bool any_white = false;
-    for (int l = 0; l < ls.L; ++l) {
+    const int nL = l1 - l0;
+    for (int l = l0; l < l1; ++l) {
         Mmax = max(Mmax, ls.l[l].M); Dmax = max(Dmax, ls.l[l].Dout);
         MDmax = max(MDmax, ls.l[l].M * ls.l[l].Dout); MDin = max(MDin, ls.l[l].M * ls.l[l].Din);
         any_white |= ls.l[l].white != 0;
     }
     int nb = (Mmax * Mmax + 255) / 256;
-    k_fin_qsqrt<<<dim3(nb, Dmax, ls.L), 256, 0, st>>>(ls, sa);
-    k_fin_qmu<<<dim3((MDmax + 255) / 256, ls.L), 256, 0, st>>>(ls, sa);
+    if (g_fin_algo == 1) {
+        const int nt = (Mmax + FT - 1) / FT;
+        k_fin_qsqrt_t<<<dim3(nt * (nt + 1) / 2, Dmax, nL), 256, 0, st>>>(ls, sa, l0);
+        k_fin_qmu_w<<<dim3((MDmax + 7) / 8, nL), 256, 0, st>>>(ls, sa, l0);
+    } else {
+        k_fin_qsqrt<<<dim3(nb, Dmax, nL), 256, 0, st>>>(ls, sa, l0);
+        k_fin_qmu<<<dim3((MDmax + 255) / 256, nL), 256, 0, st>>>(ls, sa, l0);
+    }
     *nl += 2;
     if (any_white) {
-        k_fin_w1<<<dim3(nb, ls.L), 256, 0, st>>>(ls);
-        k_fin_w2<<<dim3(nb, ls.L), 256, 0, st>>>(ls);
-        k_fin_w3<<<dim3(nb, ls.L), 256, 0, st>>>(ls);
+        k_fin_w1<<<dim3(nb, nL), 256, 0, st>>>(ls, l0);
+        k_fin_w2<<<dim3(nb, nL), 256, 0, st>>>(ls, l0);
+        k_fin_w3<<<dim3(nb, nL), 256, 0, st>>>(ls, l0);
         *nl += 3;
     }
-    k_fin_kbar<<<dim3(nb, ls.L), 256, 0, st>>>(ls, sa);
-    k_fin_kuu<<<dim3((MDin + 255) / 256, ls.L), 256, 0, st>>>(ls);
+    k_fin_kbar<<<dim3(nb, nL), 256, 0, st>>>(ls, sa, l0);
+    if (g_fin_algo == 1) k_fin_kuu_w<<<dim3((Mmax + 7) / 8, nL), 256, 0, st>>>(ls, l0);
+    else k_fin_kuu<<<dim3((MDin + 255) / 256, nL), 256, 0, st>>>(ls, l0);
     *nl += 2;
 }
 
@@ -426,5 +677,9 @@ void launch_result(const Accum* acc, const float* elbo_hi_lo, int use_hi_lo, dou
 }
 
 cudaError_t small_matrix_init() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_prepA_ldl<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
+    if ((e = cudaFuncSetAttribute(k_prepA_ldl<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
+    if ((e = cudaFuncSetAttribute(k_prepA_ldl<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
     return cudaFuncSetAttribute(k_prepA, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
