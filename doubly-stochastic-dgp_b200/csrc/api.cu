@@ -96,6 +96,7 @@ struct dsdgp_ctx {
     float* vbar[DSDGP_MAX_LAYERS];
     float* Wbuf[DSDGP_MAX_LAYERS];
     cudaStream_t stream2;                       // side branch of the step DAG (KL prep, row reductions)
+    cudaStream_t stream3;                       // second side branch: per-layer gradient assembly behind the row reductions
     cudaEvent_t ev_dag[2 * DSDGP_MAX_LAYERS + 4];
     bool overlap;
     bool fin_per_layer;
@@ -273,6 +274,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     CK(dmalloc(&c->Xd, (size_t)desc->N_max * desc->layers[0].D_in));
     CK(dmalloc(&c->Yd, (size_t)desc->N_max * desc->D_y));
     CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
     for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_dag[i], cudaEventDisableTiming));
     c->overlap = true; c->fin_per_layer = true;
     (void)Dmax; (void)Mmax;
@@ -344,7 +346,7 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
     for (int i = 0; i < 2 * (5 + 3 * DSDGP_MAX_LAYERS); ++i) cudaEventDestroy(c->prof_ev[i]);
     for (int i = 0; i < 16; ++i) cudaEventDestroy(c->sa_ev[i]);
-    cudaStreamDestroy(c->stream2);
+    cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3);
     for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 4; ++i) cudaEventDestroy(c->ev_dag[i]);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -505,9 +507,18 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             PROF_END(7 + 3 * l);
             // gradient assembly of layer l needs only this layer's accumulators and the KL preparation (same side branch):
             // it runs behind the row reductions, off the critical path, instead of for all layers at the end of the step
-            if (side && c->fin_per_layer) launch_fin(c->ls, l, l + 1, c->acc, c->sa_dev, sr, nl);
+            // (its own branch: queued behind the next layer's row reductions on stream2 it would delay them)
+            if (side && c->fin_per_layer) {
+                CK(cudaEventRecord(c->ev_dag[2 + DSDGP_MAX_LAYERS + l], sr));
+                CK(cudaStreamWaitEvent(c->stream3, c->ev_dag[2 + DSDGP_MAX_LAYERS + l], 0));
+                launch_fin(c->ls, l, l + 1, c->acc, c->sa_dev, c->stream3, nl);
+            }
         }
         if (side) { CK(cudaEventRecord(c->ev_dag[1], c->stream2)); CK(cudaStreamWaitEvent(st, c->ev_dag[1], 0)); }
+        if (side && c->fin_per_layer) {
+            CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 3], c->stream3));
+            CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 3], 0));
+        }
         PROF_BEGIN(2);
         if (!(side && c->fin_per_layer)) launch_fin(c->ls, 0, L, c->acc, c->sa_dev, st, nl);
         PROF_END(2);

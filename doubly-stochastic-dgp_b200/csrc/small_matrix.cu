@@ -122,6 +122,17 @@ __global__ void __launch_bounds__(1024) k_prepA(LayerSet ls, double jitter, Accu
 }
 
 
+// fp64 reciprocal for the pivot chains below: hardware approximation (>= 20 bits) + two Newton steps (relative error ~2^-80
+// before rounding) -- five dependent instructions instead of the IEEE division's ~40; pivots are normal, positive numbers.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 // ----------------------------------------------------------------------------------------------
 // prepA, fast path (M <= 111: both working matrices in shared memory).  Same results as k_prepA, restructured around the
 // latency of the pivot loop, which is what bounds it (measured: 2.9k cycles per pivot in k_prepA, 147 us of a 1.2 ms step):
@@ -181,7 +192,7 @@ __global__ void __launch_bounds__(NT) k_prepA_ldl(LayerSet ls, double jitter, Ac
         __syncthreads();
         double piv = B[j * MS + j];
         if (!(piv > 0.0)) { if (tid == 0) s_fail = 1; piv = 1.0; }
-        const double r = 1.0 / piv;
+        const double r = fast_rcp(piv);
         // this lane's slice of the pivot row (columns i = j+1+lane+32b) and of row j of X (columns c = lane+32b <= j)
         double pr[4], xr[4];
 #pragma unroll
@@ -202,9 +213,13 @@ __global__ void __launch_bounds__(NT) k_prepA_ldl(LayerSet ls, double jitter, Ac
     }
     __syncthreads();
     long long t2 = clock64();
-    if (tid == 0 && s_fail) atomicExch(&acc->status, blockIdx.x + 1);
-    for (int i = tid; i < M; i += NT) s_rsq[i] = rsqrt(B[i * MS + i]);
+    for (int i = tid; i < M; i += NT) {
+        const double dpiv = B[i * MS + i];
+        if (!(dpiv > 0.0)) s_fail = 1;
+        s_rsq[i] = rsqrt(dpiv > 0.0 ? dpiv : 1.0);
+    }
     __syncthreads();
+    if (tid == 0 && s_fail) atomicExch(&acc->status, blockIdx.x + 1);
     // outputs (row-major global, coalesced): Lu = Lt D^1/2, Linv = D^-1/2 Lt^-1 (fp64, fp32, fp32 transposed)
     for (int idx = tid; idx < M * M; idx += NT) {
         const int i = idx / M, j = idx % M;
@@ -232,8 +247,169 @@ __global__ void __launch_bounds__(NT) k_prepA_ldl(LayerSet ls, double jitter, Ac
     }
 }
 
-// tuning knobs (dsdgp_set_option "prep_algo" / "prep_threads"): 1 = k_prepA_ldl (default where it fits), 0 = k_prepA
-static int g_prep_algo = 1, g_prep_threads = 512;
+
+// ----------------------------------------------------------------------------------------------
+// prepA, blocked variant of k_prepA_ldl (pivots four at a time) on ONE combined M x M shared-memory array:
+//     C[k][c] = B[k][c] = A_k[c][k]   for c >= k   (transposed factor, row k = column k of the Schur complement)
+//     C[k][c] = X[k][c] = Lt^-1[k][c] for c <  k   (unit lower inverse; its diagonal of ones is implicit)
+// so that the update of row k by pivot row j is a single vector operation  C[k][c] -= t P_j[c]  over c <= j (inverse part,
+// P_j[j] = 1) and c >= k (factor part): half the instructions and half the shared memory of keeping B and X apart.
+// Per panel (rows j0..j0+3):
+//   panel phase    -- three warps bring rows j0+1..j0+3 up to date, one pivot after the other (96-thread named barrier);
+//   trailing phase -- every remaining row k gets the rank-4 update from the FINAL pivot rows, which each lane keeps in
+//                     registers (one load + one store per four FMAs), two rows per warp pass.
+// The arithmetic is that of the unblocked elimination with the four updates of an element summed in one pass.
+// ----------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) k_prepA_c4(LayerSet ls, double jitter, Accum* acc) {
+    const LayerDev& P = ls.l[blockIdx.x];
+    const int M = P.M, Din = P.Din, tid = threadIdx.x;
+    constexpr int MS = 129;                   // row stride: 4 blocks of 32 columns + 1 (M <= 128); columns >= M stay zero, so the
+                                              // 32-wide column blocks need no bounds checks (a zero pivot-row entry is a no-op)
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    static_assert(NW >= 3, "panel phase uses three warps");
+    extern __shared__ double smd[];
+    double* C = smd;                          // [M][MS]
+    __shared__ double s_il[64];
+    __shared__ double s_rsq[128];
+    __shared__ int s_fail;
+    const double var = (double)P.var[0];
+
+    long long t0 = clock64();
+    if (tid == 0) s_fail = 0;
+    for (int q = tid; q < min(Din, 64); q += NT) s_il[q] = 1.0 / (double)P.ls[P.ard ? q : 0];
+    for (int idx = tid; idx < M * MS; idx += NT) C[idx] = 0.0;
+    __syncthreads();
+    {   // Gram on i >= j: rows p and M-1-p folded into one line of M+1 entries so that all threads carry the same load
+        const int H = (M + 1) / 2, W = M + 1;
+        for (int idx = tid; idx < H * W; idx += NT) {
+            const int p = idx / W, q = idx % W;
+            int i, j;
+            if (q <= p) { i = p; j = q; }
+            else { i = M - 1 - p; j = q - p - 1; if (i == p) continue; }
+            double r2 = 0.0;
+            for (int qq = 0; qq < Din; ++qq) {
+                const double il = qq < 64 ? s_il[qq] : 1.0 / (double)P.ls[P.ard ? qq : 0];
+                const double d = ((double)P.Z[i * Din + qq] - (double)P.Z[j * Din + qq]) * il;
+                r2 += d * d;
+            }
+            double k, kp;
+            kern_eval_d(P.kern, r2, var, k, kp);
+            if (i == j) k += jitter;
+            P.K64[i * M + j] = k;
+            P.K64[j * M + i] = k;
+            C[j * MS + i] = k;
+        }
+    }
+    long long t1 = clock64();
+    for (int j0 = 0; j0 < M; j0 += 4) {
+        const int w = min(4, M - j0);
+        __syncthreads();                                   // trailing updates of the previous panel are complete
+        if (warp < 3) {
+            const int rrow = j0 + 1 + warp;
+            double* rr = C + rrow * MS + lane;
+            for (int p = 0; p < 3; ++p) {                  // pivot j = j0 + p  (all three warps run every iteration: named barrier)
+                const int j = j0 + p;
+                if (p < w - 1 && rrow < j0 + w && rrow > j) {
+                    const double* rj = C + j * MS + lane;
+                    double piv = C[j * MS + j];
+                    if (!(piv > 0.0)) piv = 1.0;           // (reported by the final pass over the pivots)
+                    const double t = C[j * MS + rrow] * fast_rcp(piv);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int c = lane + 32 * b;
+                        const double pj = (c == j) ? 1.0 : rj[32 * b];
+                        if (c <= j || c >= rrow) rr[32 * b] -= t * pj;
+                    }
+                }
+                asm volatile("bar.sync 1, 96;" ::: "memory");
+            }
+        }
+        __syncthreads();                                   // the panel's pivot rows are final
+        const int kb = j0 + w;                             // first trailing row
+        if (kb >= M) continue;
+        double rq[4], pr[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int jq = j0 + q;
+            rq[q] = 0.0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) pr[q][b] = 0.0;
+            if (q < w) {
+                double piv = C[jq * MS + jq];
+                if (!(piv > 0.0)) piv = 1.0;
+                rq[q] = fast_rcp(piv);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int c = lane + 32 * b;
+                    const double v = C[jq * MS + c];        // zero in the padding columns
+                    pr[q][b] = (c == jq) ? 1.0 : ((c < jq || c >= kb) ? v : 0.0);
+                }
+            }
+        }
+        for (int k = kb + warp; k < M; k += 2 * NW) {      // two rows per pass: their loads are issued together
+            const bool has2 = k + NW < M;
+            const int k2 = has2 ? k + NW : k;
+            double* rk = C + k * MS + lane;
+            double* rk2 = C + k2 * MS + lane;
+            double t[4], u[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                t[q] = 0.0; u[q] = 0.0;
+                if (q < w) { t[q] = C[(j0 + q) * MS + k] * rq[q]; u[q] = C[(j0 + q) * MS + k2] * rq[q]; }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int c0 = 32 * b, c = c0 + lane;
+                if (c0 >= kb && c0 + 31 < k) continue;       // block strictly between the two parts of row k (and of k2 > k)
+                const bool a1 = c < kb || c >= k;
+                const bool a2 = has2 && (c < kb || c >= k2);
+                double v1 = rk[c0], v2 = rk2[c0];
+                v1 -= t[0] * pr[0][b]; v1 -= t[1] * pr[1][b]; v1 -= t[2] * pr[2][b]; v1 -= t[3] * pr[3][b];
+                v2 -= u[0] * pr[0][b]; v2 -= u[1] * pr[1][b]; v2 -= u[2] * pr[2][b]; v2 -= u[3] * pr[3][b];
+                if (a1) rk[c0] = v1;
+                if (a2) rk2[c0] = v2;
+            }
+        }
+    }
+    __syncthreads();
+    long long t2 = clock64();
+    // final pass over the pivots: any non-positive (or NaN) one means Kuu + jitter I is not positive definite
+    for (int i = tid; i < M; i += NT) {
+        const double dpiv = C[i * MS + i];
+        if (!(dpiv > 0.0)) s_fail = 1;
+        s_rsq[i] = rsqrt(dpiv > 0.0 ? dpiv : 1.0);
+    }
+    __syncthreads();
+    if (tid == 0 && s_fail) atomicExch(&acc->status, blockIdx.x + 1);
+    // outputs (row-major global, coalesced): Lu = Lt D^1/2, Linv = D^-1/2 Lt^-1 (fp64, fp32, fp32 transposed)
+    for (int idx = tid; idx < M * M; idx += NT) {
+        const int i = idx / M, j = idx % M;
+        double l = 0.0, x = 0.0, xt = 0.0;
+        if (j < i) { l = C[j * MS + i] * s_rsq[j]; x = C[i * MS + j] * s_rsq[i]; }
+        else if (j == i) { l = 1.0 / s_rsq[i]; x = s_rsq[i]; xt = x; }
+        else xt = C[j * MS + i] * s_rsq[j];                 // LinvT[i][j] = Linv[j][i], i < j
+        P.Lu64[idx] = l; P.Linv64[idx] = x;
+        P.Linv32[idx] = (float)x;
+        P.LinvT32[idx] = (float)xt;
+    }
+    double s = 0.0;
+    for (int i = tid; i < M; i += NT) s -= log(s_rsq[i]);          // sum log diag Lu = -sum log d^-1/2
+    s = warp_sum_d(s);
+    __shared__ double red[32];
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < NW; ++w) t += red[w];
+        P.scal[0] = t; P.scal[2] = 0.0; P.scal[3] = 0.0;
+        P.scal[5] = (double)(t1 - t0); P.scal[6] = (double)(t2 - t1); P.scal[7] = (double)(clock64() - t2);
+    }
+}
+
+// tuning knobs (dsdgp_set_option "prep_algo" / "prep_threads"): 2 = k_prepA_c4 (default where M <= 128), 1 = k_prepA_ldl (default where it fits), 0 = k_prepA
+static int g_prep_algo = 2, g_prep_threads = 512;
 void small_matrix_set_tuning(int algo, int threads) {
     if (algo >= 0) g_prep_algo = algo;
     if (threads == 256 || threads == 512 || threads == 1024) g_prep_threads = threads;
@@ -345,7 +521,12 @@ void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* 
     size_t sm = 2 * (size_t)Mmax * Mmax * sizeof(double);
     int use_smem = sm <= 200 * 1024;
     const size_t sm_ldl = 2 * (size_t)Mmax * (Mmax | 1) * sizeof(double);
-    if (g_prep_algo == 1 && Mmax <= 128 && sm_ldl <= 200 * 1024) {
+    const size_t sm_c4 = (size_t)Mmax * 129 * sizeof(double);
+    if (g_prep_algo == 2 && Mmax <= 128) {
+        if (g_prep_threads == 256) k_prepA_c4<256><<<ls.L, 256, sm_c4, st>>>(ls, jitter, acc);
+        else if (g_prep_threads == 1024) k_prepA_c4<1024><<<ls.L, 1024, sm_c4, st>>>(ls, jitter, acc);
+        else k_prepA_c4<512><<<ls.L, 512, sm_c4, st>>>(ls, jitter, acc);
+    } else if (g_prep_algo == 1 && Mmax <= 128 && sm_ldl <= 200 * 1024) {
         if (g_prep_threads == 256) k_prepA_ldl<256><<<ls.L, 256, sm_ldl, st>>>(ls, jitter, acc);
         else if (g_prep_threads == 1024) k_prepA_ldl<1024><<<ls.L, 1024, sm_ldl, st>>>(ls, jitter, acc);
         else k_prepA_ldl<512><<<ls.L, 512, sm_ldl, st>>>(ls, jitter, acc);
@@ -678,6 +859,9 @@ void launch_result(const Accum* acc, const float* elbo_hi_lo, int use_hi_lo, dou
 
 cudaError_t small_matrix_init() {
     cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_prepA_c4<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
+    if ((e = cudaFuncSetAttribute(k_prepA_c4<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
+    if ((e = cudaFuncSetAttribute(k_prepA_c4<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_prepA_ldl<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_prepA_ldl<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
     if ((e = cudaFuncSetAttribute(k_prepA_ldl<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))) return e;
