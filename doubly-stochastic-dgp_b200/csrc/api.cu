@@ -97,7 +97,7 @@ struct dsdgp_ctx {
     float* Wbuf[DSDGP_MAX_LAYERS];
     cudaStream_t stream2;                       // side branch of the step DAG (KL prep, row reductions)
     cudaStream_t stream3;                       // second side branch: per-layer gradient assembly behind the row reductions
-    cudaEvent_t ev_dag[2 * DSDGP_MAX_LAYERS + 4];
+    cudaEvent_t ev_dag[2 * DSDGP_MAX_LAYERS + 8];
     bool overlap;
     bool fin_per_layer;
     // step scalars
@@ -275,7 +275,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     CK(dmalloc(&c->Yd, (size_t)desc->N_max * desc->D_y));
     CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
-    for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_dag[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 8; ++i) CK(cudaEventCreateWithFlags(&c->ev_dag[i], cudaEventDisableTiming));
     c->overlap = true; c->fin_per_layer = true;
     (void)Dmax; (void)Mmax;
     {
@@ -347,7 +347,7 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     for (int i = 0; i < 2 * (5 + 3 * DSDGP_MAX_LAYERS); ++i) cudaEventDestroy(c->prof_ev[i]);
     for (int i = 0; i < 16; ++i) cudaEventDestroy(c->sa_ev[i]);
     cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3);
-    for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 4; ++i) cudaEventDestroy(c->ev_dag[i]);
+    for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 8; ++i) cudaEventDestroy(c->ev_dag[i]);
     cudaStreamDestroy(c->stream);
     delete c;
     return DSDGP_OK;
@@ -433,10 +433,20 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         CK(cudaMemsetAsync(c->grads, 0, (c->n_params + 2) * sizeof(float), st));
     }
     PROF_BEGIN(0);
-    launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, st, side ? c->stream2 : st, c->ev_dag[0], nl);
     bool any_tc = false;
     for (int l = 0; l < L; ++l) any_tc |= c->path == 1 && tc_fwd_supported(c->ls.l[l]);
-    if (any_tc) launch_pack_fwd(c->ls, st, nl);
+    const bool split_pack = any_tc && side;
+    if (split_pack) {       // the q_sqrt weight tiles depend on parameters only: pack them beside the factorisation
+        CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 2], st));
+        CK(cudaStreamWaitEvent(c->stream2, c->ev_dag[2 * DSDGP_MAX_LAYERS + 2], 0));
+        launch_pack_fwd(c->ls, 2, c->stream2, nl);
+        CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 4], c->stream2));
+    }
+    launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, st, side ? c->stream2 : st, c->ev_dag[0], nl);
+    if (split_pack) {
+        launch_pack_fwd(c->ls, 1, st, nl);
+        CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 4], 0));
+    } else if (any_tc) launch_pack_fwd(c->ls, 0, st, nl);
     PROF_END(0);
     // forward
     const bool chain = c->chain && c->path == 1 && mode != MODE_PROPAGATE && tc_chain_fwd_supported(c->ls);

@@ -197,7 +197,7 @@ cudaError_t layer_kernels_init();
 cudaError_t layer_tc_init();
 bool tc_fwd_supported(const LayerDev& P);
 size_t tc_fwd_pack_bytes(int M, int D, int white);
-void launch_pack_fwd(const LayerSet& ls, cudaStream_t st, long long* nlaunch);
+void launch_pack_fwd(const LayerSet& ls, int part, cudaStream_t st, long long* nlaunch);
 void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nlaunch);
 bool tc_chain_fwd_supported(const LayerSet& ls);
 void launch_chain_fwd_tc(const LayerSet& ls, const FwdChain& fc, int num_sms, cudaStream_t st, long long* nlaunch);

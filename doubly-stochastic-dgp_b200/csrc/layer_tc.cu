@@ -20,16 +20,19 @@
 // ----------------------------------------------------------------------------------------------
 // weight packing (layout: tc_pack.cuh).  One thread per stored element; hi = tf32(x), lo = tf32(x - hi).
 // ----------------------------------------------------------------------------------------------
-__global__ void k_pack_fwd(LayerSet ls) {
+// part 0: every block; 1: the four Linv blocks (need this step's factorisation); 2: the q_sqrt blocks (parameters only --
+// packed on the side branch of the step DAG while the factorisation runs)
+__global__ void k_pack_fwd(LayerSet ls, int part) {
     const LayerDev& P = ls.l[blockIdx.y];
     if (!P.wpack_fwd) return;
     const int M = P.M, D = P.Dout, nkb = tcp::nkb_of(M);
     const uint32_t slot = tcp::slot_bytes(M);
     const int nblk = tcp::num_blocks(D);
     const int per_blk = nkb * 128 * 32;                 // (kb, n, kk) index space; rows outside a band are skipped
-    const size_t total = (size_t)nblk * per_blk;
+    const int blk0 = part == 2 ? 4 : 0, blk1 = part == 1 ? 4 : nblk;
+    const size_t total = (size_t)(blk1 - blk0) * per_blk;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int blk = (int)(e / per_blk), w = (int)(e % per_blk), kb = w >> 12, n = (w >> 5) & 127, kk = w & 31, k = kb * 32 + kk;
+        const int blk = blk0 + (int)(e / per_blk), w = (int)(e % per_blk), kb = w >> 12, n = (w >> 5) & 127, kk = w & 31, k = kb * 32 + kk;
         const int pat = (blk < 2 || blk >= 4 + D) ? tcp::PAT_LE : tcp::PAT_GE;
         const int r0 = tcp::band_row0(pat, kb), nr = tcp::band_rows(pat, M, kb);
         if (n < r0 || n >= r0 + nr) continue;
@@ -54,8 +57,8 @@ __global__ void k_pack_fwd(LayerSet ls) {
     }
 }
 
-void launch_pack_fwd(const LayerSet& ls, cudaStream_t st, long long* nl) {
-    k_pack_fwd<<<dim3(96, ls.L), 256, 0, st>>>(ls);
+void launch_pack_fwd(const LayerSet& ls, int part, cudaStream_t st, long long* nl) {
+    k_pack_fwd<<<dim3(part == 1 ? 24 : 96, ls.L), 256, 0, st>>>(ls, part);
     *nl += 1;
 }
 

@@ -124,6 +124,22 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int row = tile * 128 + t;
             const bool valid = row < R;
+            // pull the next tile's row slices towards L1 while this tile is converted and multiplied: the row threads are
+            // long-scoreboard bound on exactly these loads (46% of the stall samples, profiles/r1b_big3_ncu_stalls.txt)
+            if (it + 1 < my_tiles) {
+                const int nrow = row + 128 * (int)gridDim.x;
+                if (nrow < R) {
+                    const char* pu = reinterpret_cast<const char*>(U + (size_t)nrow * M + c_lo);
+                    const int nbytes = 4 * (c_hi - c_lo);
+                    for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pu + o));
+                    if (is_g) {
+                        const char* pw = reinterpret_cast<const char*>(W + (size_t)nrow * M + c_lo);
+                        for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pw + o));
+                    } else if (half == 0) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(vbar + (size_t)nrow * D)));
+                    }
+                }
+            }
             // this half's slice of the row(s), tf32-rounded, kept in registers
             float4 uv[16];
 #pragma unroll
@@ -235,9 +251,15 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                 __syncwarp();
                 tmem_ld8(lane_addr + dcol + c0, v);
                 if (i < M) {
+                    float* dst = &out[(size_t)i * ldo + c0];
+                    if ((ldo & 3) == 0 && c0 + 8 <= ncols) {       // 16-byte aligned: two vector reductions instead of eight scalar
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+                    } else {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (c0 + u < ncols) atomicAdd(&out[(size_t)i * ldo + c0 + u], v[u]);
+                        for (int u = 0; u < 8; ++u)
+                            if (c0 + u < ncols) atomicAdd(dst + u, v[u]);
+                    }
                 }
             }
         }
