@@ -4,11 +4,11 @@
 // MN-major shared-memory layout tcgen05 accepts is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:92): blocks of
 // 32 features (128 B rows), 4 k-rows per swizzle atom, 32-byte granules XOR-ed with the k-row index (Swizzle<2,5,2>);
 // the row tile is written as [feature block][128 rows][32 features] in that pattern; one UMMA k-step = 8 rows.
-// Grid: x = row split, y = output group (up to three P_d's (+ qmubar on the last) per CTA -- TMEM holds 512
-// columns -- and one group for G).  Each CTA keeps its accumulators in TMEM over all its row tiles and flushes
-// once with atomics.  P_d and qmubar are 1xTF32 (gradients; tolerance in tests/test_gpu_parity.py); G feeds the
-// Kuu adjoint whose kernel-hyper-parameter sums cancel heavily, so it is accumulated as 3xTF32
-// (W_hi U_hi + W_lo U_hi + W_hi U_lo: three CTA groups, one per pass, summed by the flush atomics).
+// Grid (1-D): output groups x row splits -- up to three P_d's (+ qmubar on the last) per P-group CTA (TMEM holds 512
+// columns) and one group for G.  Each CTA keeps its accumulators in TMEM over all its row tiles and flushes once with
+// vector reductions.  P_d and qmubar are 1xTF32 (gradients; tolerance in tests/test_gpu_parity.py); G feeds the Kuu
+// adjoint whose kernel-hyper-parameter sums cancel heavily, so it is accumulated as 3xTF32: the G CTA runs
+// W_hi U_hi + W_hi U_lo and then W_lo U_hi into ONE accumulator (two sub-iterations per row tile).
 // Math: tests/algo_mirror.py::layer_bwdB.
 #include "dsdgp_internal.cuh"
 #include "tc_common.cuh"
@@ -38,7 +38,8 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mnmajor(uint32_t smem_addr, 
 
 __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, const float* __restrict__ U,
                                                                  const float* __restrict__ W, const float* __restrict__ mubar,
-                                                                 const float* __restrict__ vbar, int R, int ngroups_d) {
+                                                                 const float* __restrict__ vbar, int R, int ngroups_d,
+                                                                 int nsplit_p, int nsplit_g) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw_r[];
     const uint32_t sbase = (smem_u32(smem_raw_r) + 1023u) & ~1023u;
@@ -51,15 +52,20 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
 
     const int M = P.M, D = P.Dout, NPAD = (M + 15) & ~15;
     const int warp = threadIdx.x >> 5;
-    const int group = blockIdx.y;
-    const bool is_g = group >= ngroups_d;                 // the G = W^T U groups: one per 3xTF32 pass
-    const int pass = is_g ? group - ngroups_d : 0;        // 0: W_hi U_hi, 1: W_lo U_hi, 2: W_hi U_lo
+    // 1-D grid: ngroups_d P-groups of nsplit_p row splits each, then ONE G group of nsplit_g splits.  The G group does the
+    // three 3xTF32 passes itself (W_hi U_hi + W_hi U_lo, then W_lo U_hi, all into one TMEM accumulator): a row tile costs it
+    // ~1.5x a P-group's, hence its own (larger) number of splits.
+    const bool is_g = (int)blockIdx.x >= ngroups_d * nsplit_p;
+    const int group = is_g ? ngroups_d : (int)blockIdx.x / nsplit_p;
+    const int split = is_g ? (int)blockIdx.x - ngroups_d * nsplit_p : (int)blockIdx.x % nsplit_p;
+    const int gsz = is_g ? nsplit_g : nsplit_p;
     const int d0 = group * 3;
     const int nd = is_g ? 0 : min(3, D - d0);             // P_d's of this CTA
     const bool has_q = !is_g && group == ngroups_d - 1;   // qmubar rides with the last P group
     const int nb = is_g ? 1 : nd + (has_q ? 1 : 0);       // B operands per row tile
     const int ntiles = (R + 127) / 128;
-    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int my_tiles = (split < ntiles) ? (ntiles - 1 - split) / gsz + 1 : 0;
+    const int n_it = is_g ? 2 * my_tiles : my_tiles;      // G: two sub-iterations per row tile (A = W_hi, then A = W_lo)
 
     if (threadIdx.x == 0) {
         mbar_init(bar_aready, RR_ROWTHREADS); mbar_init(bar_afree, 1);
@@ -83,23 +89,25 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
         // ===================== MMA issuer =====================
         const uint32_t id_full = make_idesc_tf32(128, NPAD, 1, 1), id_q = make_idesc_tf32(128, 16, 1, 1);
         int bcount = 0;          // B operands consumed so far (buffer = bcount & 1, phase = (bcount >> 1) & 1)
-        for (int it = 0; it < my_tiles; ++it) {
+        for (int it = 0; it < n_it; ++it) {
             mbar_wait(bar_aready, it & 1);
-            for (int b = 0; b < nb; ++b, ++bcount) {
+            const int nbi = is_g ? ((it & 1) ? 1 : 2) : nb;
+            for (int b = 0; b < nbi; ++b, ++bcount) {
                 const int buf = bcount & 1;
                 mbar_wait(bar_bready + 8 * buf, (bcount >> 1) & 1);
                 tc_fence_after();
                 const bool isq = has_q && b == nd;
-                const uint32_t dcol = isq ? 384u : 128u * (uint32_t)b;
+                const uint32_t dcol = is_g ? 0u : (isq ? 384u : 128u * (uint32_t)b);
                 if (elect_one_rr()) {
                     const uint64_t ad0 = make_desc_sw128_mnmajor(A_t, 16384);
                     const uint64_t bd0 = make_desc_sw128_mnmajor(B_t + buf * RR_TILE_BYTES, 16384);
                     const uint32_t idd = isq ? id_q : id_full;
 #pragma unroll
                     for (int ks = 0; ks < 16; ++ks)      // one k-step = 8 rows = 1024 B: +64 in the (>>4) start-address field
-                        mma_tf32(tmem + dcol, ad0 + (uint64_t)(ks * 64), bd0 + (uint64_t)(ks * 64), idd, (it == 0 && ks == 0) ? 0u : 1u);
+                        mma_tf32(tmem + dcol, ad0 + (uint64_t)(ks * 64), bd0 + (uint64_t)(ks * 64), idd,
+                                 (it == 0 && ks == 0 && (!is_g || b == 0)) ? 0u : 1u);
                     mma_commit(bar_bfree + 8 * buf);
-                    if (b == nb - 1) mma_commit(bar_afree);
+                    if (b == nbi - 1) mma_commit(bar_afree);
                 }
                 __syncwarp();
             }
@@ -120,14 +128,16 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
         const int c_lo = half ? NH : 0, c_hi = half ? NPAD : NH;      // this thread's feature range (<= 64 wide)
         const float* Asrc = is_g ? W : U;
         int bcount = 0;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        for (int it = 0; it < n_it; ++it) {
+            const int tit = is_g ? (it >> 1) : it, sub = is_g ? (it & 1) : 0;
+            const int tile = split + tit * gsz;
             const int row = tile * 128 + t;
             const bool valid = row < R;
+            const int nbi = is_g ? (sub ? 1 : 2) : nb;
             // pull the next tile's row slices towards L1 while this tile is converted and multiplied: the row threads are
             // long-scoreboard bound on exactly these loads (46% of the stall samples, profiles/r1b_big3_ncu_stalls.txt)
-            if (it + 1 < my_tiles) {
-                const int nrow = row + 128 * (int)gridDim.x;
+            if (tit + 1 < my_tiles && sub == 0) {
+                const int nrow = row + 128 * gsz;
                 if (nrow < R) {
                     const char* pu = reinterpret_cast<const char*>(U + (size_t)nrow * M + c_lo);
                     const int nbytes = 4 * (c_hi - c_lo);
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                         }
                     }
                     float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-                    if (pass == 1) hi = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
+                    if (sub == 1) hi = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
                     store4(A_t, c0, hi);
                 }
             }
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
             fence_proxy_async();
             mbar_arrive(bar_aready);
             // ---- B operands
-            for (int b = 0; b < nb; ++b, ++bcount) {
+            for (int b = 0; b < nbi; ++b, ++bcount) {
                 const int buf = bcount & 1;
                 if (bcount >= 2) mbar_wait(bar_bfree + 8 * buf, ((bcount >> 1) - 1) & 1);
                 const uint32_t Bb = B_t + buf * RR_TILE_BYTES;
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                         if (c0 < c_hi) {
                             float4 v = uv[c];
                             float4 hi = make_float4(tf32_rna(v.x * sc), tf32_rna(v.y * sc), tf32_rna(v.z * sc), tf32_rna(v.w * sc));
-                            if (pass == 2) hi = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
+                            if (is_g && b == 1) hi = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));   // U_lo
                             store4(Bb, c0, hi);
                         }
                     }
@@ -276,10 +286,12 @@ cudaError_t rowred_tc_init() {
 }
 
 void launch_bwd_rowred_tc(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nl) {
-    const int ngroups_d = (P.Dout + 2) / 3, ngroups = ngroups_d + 3;
+    const int ngroups_d = (P.Dout + 2) / 3;
     const int ntiles = (a.R + 127) / 128;
-    int nsplit = max(1, min(ntiles, num_sms / ngroups));
-    k_layer_rowred_tc<<<dim3(nsplit, ngroups), RR_THREADS, 3 * RR_TILE_BYTES + 1024 + 256, st>>>(P, a.U, a.W, a.mubar, a.vbar, a.R,
-                                                                                                 ngroups_d);
+    // the G group's row tile costs ~1.5x a P group's (five operand tiles and two row sets instead of four and one)
+    int nsplit_p = max(1, min(ntiles, (int)(num_sms / (ngroups_d + 1.5))));
+    int nsplit_g = max(1, min(ntiles, num_sms - ngroups_d * nsplit_p));
+    k_layer_rowred_tc<<<ngroups_d * nsplit_p + nsplit_g, RR_THREADS, 3 * RR_TILE_BYTES + 1024 + 256, st>>>(
+        P, a.U, a.W, a.mubar, a.vbar, a.R, ngroups_d, nsplit_p, nsplit_g);
     *nl += 1;
 }
