@@ -297,50 +297,57 @@ def main_b200(args):
             res["e2e"] = {"value": units * K / dt, "unit": "steps/s",
                           "h2d_bytes_per_step": int(Xh[0].nbytes + Yh[0].nbytes), "d2h_bytes_per_step": 16,
                           "timing": "host wall clock around K public-API calls (model.train_step), each returning the ELBO"}
-        # ---- per-stage profile (eager launches bracketed by events) -> dominant kernel and its roofline
         if want_profile:
-            ctx.set_option("profile", 1)
-            acc = None
-            reps = 5
-            for i in range(reps + 1):
-                dev_step(5000 + i, True)
-                p = np.array(ctx.profile())
-                if i > 0:
-                    acc = p if acc is None else acc + p
-            ctx.set_option("profile", 0)
-            p = acc / reps
-            L = len(WORKLOAD['dims']) - 1
-            names = ["prep(Kuu,chol,KL)", "likelihood", "grad-assembly", "allreduce", "adam"]
-            for l in range(L):
-                names += [f"layer{l + 1}.fwd", f"layer{l + 1}.bwd_rows", f"layer{l + 1}.rowred"]
-            fwd_fl, fixed, step_fl = algorithmic_flops(WORKLOAD['dims'], N_loc, WORKLOAD['M'], S)
-            chained = all(p[5 + 3 * l] == 0 for l in range(1, L))     # persistent kernel: all layers' forward in one launch
-            if chained:
-                names[5] = "fwd_chain(all layers, one persistent launch)"
-                fwd_fl = list(fwd_fl)
-                fwd_fl[0] = float(sum(fwd_fl))
-            res["stage_ms"] = {n: round(float(v), 4) for n, v in zip(names, p)}
-            top = int(np.argmax(p[5:])) + 5
-            l = (top - 5) // 3
-            peaks, how = measured_peaks()
-            peak_tf32 = peaks["bf16_tflops"] / 2.0
-            ach = fwd_fl[l] / (p[top] * 1e-3) / 1e12
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
-            if os.path.exists(tpath):
-                with open(tpath) as f:
-                    traffic = json.load(f).get("fwd_chain" if names[top].startswith("fwd_chain") else names[top].split(".")[1])
-            res["roofline"] = {
-                "bound": "tensor", "kernel": names[top], "achieved": ach, "peak": peak_tf32, "unit": "TFLOP/s",
-                "frac": ach / peak_tf32, "traffic": traffic,
-                "note": f"algorithmic flops/launch = rows*f(l) = {fwd_fl[l]:.4g} (SURVEY 8(d): each of forward, row-backward "
-                        f"and row-reduction kernels of a layer carries rows*f(l)); kernel time from CUDA events around the "
-                        f"launch in an eager (non-graph) pass; peak = {how} bf16_tflops/2 = TF32-dense equivalent (the kernel "
-                        "issues tcgen05 kind::tf32, ~1.3-1.4x the algorithmic MMA work because of the 3xTF32 stages); "
-                        "traffic = dram read+write bytes per launch from the ncu --set full capture summarised in profiles/",
-                "step_achieved": step_fl / (tot_ms / K * 1e-3) / 1e12, "step_algorithmic_gflop": step_fl / 1e9}
+            try:
+                profile_leg(ctx, dev_step, res, N_loc, tot_ms)
+            except Exception as ex:      # an auxiliary leg must not cost the headline line
+                res["roofline_error"] = f"{type(ex).__name__}: {ex}"
         m._ctx.close()
         return res
+
+    def profile_leg(ctx, dev_step, res, N_loc, tot_ms):
+        """Per-stage device times (eager launches bracketed by CUDA events) -> dominant kernel and its roofline entry."""
+        # ---- per-stage profile (eager launches bracketed by events) -> dominant kernel and its roofline
+        ctx.set_option("profile", 1)
+        acc = None
+        reps = 5
+        for i in range(reps + 1):
+            dev_step(5000 + i, True)
+            p = np.array(ctx.profile())
+            if i > 0:
+                acc = p if acc is None else acc + p
+        ctx.set_option("profile", 0)
+        p = acc / reps
+        L = len(WORKLOAD['dims']) - 1
+        names = ["prep(Kuu,chol,KL)", "likelihood", "grad-assembly", "allreduce", "adam"]
+        for l in range(L):
+            names += [f"layer{l + 1}.fwd", f"layer{l + 1}.bwd_rows", f"layer{l + 1}.rowred"]
+        fwd_fl, fixed, step_fl = algorithmic_flops(WORKLOAD['dims'], N_loc, WORKLOAD['M'], S)
+        chained = all(p[5 + 3 * l] == 0 for l in range(1, L))     # persistent kernel: all layers' forward in one launch
+        if chained:
+            names[5] = "fwd_chain(all layers, one persistent launch)"
+            fwd_fl = list(fwd_fl)
+            fwd_fl[0] = float(sum(fwd_fl))
+        res["stage_ms"] = {n: round(float(v), 4) for n, v in zip(names, p)}
+        top = int(np.argmax(p[5:])) + 5
+        l = (top - 5) // 3
+        peaks, how = measured_peaks()
+        peak_tf32 = peaks["bf16_tflops"] / 2.0
+        ach = fwd_fl[l] / (p[top] * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("fwd_chain" if names[top].startswith("fwd_chain") else names[top].split(".")[1])
+        res["roofline"] = {
+            "bound": "tensor", "kernel": names[top], "achieved": ach, "peak": peak_tf32, "unit": "TFLOP/s",
+            "frac": ach / peak_tf32, "traffic": traffic,
+            "note": f"algorithmic flops/launch = rows*f(l) = {fwd_fl[l]:.4g} (SURVEY 8(d): each of forward, row-backward "
+                    f"and row-reduction kernels of a layer carries rows*f(l)); kernel time from CUDA events around the "
+                    f"launch in an eager (non-graph) pass; peak = {how} bf16_tflops/2 = TF32-dense equivalent (the kernel "
+                    "issues tcgen05 kind::tf32, ~1.3-1.4x the algorithmic MMA work because of the 3xTF32 stages); "
+                    "traffic = dram read+write bytes per launch from the ncu --set full capture summarised in profiles/",
+            "step_achieved": step_fl / (tot_ms / K * 1e-3) / 1e12, "step_algorithmic_gflop": step_fl / 1e9}
 
     primary = run_mode(args.scaling, want_profile=True, want_e2e=not args.no_e2e)
     other = None
@@ -377,6 +384,8 @@ def main_b200(args):
             "clocks": primary["clocks"], "e2e": primary["e2e"], "roofline": primary["roofline"], "cpu_baseline": cpu,
             "stage_ms": primary["stage_ms"], "other_scaling": other,
         }
+        if primary.get("roofline_error"):
+            out["roofline_error"] = primary["roofline_error"]
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
