@@ -176,16 +176,44 @@ class DGP_Base(Parameterized):
         return self.X, self.Y
 
     # ------------------------------------------------------------------ reference API
+    def _plan(self, N, S, full_cov=False):
+        """Row and sample chunks of one prediction call.  Normally a single chunk (the context is re-created with larger
+        workspaces when a call outgrows them); once training has started the optimiser state lives in the context, so a
+        larger prediction (the reference predicts with S=100 after training with num_samples=1, demos/run_regression.py:
+        108-113) is evaluated in chunks instead -- exact, since with full_cov=False every (sample, row) is independent
+        (layers.py:71-74), and with full_cov=True every sample is (layers.py:66-69)."""
+        c = self._ctx
+        if c is None or self._adam is None or (N <= c.N_max and S <= c.S_max):
+            return [(0, N)], [(0, S)]
+        if full_cov and N > c.N_max:
+            raise RuntimeError(f"full_cov prediction needs all N={N} rows at once (N_max={c.N_max} after training started)")
+        rows = [(a, min(a + c.N_max, N)) for a in range(0, N, c.N_max)]
+        samples = [(a, min(a + c.S_max, S)) for a in range(0, S, c.S_max)]
+        return rows, samples
+
+    @staticmethod
+    def _cut(zs, s0, s1, n0, n1):
+        return None if zs is None else [None if z is None else np.asarray(z)[s0:s1, n0:n1] for z in zs]
+
     def propagate(self, X, full_cov=False, S=1, zs=None):
-        """dgp.py:61-76 -> (Fs, Fmeans, Fvars), lists of (S,N,D_l) float64 arrays."""
+        """dgp.py:61-76 -> (Fs, Fmeans, Fvars), lists of (S,N,D_l) float64 arrays ((S,N,N,D_l) variances with full_cov)."""
         X = np.asarray(X, dtype=np.float64)
-        ctx = self._ensure_ctx(X.shape[0], S)
-        if full_cov:      # Fvars[l] is (S,N,N,D_l): float64 device pipeline of csrc/full_cov.cu
-            Fs, Fmeans, Fvars = ctx.propagate_full_cov(X, S, zs=zs, seed=self._next_seed())
-        else:
-            Fs, Fmeans, Fvars = ctx.propagate(X, S, zs=zs, seed=self._next_seed())
-        f64 = lambda lst: [a.astype(np.float64) for a in lst]
-        return f64(Fs), f64(Fmeans), f64(Fvars)
+        N = X.shape[0]
+        rows, samples = self._plan(N, S, full_cov)
+        parts = []
+        for s0, s1 in samples:
+            line = []
+            for n0, n1 in rows:
+                ctx = self._ensure_ctx(n1 - n0, s1 - s0)
+                fn = ctx.propagate_full_cov if full_cov else ctx.propagate     # full_cov: csrc/full_cov.cu (float64 pipeline)
+                line.append(fn(X[n0:n1], s1 - s0, zs=self._cut(zs, s0, s1, n0, n1), seed=self._next_seed()))
+            parts.append(line)
+        L = len(self.layers)
+        out = []
+        for which in range(3):
+            out.append([np.concatenate([np.concatenate([cell[which][l] for cell in line], axis=1) for line in parts], axis=0)
+                        .astype(np.float64) for l in range(L)])
+        return out[0], out[1], out[2]
 
     def _build_predict(self, X, full_cov=False, S=1, zs=None):
         """dgp.py:78-81."""
@@ -236,16 +264,34 @@ class DGP_Base(Parameterized):
         """dgp.py:116-119: likelihood.predict_mean_and_var of the last layer's marginals, (S,N,D) each; the likelihood
         epilogue runs on the device (csrc/lik_adam.cu)."""
         Xnew = np.asarray(Xnew, dtype=np.float64)
-        ctx = self._ensure_ctx(Xnew.shape[0], num_samples)
-        mean, var = ctx.predict_y(Xnew, num_samples, zs=zs, seed=self._next_seed())
-        return mean.astype(np.float64), var.astype(np.float64)
+        rows, samples = self._plan(Xnew.shape[0], num_samples)
+        means, vars_ = [], []
+        for s0, s1 in samples:
+            ms, vs = [], []
+            for n0, n1 in rows:
+                ctx = self._ensure_ctx(n1 - n0, s1 - s0)
+                m, v = ctx.predict_y(Xnew[n0:n1], s1 - s0, zs=self._cut(zs, s0, s1, n0, n1), seed=self._next_seed())
+                ms.append(m); vs.append(v)
+            means.append(np.concatenate(ms, 1)); vars_.append(np.concatenate(vs, 1))
+        return np.concatenate(means, 0).astype(np.float64), np.concatenate(vars_, 0).astype(np.float64)
 
     def predict_density(self, Xnew, Ynew, num_samples, zs=None):
-        """dgp.py:121-126: logsumexp_S(likelihood.predict_density(Fmean, Fvar, Ynew) - log S), on the device."""
+        """dgp.py:121-126: logsumexp_S(likelihood.predict_density(Fmean, Fvar, Ynew) - log S), on the device.  When the
+        samples have to be evaluated in chunks (see _plan) the per-chunk log-mean-exps are merged here."""
         Xnew = np.asarray(Xnew, dtype=np.float64)
-        ctx = self._ensure_ctx(Xnew.shape[0], num_samples)
-        out = ctx.predict_density(Xnew, np.asarray(Ynew, dtype=np.float64), num_samples, zs=zs, seed=self._next_seed())
-        return out.astype(np.float64)
+        Ynew = np.asarray(Ynew, dtype=np.float64)
+        rows, samples = self._plan(Xnew.shape[0], num_samples)
+        cols = []
+        for n0, n1 in rows:
+            acc = None
+            for s0, s1 in samples:
+                ctx = self._ensure_ctx(n1 - n0, s1 - s0)
+                d = ctx.predict_density(Xnew[n0:n1], Ynew[n0:n1], s1 - s0, zs=self._cut(zs, s0, s1, n0, n1),
+                                        seed=self._next_seed()).astype(np.float64)
+                d = d + np.log((s1 - s0) / float(num_samples))          # chunk's share of the mean over all S
+                acc = d if acc is None else np.logaddexp(acc, d)
+            cols.append(acc)
+        return np.concatenate(cols, 0)
 
     # ------------------------------------------------------------------ training (AdamOptimizer.minimize)
     def adam_init(self, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):

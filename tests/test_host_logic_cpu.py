@@ -40,9 +40,9 @@ def test_parameters_reach_the_device_and_come_back():
     z0 = m.layers[0].feature.Z.value
     m.train_step(zs=prob['zs'])
     assert np.abs(m.layers[0].feature.Z.value - z0).max() > 0
-    # growing N / S after training started is refused (Adam state lives on the device)
+    # the training entry points refuse to outgrow the workspaces once training has started (Adam state lives on the device)
     with pytest.raises(RuntimeError):
-        m.predict_f(np.zeros((10000, 3)), 2)
+        m.compute_log_likelihood(X=np.zeros((10000, 3)), Y=np.zeros((10000, 1)))
 
 
 def test_set_trainable_is_forwarded_and_respected():
@@ -167,3 +167,40 @@ def test_standalone_layer_services():
     assert abs(lay.KL() - float(olay.KL())) < 1e-8
     f3, _, _ = lay.sample_from_conditional(X)           # z=None draws on the host and still goes through the device
     assert f3.shape == (S, N, D)
+
+
+def test_predictions_larger_than_the_workspaces_after_training_are_chunked():
+    """demos/run_regression.py:108-113 predicts with S=100 in batches of 1000 rows after training with num_samples=1: once
+    Adam state lives in the context it cannot be re-created, so the host evaluates the call in (row, sample) chunks."""
+    prob = round_f32(make_problem(seed=6, dims=[3, 3, 2], N=20, M=6, S=2, inner_q_scale=0.3))
+    m = _model(prob)
+    m.adam_init(0.01)
+    m.train_step(zs=prob['zs'])
+    ctx = m._ctx
+    ctx.N_max, ctx.S_max = 16, 4                    # pretend small workspaces
+    rng = np.random.default_rng(0)
+    N, S = 37, 10
+    Xs = np.float32(rng.normal(size=(N, 3))).astype(np.float64)
+    Ys = np.float32(rng.normal(size=(N, 2))).astype(np.float64)
+    zs = [np.float32(rng.normal(size=(S, N, 3))).astype(np.float64), np.float32(rng.normal(size=(S, N, 2))).astype(np.float64)]
+    assert m._plan(N, S) == ([(0, 16), (16, 32), (32, 37)], [(0, 4), (4, 8), (8, 10)])
+    # reference values: the same (device-side) parameters in an unchunked oracle model
+    o = ctx._model(S)
+    oFs, oFm, oFv = o.propagate(Xs, S=S, zs=zs)
+    Fs, Fm, Fv = m.propagate(Xs, S=S, zs=zs)
+    assert m._ctx is ctx                             # not re-created
+    for l in range(2):
+        assert Fs[l].shape == (S, N, prob['dims'][l + 1])
+        assert_allclose(Fm[l], oFm[l].numpy(), rtol=1e-5, atol=1e-6)
+        assert_allclose(Fs[l], oFs[l].numpy(), rtol=1e-5, atol=1e-6)
+    ym, yv = m.predict_y(Xs, S, zs=zs)
+    om, ov = o.predict_y(Xs, S, zs=zs)
+    assert_allclose(ym, om.numpy(), rtol=1e-5, atol=1e-6)
+    assert_allclose(yv, ov.numpy(), rtol=1e-5, atol=1e-6)
+    d = m.predict_density(Xs, Ys, S, zs=zs)
+    assert_allclose(d, o.predict_density(Xs, Ys, S, zs=zs).numpy(), rtol=1e-4, atol=1e-5)
+    # full_cov: samples may be chunked, rows may not
+    fm, fv = m.predict_f_full_cov(Xs[:12], S)
+    assert fm.shape == (S, 12, 2) and fv.shape == (S, 12, 12, 2)
+    with pytest.raises(RuntimeError):
+        m.predict_f_full_cov(Xs, S)
