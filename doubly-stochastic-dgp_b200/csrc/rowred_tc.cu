@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                 const int nrow = row + 128 * gsz;
                 if (nrow < R) {
                     const char* pu = reinterpret_cast<const char*>(U + (size_t)nrow * M + c_lo);
-                    const int nbytes = 4 * (c_hi - c_lo);
+                    const int nbytes = 4 * (min(c_hi, M) - c_lo);      // stay inside the row (c_hi is padded to 16 features)
                     for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pu + o));
                     if (is_g) {
                         const char* pw = reinterpret_cast<const char*>(W + (size_t)nrow * M + c_lo);
