@@ -104,3 +104,28 @@ def test_minibatch_is_aligned_and_covers_data():
         assert xb.shape == (8, 2) and np.all(yb[:, 0] == xb[:, 0] * 10)
         seen.extend(xb[:, 0].tolist())
     assert set(seen) == set(X[:, 0].tolist())
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/dsdgp.h parses as C99 and a C program links against libdsdgp.so and gets the
+    documented error behaviour (negative code + message, no exception) for an invalid descriptor."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    lib = _ensure_built()
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, "dsdgp.h")])
+    src = tmp_path / "abi.c"
+    src.write_text('#include "dsdgp.h"\n#include <stdio.h>\n#include <string.h>\n'
+                   'int main(void) { dsdgp_ctx* c = 0; dsdgp_desc d; memset(&d, 0, sizeof d);\n'
+                   '  int rc = dsdgp_create(&c, &d); printf("%s|%d|%s\\n", dsdgp_version(), rc, dsdgp_last_error());\n'
+                   '  return (rc == DSDGP_ERR_INVALID && c == 0) ? 0 : 1; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(lib)
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ldsdgp",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ver, rc, msg = out.stdout.strip().split("|")
+    assert ver.startswith("dsdgp") and int(rc) == -1 and "out of range" in msg
