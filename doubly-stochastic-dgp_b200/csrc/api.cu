@@ -281,6 +281,7 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     {
         double* p64 = c->sm64; float* p32 = c->sm32; float* pa = c->accf;
         c->ls.L = L;
+        c->ls.prep_algo = 2; c->ls.prep_threads = 512; c->ls.fin_algo = 1;
         for (int l = 0; l < L; ++l) {
             const dsdgp_layer_desc& d = desc->layers[l];
             const LayerOff& o = c->off[l];
@@ -1035,12 +1036,14 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
         c->graphs.clear(); c->graph_launches.clear();
     }
     else if (n == "fin_algo") {
-        small_matrix_set_fin_algo((int)value);
+        c->ls.fin_algo = (int)value;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     }
-    else if (n == "prep_algo" || n == "prep_threads") {      // library-wide tuning knobs of the fp64 prep kernels
-        small_matrix_set_tuning(n == "prep_algo" ? (int)value : -1, n == "prep_threads" ? (int)value : -1);
+    else if (n == "prep_algo" || n == "prep_threads") {      // kernel selection of the fp64 prep stage (per context)
+        const int v = (int)value;
+        if (n == "prep_algo") { if (v < 0 || v > 2) return set_err(DSDGP_ERR_INVALID, "prep_algo must be 0, 1 or 2"); c->ls.prep_algo = v; }
+        else { if (v != 256 && v != 512 && v != 1024) return set_err(DSDGP_ERR_INVALID, "prep_threads must be 256, 512 or 1024"); c->ls.prep_threads = v; }
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     }

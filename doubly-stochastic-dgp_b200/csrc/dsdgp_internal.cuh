@@ -28,7 +28,13 @@ struct LayerDev {
     float *qmubar;  // M x D     : sum_r u_r mubar_r^T
 };
 
-struct LayerSet { LayerDev l[DSDGP_MAX_LAYERS]; int L; };
+struct LayerSet {
+    LayerDev l[DSDGP_MAX_LAYERS];
+    int L;
+    // host-side kernel selection of the fp64 prep / gradient-assembly stages (dsdgp_set_option "prep_algo", "prep_threads",
+    // "fin_algo"; per context): prep_algo 2 = k_prepA_c4, 1 = k_prepA_ldl, 0 = k_prepA; fin_algo 1 = tiled kernels, 0 = per element
+    int prep_algo, prep_threads, fin_algo;
+};
 
 // Scalars that change every step live in device memory so that a captured CUDA graph can be replayed.
 struct StepArgs {
@@ -208,8 +214,6 @@ cudaError_t rowred_tc_init();
 bool tc_rowred_supported(const LayerDev& P);
 void launch_bwd_rowred_tc(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
 cudaError_t small_matrix_init();
-void small_matrix_set_tuning(int prep_algo, int prep_threads);   // -1: leave as is
-void small_matrix_set_fin_algo(int algo);
 void launch_adam(float* params, float* free_, float* m, float* v, const float* grads, const unsigned char* kinds,
                  const int* tril_m, size_t n, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
 void launch_constrain_init(const float* params, float* free_, const unsigned char* kinds, size_t n, cudaStream_t st,

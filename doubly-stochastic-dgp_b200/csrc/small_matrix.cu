@@ -408,13 +408,6 @@ __global__ void __launch_bounds__(NT) k_prepA_c4(LayerSet ls, double jitter, Acc
     }
 }
 
-// tuning knobs (dsdgp_set_option "prep_algo" / "prep_threads"): 2 = k_prepA_c4 (default where M <= 128), 1 = k_prepA_ldl (default where it fits), 0 = k_prepA
-static int g_prep_algo = 2, g_prep_threads = 512;
-void small_matrix_set_tuning(int algo, int threads) {
-    if (algo >= 0) g_prep_algo = algo;
-    if (threads == 256 || threads == 512 || threads == 1024) g_prep_threads = threads;
-}
-
 // q_sqrtT[d][j][i] = q_sqrt[d][i][j]; scal[1] = sum log diag^2 ; scal[4] = sum q_sqrt^2 + sum q_mu^2
 __global__ void k_qsqrtT(LayerSet ls) {
     const LayerDev& P = ls.l[blockIdx.y];
@@ -522,13 +515,13 @@ void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* 
     int use_smem = sm <= 200 * 1024;
     const size_t sm_ldl = 2 * (size_t)Mmax * (Mmax | 1) * sizeof(double);
     const size_t sm_c4 = (size_t)Mmax * 129 * sizeof(double);
-    if (g_prep_algo == 2 && Mmax <= 128) {
-        if (g_prep_threads == 256) k_prepA_c4<256><<<ls.L, 256, sm_c4, st>>>(ls, jitter, acc);
-        else if (g_prep_threads == 1024) k_prepA_c4<1024><<<ls.L, 1024, sm_c4, st>>>(ls, jitter, acc);
+    if (ls.prep_algo == 2 && Mmax <= 128) {
+        if (ls.prep_threads == 256) k_prepA_c4<256><<<ls.L, 256, sm_c4, st>>>(ls, jitter, acc);
+        else if (ls.prep_threads == 1024) k_prepA_c4<1024><<<ls.L, 1024, sm_c4, st>>>(ls, jitter, acc);
         else k_prepA_c4<512><<<ls.L, 512, sm_c4, st>>>(ls, jitter, acc);
-    } else if (g_prep_algo == 1 && Mmax <= 128 && sm_ldl <= 200 * 1024) {
-        if (g_prep_threads == 256) k_prepA_ldl<256><<<ls.L, 256, sm_ldl, st>>>(ls, jitter, acc);
-        else if (g_prep_threads == 1024) k_prepA_ldl<1024><<<ls.L, 1024, sm_ldl, st>>>(ls, jitter, acc);
+    } else if (ls.prep_algo == 1 && Mmax <= 128 && sm_ldl <= 200 * 1024) {
+        if (ls.prep_threads == 256) k_prepA_ldl<256><<<ls.L, 256, sm_ldl, st>>>(ls, jitter, acc);
+        else if (ls.prep_threads == 1024) k_prepA_ldl<1024><<<ls.L, 1024, sm_ldl, st>>>(ls, jitter, acc);
         else k_prepA_ldl<512><<<ls.L, 512, sm_ldl, st>>>(ls, jitter, acc);
     } else
         k_prepA<<<ls.L, 1024, use_smem ? sm : 0, st>>>(ls, jitter, acc, use_smem);
@@ -793,8 +786,6 @@ __global__ void __launch_bounds__(256) k_fin_kuu_w(LayerSet ls, int lbase) {
     if (lane == 0 && !P.ard) atomicAdd(&P.gls[0], (float)ls_acc);
 }
 
-static int g_fin_algo = 1;         // dsdgp_set_option "fin_algo": 1 = the tiled kernels, 0 = one thread per element
-void small_matrix_set_fin_algo(int a) { g_fin_algo = a; }
 
 __global__ void k_elbo_finish(Accum* acc, const StepArgs* sa, float* glikvar, float* elbo_hi_lo) {
     double e = acc->lik - sa->kl_weight * acc->kl;
@@ -819,7 +810,7 @@ void launch_fin(const LayerSet& ls, int l0, int l1, Accum* acc, const StepArgs* 
         any_white |= ls.l[l].white != 0;
     }
     int nb = (Mmax * Mmax + 255) / 256;
-    if (g_fin_algo == 1) {
+    if (ls.fin_algo == 1) {
         const int nt = (Mmax + FT - 1) / FT;
         k_fin_qsqrt_t<<<dim3(nt * (nt + 1) / 2, Dmax, nL), 256, 0, st>>>(ls, sa, l0);
         k_fin_qmu_w<<<dim3((MDmax + 7) / 8, nL), 256, 0, st>>>(ls, sa, l0);
@@ -835,7 +826,7 @@ void launch_fin(const LayerSet& ls, int l0, int l1, Accum* acc, const StepArgs* 
         *nl += 3;
     }
     k_fin_kbar<<<dim3(nb, nL), 256, 0, st>>>(ls, sa, l0);
-    if (g_fin_algo == 1) k_fin_kuu_w<<<dim3((Mmax + 7) / 8, nL), 256, 0, st>>>(ls, l0);
+    if (ls.fin_algo == 1) k_fin_kuu_w<<<dim3((Mmax + 7) / 8, nL), 256, 0, st>>>(ls, l0);
     else k_fin_kuu<<<dim3((MDin + 255) / 256, nL), 256, 0, st>>>(ls, l0);
     *nl += 2;
 }
