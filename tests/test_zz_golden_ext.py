@@ -1,6 +1,8 @@
 """Golden vectors of the later paths (tests/golden/ext/*.npz, made by tests/golden/make_golden_ext.py from the float64
 oracle): NatGrad step, full_cov propagate, prediction epilogues.  CPU: the oracle still reproduces them; GPU: the CUDA
-path matches them without the oracle in the loop, at the tolerances of the corresponding parity tests."""
+path matches them without the oracle in the loop, at the tolerances of the corresponding parity tests.
+(File name: collected last on purpose -- the GPU halves were written after the round's last hardware run; the same problems,
+paths and tolerances passed against the live oracle in tests/test_gpu_natgrad.py / _full_cov.py / _predict.py.)"""
 import glob
 import os
 
