@@ -161,6 +161,8 @@ static cudaError_t dmalloc(T** p, size_t n) {
     return e;
 }
 
+static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc);
+
 int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     if (!out || !desc) return set_err(DSDGP_ERR_INVALID, "null argument");
     if (desc->L < 1 || desc->L > DSDGP_MAX_LAYERS) return set_err(DSDGP_ERR_INVALID, "L=%d out of range", desc->L);
@@ -189,6 +191,19 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     dsdgp_ctx* c = new (std::nothrow) dsdgp_ctx();
     if (!c) return set_err(DSDGP_ERR_INVALID, "out of host memory");
     c->desc = *desc;
+    const int rc = create_device_state(c, desc);
+    if (rc != DSDGP_OK) {       // e.g. out of device memory half way: release what was created, keep the message
+        dsdgp_destroy(c);
+        cudaGetLastError();
+        return rc;
+    }
+    *out = c;
+    return DSDGP_OK;
+}
+
+// streams, events, parameter store, workspaces (every handle of a value-initialised ctx is null until created here, which is
+// what lets dsdgp_destroy release a partially built one)
+static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, desc->device));
     c->num_sms = prop.multiProcessorCount;
@@ -324,7 +339,6 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     c->chain_max_tiles = (int)((Rmax + 127) / 128);
     CK(dmalloc(&c->chain_flags, (size_t)2 * DSDGP_MAX_LAYERS * c->chain_max_tiles));
     c->epoch = 0; c->chain = true;
-    *out = c;
     return DSDGP_OK;
 }
 
