@@ -140,13 +140,16 @@ def run_cpu_reference(steps, warmup, max_seconds=None):
     for _ in range(warmup):
         one()
     t0 = time.perf_counter()
-    done = 0
+    done, per_step = 0, []
     for _ in range(steps):
+        t1 = time.perf_counter()
         one()
+        per_step.append(time.perf_counter() - t1)
         done += 1
         if max_seconds and time.perf_counter() - t0 > max_seconds:
             break
     dt = time.perf_counter() - t0
+    run_cpu_reference.last_stats = {"median_ms": 1e3 * float(np.median(per_step)), "min_ms": 1e3 * float(np.min(per_step))}
     return done / dt, done, dt, cores
 
 
@@ -160,7 +163,7 @@ def main_reference(args):
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / done, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "BASELINE configs[2]: 5-layer RBF DGP N=1000 M=100 S=20 dims 8-8-8-8-8-1", **WORKLOAD},
-        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", **run_cpu_reference.last_stats,
                          "sample": f"{done} full steps of the same workload; reference restatement (torch-CPU float64, "
                                    "reference-faithful D_out tiling, autograd, Adam), not TF 1.8"},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -360,7 +363,7 @@ def main_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sps, done, dt, cores = run_cpu_reference(steps=args.cpu_steps, warmup=1, max_seconds=25)
-        cpu = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+        cpu = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", **run_cpu_reference.last_stats,
                "sample": f"{done} full steps ({dt:.1f} s) of the same workload: reference restatement (torch-CPU float64, "
                          "reference-faithful tiling, autograd backward, Adam), not TF 1.8"}
 
