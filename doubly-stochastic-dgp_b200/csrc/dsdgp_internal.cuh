@@ -90,6 +90,29 @@ static __device__ __noinline__ float dsdgp_normal(unsigned long long seed, int l
     return (d & 1) ? rad * sn : rad * cs;
 }
 
+// both draws of the Box-Muller pair holding d_even (even) and d_even + 1: bit-identical to dsdgp_normal(.., d_even) and
+// dsdgp_normal(.., d_even + 1) at a quarter of the cost per draw (one Philox block, one log/sincos)
+static __device__ __noinline__ void dsdgp_normal2(unsigned long long seed, int layer, int s, int n_global, int d_even,
+                                                  float& z0, float& z1) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)n_global, (uint32_t)s, (uint32_t)layer, (uint32_t)(d_even >> 2),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    int p = (d_even & 2);
+    float u1 = ((float)r[p] + 0.5f) * 2.3283064365386963e-10f;
+    float u2 = ((float)r[p + 1] + 0.5f) * 2.3283064365386963e-10f;
+    float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+// 2^x, single MUFU (ex2.approx): relative error 2^-22.5
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // kernel value and d k / d r2   (r2 already scaled by lengthscales)
 __device__ __forceinline__ void kern_eval_f(int kern, float r2, float var, float& k, float& kp) {
     if (kern == DSDGP_KERN_RBF) {

@@ -15,7 +15,7 @@
 #define TC_NSTAGE 3          // weight ring slots (barriers): slots 0,1 in the ring area, slot 2 = the A_lo operand buffer
                              // once the 3xTF32 projections are done (G2 streams 1.5x more bytes in flight)
 #define TC_CHUNK_BYTES 16384 // one [128 rows] x [32 k] activation k-block
-#define TC_THREADS 320
+#define TC_THREADS 576
 
 // ----------------------------------------------------------------------------------------------
 // weight packing (layout: tc_pack.cuh).  One thread per stored element; hi = tf32(x), lo = tf32(x - hi).
@@ -63,10 +63,20 @@ void launch_pack_fwd(const LayerSet& ls, int part, cudaStream_t st, long long* n
 }
 
 // ----------------------------------------------------------------------------------------------
-// forward kernel.  288 threads: warps 0-7 = row warps (two threads per row: thread t and t+128 share TMEM lane t&127
-// and split the accumulator columns / the inducing points between them), warp 8 = control (TMA + MMA issue).
+// forward kernel.  576 threads: warps 0-15 = row warps (FOUR threads per row: threads t, t+128, t+256, t+384 share TMEM
+// lane t&127; a warp may only touch the TMEM lane quadrant warp%4, which is the quadrant of its rows), warp 16 = TMA
+// producer, warp 17 = MMA issue.  A tile is a serial chain of short SIMT phases between MMAs, so the phases are latency
+// bound: 16 row warps (4 per scheduler) instead of 8 roughly halve every phase (profiles/r2_*).  Work split of a row's
+// four threads ("quarters" q = 0..3):
+//   Gram, E1 (b), E1' (u)   : columns / inducing points split four ways
+//   E2 (|c_d|^2)            : quarter pair p = q>>1 owns the outputs d = p, p+2, ... (= TMEM accumulator buffer p), the
+//                             two quarters of a pair split the columns in halves -> two partial sums per (row, d)
+//   mean, draw, stores      : quarter q owns outputs d = 2q, 2q+1 (+8k): complete dot products, no partial sums, and one
+//                             Philox block + one Box-Muller pair yields both draws
 // ----------------------------------------------------------------------------------------------
-#define TC_ROWTHREADS 256
+#define TC_ROWTHREADS 512
+#define TC_WARP_TMA 16
+#define TC_WARP_MMA 17
 // One 128-row tile of one layer.  `tile` = row-tile index; tmem = base of this CTA's 512 TMEM columns; reinit = the
 // mbarriers were used by a previous tile of this CTA (persistent chain kernel) and must be invalidated first.
 template <int DINP, int DOUTP>
@@ -83,12 +93,11 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
     const uint32_t bar_acc = bar_a + 24;                      // acc_full[2]
     const uint32_t bar_acc2f = bar_acc + 16;                  // acc2_full[2]
     const uint32_t bar_acc2e = bar_acc2f + 16;                // acc2_empty[2]
-    float* part_s = reinterpret_cast<float*>(sgen + (misc + 256 - sbase));        // [2][128] |b|^2 partials
-    float* Zs = part_s + 256;                                                       // [M][Din]
+    float* part_s = reinterpret_cast<float*>(sgen + (misc + 256 - sbase));        // [4][128] |b|^2 partials
+    float* Zs = part_s + 512;                                                       // [M][Din], pre-scaled by 1/lengthscale
     float* qmu_s = Zs + ((P.M * P.Din + 3) & ~3);                                   // [M][D], 16-byte aligned
-    // scratch aliased on A_lo once it is dead (G2 reads A_hi only): mean partials [2][128][D], |c_d|^2 partials [2][D][128]
-    float* mean_p = reinterpret_cast<float*>(sgen + (A_lo - sbase) + (three ? 40960 : 0));
-    float* csq_p = mean_p + 2 * 128 * P.Dout;
+    // scratch aliased on A_lo once it is dead (G2 reads A_hi only): |c_d|^2 partials [2][D][128]
+    float* csq_p = reinterpret_cast<float*>(sgen + (A_lo - sbase) + (three ? 40960 : 0));
 
     const int M = P.M, Din = P.Din, D = P.Dout;
     const int nkb = (M + 31) / 32, NPAD = (M + 15) & ~15;
@@ -100,17 +109,17 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
             for (int i = 0; i < 2 * TC_NSTAGE + 9; ++i) mbar_inval(misc + 8 * i);
         for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int i = 0; i < 3; ++i) mbar_init(bar_a + 8 * i, TC_ROWTHREADS);
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc + 8 * i, 1); mbar_init(bar_acc2f + 8 * i, 1); mbar_init(bar_acc2e + 8 * i, TC_ROWTHREADS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc + 8 * i, 1); mbar_init(bar_acc2f + 8 * i, 1); mbar_init(bar_acc2e + 8 * i, TC_ROWTHREADS / 2); }
         fence_mbar_init();
     }
-    for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) Zs[e] = P.Z[e];
+    for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) Zs[e] = P.Z[e] * (1.0f / P.ls[P.ard ? e % Din : 0]);
     for (int e = threadIdx.x; e < M * D; e += TC_THREADS) qmu_s[e] = P.q_mu[e];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
 
-    if (warp == 8) {
+    if (warp == TC_WARP_TMA) {
         // ===================== TMA producer (one lane): streams the packed weight chunks through the ring ==========
         if (lane == 0) {
             const char* wsrc = reinterpret_cast<const char*>(P.wpack_fwd);
@@ -130,7 +139,7 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
                 load(tcp::blk_g2(d), tcp::PAT_GE, sl);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer: whole warp runs the uniform control flow, one elected lane issues ==========
         {
             int cnt[3] = {0, 0, 0};
@@ -183,7 +192,7 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
                 do_block(128u, tcp::PAT_GE, 1, 1);
                 commit(bar_acc + 8);
             }
-            // G2: c_d = L_d^T u   (1xTF32), accumulators double-buffered
+            // G2: c_d = L_d^T u   (1xTF32), accumulators double-buffered (buffer d&1 is consumed by quarter pair d&1)
             mbar_wait(bar_a + 16, 0);
             tc_fence_after();
             for (int d = 0; d < D; ++d) {
@@ -194,7 +203,8 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
         }
     } else {
         // ===================== row warps =====================
-        const int t = threadIdx.x & 127, half = threadIdx.x >> 7, row = row0 + t;
+        const int t = threadIdx.x & 127, qt = threadIdx.x >> 7, row = row0 + t;       // qt: quarter 0..3
+        const int pair = qt >> 1, half = qt & 1;
         const bool dbg = a.dbg && tile == 0 && threadIdx.x == 0;
         int dbi = 0;
 #define STAMP() do { if (dbg) a.dbg[dbi++] = clock64(); } while (0)
@@ -216,57 +226,70 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
                 a_store4(A_lo, k4, lo);
             }
         };
-        // column range of this half: [c_lo, c_hi), multiples of 8
+        // column ranges (multiples of 8): this quarter's [c_lo, c_hi) of the NPAD accumulator columns, and this thread's
+        // half [h_lo, h_hi) inside its pair (E2)
+        const int nch8 = NPAD >> 3;
+        const int cq = nch8 >> 2, cr = nch8 & 3;
+        const int c_lo = 8 * (qt * cq + min(qt, cr)), c_hi = c_lo + 8 * (cq + (qt < cr ? 1 : 0));
         const int NH = ((NPAD >> 1) + 7) & ~7;
-        const int c_lo = half ? NH : 0, c_hi = half ? NPAD : NH;
+        const int h_lo = half ? NH : 0, h_hi = half ? NPAD : NH;
 
-        // ---- Gram: k_i = k(z_i, x) -> A_hi / A_lo (tf32 split); the halves take alternate groups of 4
-        float x[DINP], il[DINP];
+        // ---- Gram: k_i = k(z_i, x) -> A_hi / A_lo (tf32 split); the quarters take alternate groups of 4 inducing points.
+        // Inputs and inducing points are pre-scaled by 1/lengthscale (Zs above).
+        float xs[DINP];
 #pragma unroll
-        for (int q = 0; q < DINP; ++q) {
-            x[q] = (valid && q < Din) ? __ldcg(&a.Xin[(size_t)row * Din + q]) : 0.f;
-            il[q] = q < Din ? 1.0f / P.ls[P.ard ? q : 0] : 0.f;
-        }
+        for (int q = 0; q < DINP; ++q)
+            xs[q] = (valid && q < Din) ? __ldcg(&a.Xin[(size_t)row * Din + q]) * (1.0f / P.ls[P.ard ? q : 0]) : 0.f;
         const float var0 = P.var[0];
-        for (int i4 = 4 * half; i4 < nkb * 32; i4 += 8) {
-            float r2[4];
-            if (Din == DINP) {
-                // vector loads of the inducing inputs (row i = DINP consecutive floats, 16-byte aligned)
+        const bool rbf = P.kern == DSDGP_KERN_RBF;
+        const float l2var = log2f(var0);
+        for (int i4 = 4 * qt; i4 < nkb * 32; i4 += 16) {
+            float kv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (i4 < M) {
+                float r2[4];
+                if (Din == DINP) {
+                    // vector loads of the inducing inputs (row i = DINP consecutive floats, 16-byte aligned)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = min(i4 + u, M - 1);
-                    const float4* zr = reinterpret_cast<const float4*>(Zs + i * DINP);
-                    float s = 0.f;
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = min(i4 + u, M - 1);
+                        const float4* zr = reinterpret_cast<const float4*>(Zs + i * DINP);
+                        float s = 0.f;
 #pragma unroll
-                    for (int q4 = 0; q4 < DINP / 4; ++q4) {
-                        const float4 zv = zr[q4];
-                        float d0 = (x[4 * q4] - zv.x) * il[4 * q4], d1 = (x[4 * q4 + 1] - zv.y) * il[4 * q4 + 1];
-                        float d2 = (x[4 * q4 + 2] - zv.z) * il[4 * q4 + 2], d3 = (x[4 * q4 + 3] - zv.w) * il[4 * q4 + 3];
-                        s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d2, d2, s); s = fmaf(d3, d3, s);
-                    }
-                    r2[u] = s;
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = min(i4 + u, M - 1);
-                    float s = 0.f;
-#pragma unroll
-                    for (int q = 0; q < DINP; ++q) {
-                        if (q < Din) {
-                            float dd = (x[q] - Zs[i * Din + q]) * il[q];
-                            s = fmaf(dd, dd, s);
+                        for (int q4 = 0; q4 < DINP / 4; ++q4) {
+                            const float4 zv = zr[q4];
+                            const float d0 = xs[4 * q4] - zv.x, d1 = xs[4 * q4 + 1] - zv.y;
+                            const float d2 = xs[4 * q4 + 2] - zv.z, d3 = xs[4 * q4 + 3] - zv.w;
+                            s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d2, d2, s); s = fmaf(d3, d3, s);
                         }
+                        r2[u] = s;
                     }
-                    r2[u] = s;
-                }
-            }
-            float kv[4];
+                } else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float k, kp;
-                kern_eval_fast(P.kern, r2[u], var0, k, kp);
-                kv[u] = (i4 + u < M) ? k : 0.f;
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = min(i4 + u, M - 1);
+                        float s = 0.f;
+#pragma unroll
+                        for (int q = 0; q < DINP; ++q) {
+                            if (q < Din) {
+                                const float dd = xs[q] - Zs[i * Din + q];
+                                s = fmaf(dd, dd, s);
+                            }
+                        }
+                        r2[u] = s;
+                    }
+                }
+                if (rbf) {
+                    // var * exp(-r2/2) = 2^(log2(var) - r2 * log2(e)/2): one FMA + ex2.approx per point
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) kv[u] = (i4 + u < M) ? fast_ex2(fmaf(r2[u], -0.72134752044448170368f, l2var)) : 0.f;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float k, kp;
+                        kern_eval_fast(P.kern, r2[u], var0, k, kp);
+                        kv[u] = (i4 + u < M) ? k : 0.f;
+                    }
+                }
             }
             split_store(i4, kv, true);
         }
@@ -274,12 +297,9 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
         mbar_arrive(bar_a);
         STAMP();      // 1: Gram done
 
-        // ---- E1 (b) and E1' (u): this half's columns
+        // ---- E1 (b) and E1' (u): this quarter's columns
         float bn = 0.f;
-        float meanv[DOUTP];
-#pragma unroll
-        for (int d = 0; d < DOUTP; ++d) meanv[d] = 0.f;
-        auto consume = [&](uint32_t dcol, bool acc_bn, bool is_u, bool write_lo) {
+        auto consume = [&](uint32_t dcol, bool acc_bn, bool write_lo) {
             for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
                 float v[8];
                 __syncwarp();
@@ -296,12 +316,12 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
         tc_fence_after();
         STAMP();      // 2: G1 accumulators ready
         if (P.white) {
-            consume(0u, true, false, false);
+            consume(0u, true, false);
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_a + 16);
         } else {
-            consume(0u, true, false, true);
+            consume(0u, true, true);
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_a + 8);
@@ -309,115 +329,118 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
             mbar_wait(bar_acc + 8, 0);
             tc_fence_after();
             STAMP();  // 4: G1' ready
-            consume(128u, false, false, false);       // critical path: u -> A_hi only
+            consume(128u, false, false);       // critical path: u -> A_hi only
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_a + 16);
         }
         STAMP();      // 5: operands for G2 published
-        // off the critical path (interleaved with the G2 epilogues): mean = u . q_mu and the U store, re-reading u from TMEM
+        part_s[qt * 128 + t] = bn;
+        // off the critical path (interleaved with the G2 epilogues), re-reading u from TMEM: mean_d = u . q_mu[:, d] for the
+        // outputs this quarter owns (d = 2 qt + (j & 1) + 8 (j >> 1)), and the U store of this quarter's columns
+        constexpr int MD = DOUTP <= 8 ? 2 : DOUTP / 4;
+        float meanv[MD];
+#pragma unroll
+        for (int j = 0; j < MD; ++j) meanv[j] = 0.f;
         const uint32_t ucol = P.white ? 0u : 128u;
         auto deferred = [&](int c0) {
-            {
-                float v[8];
-                __syncwarp();
-                tmem_ld8(lane_addr + ucol + c0, v);
+            float v[8];
+            __syncwarp();
+            tmem_ld8(lane_addr + ucol + c0, v);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int i = c0 + u;
-                    if (i < M) {
-                        bool done = false;
-                        if constexpr (DOUTP % 4 == 0) {
-                            if (D == DOUTP) {
-                                const float4* qr = reinterpret_cast<const float4*>(qmu_s + i * DOUTP);
-#pragma unroll
-                                for (int d4 = 0; d4 < DOUTP / 4; ++d4) {
-                                    float4 qv = qr[d4];
-                                    meanv[4 * d4] = fmaf(v[u], qv.x, meanv[4 * d4]);
-                                    meanv[4 * d4 + 1] = fmaf(v[u], qv.y, meanv[4 * d4 + 1]);
-                                    meanv[4 * d4 + 2] = fmaf(v[u], qv.z, meanv[4 * d4 + 2]);
-                                    meanv[4 * d4 + 3] = fmaf(v[u], qv.w, meanv[4 * d4 + 3]);
-                                }
-                                done = true;
-                            }
-                        }
-                        if (!done) {
-#pragma unroll
-                            for (int d = 0; d < DOUTP; ++d)
-                                if (d < D) meanv[d] = fmaf(v[u], qmu_s[i * D + d], meanv[d]);
-                        }
-                    }
-                }
-                if (valid) {
-                    if (c0 + 8 <= M && (M & 3) == 0) {
-                        float4* dst = reinterpret_cast<float4*>(a.U + (size_t)row * M + c0);
-                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            for (int u = 0; u < 8; ++u) {
+                const int i = c0 + u;
+                if (i < M) {
+                    if (DOUTP == 8 && D == 8) {
+                        const float2 qv = *reinterpret_cast<const float2*>(qmu_s + i * 8 + 2 * qt);
+                        meanv[0] = fmaf(v[u], qv.x, meanv[0]);
+                        meanv[1] = fmaf(v[u], qv.y, meanv[1]);
                     } else {
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) if (c0 + u < M) a.U[(size_t)row * M + c0 + u] = v[u];
+                        for (int j = 0; j < MD; ++j) {
+                            const int d = 2 * qt + (j & 1) + 8 * (j >> 1);
+                            if (d < D) meanv[j] = fmaf(v[u], qmu_s[i * D + d], meanv[j]);
+                        }
                     }
                 }
             }
+            if (valid && c0 >= c_lo && c0 < c_hi) {
+                if (c0 + 8 <= M && (M & 3) == 0) {
+                    float4* dst = reinterpret_cast<float4*>(a.U + (size_t)row * M + c0);
+                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (c0 + u < M) a.U[(size_t)row * M + c0 + u] = v[u];
+                }
+            }
         };
-        part_s[half * 128 + t] = bn;
 
-        // ---- E2: |c_d|^2 partials of this half's columns
-        const int ndef = (c_hi - c_lo) >> 3;
-        for (int d = 0; d < D; ++d) {
-            const int b = d & 1;
-            for (int j = d; j < ndef; j += D) deferred(c_lo + 8 * j);
-            mbar_wait(bar_acc2f + 8 * b, (d >> 1) & 1);
+        // ---- E2: |c_d|^2 partials: pair `pair` consumes accumulator buffer `pair` (d = pair, pair+2, ...), this thread sums
+        // its half of the columns
+        const int nmine = (D - pair + 1) >> 1;            // outputs this pair consumes
+        int kdef = 0;
+        for (int d = pair; d < D; d += 2, ++kdef) {
+            for (int j = kdef; j < nch8; j += nmine) deferred(8 * j);
+            mbar_wait(bar_acc2f + 8 * pair, (d >> 1) & 1);
             tc_fence_after();
-            STAMP();  // 6+2d: G2[d] ready
+            STAMP();  // G2[d] ready
             float s = 0.f;
-            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+            for (int c0 = h_lo; c0 < h_hi; c0 += 8) {
                 float v[8];
                 __syncwarp();
-                tmem_ld8(lane_addr + 256 + 128 * b + c0, v);
+                tmem_ld8(lane_addr + 256 + 128 * pair + c0, v);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) s = fmaf(v[u], v[u], s);
             }
             tc_fence_before();
-            mbar_arrive(bar_acc2e + 8 * b);
+            mbar_arrive(bar_acc2e + 8 * pair);
             csq_p[(half * D + d) * 128 + t] = s;
-            STAMP();  // 7+2d: E2[d] done
+            STAMP();  // E2[d] done
         }
-#pragma unroll
-        for (int d = 0; d < DOUTP; ++d)
-            if (d < D) mean_p[(half * 128 + t) * D + d] = meanv[d];      // A_lo is dead (G1/G1' completed long ago)
+        if (nmine == 0)
+            for (int j = 0; j < nch8; ++j) deferred(8 * j);
         named_bar_sync(1, TC_ROWTHREADS);
         STAMP();
-        // ---- finalise: half h handles outputs d = h, h+2, ...
+        // ---- finalise: quarter qt handles outputs d0 = 2 qt + 8 k and d0 + 1
         const float jit = a.jitter;
         const unsigned long long seed = a.sa->seed;
         const int noff = a.sa->n_offset, soff = a.sa->s_offset;
-        const float bnt = part_s[t] + part_s[128 + t];
+        const float bnt = (part_s[t] + part_s[128 + t]) + (part_s[256 + t] + part_s[384 + t]);
         if (valid) {
-            for (int d = half; d < D; d += 2) {
-                float mean = mean_p[t * D + d] + mean_p[(128 + t) * D + d];
-                if (P.mean == DSDGP_MEAN_IDENTITY) mean += x[d < DINP ? d : 0];
-                else if (P.mean == DSDGP_MEAN_LINEAR) {
-                    float ms = P.meanB[d];
-                    for (int q = 0; q < Din; ++q) ms = fmaf(__ldcg(&a.Xin[(size_t)row * Din + q]), __ldg(&P.meanW[q * D + d]), ms);
-                    mean += ms;
+#pragma unroll
+            for (int jp = 0; jp < MD; jp += 2) {
+                const int d0 = 2 * qt + 8 * (jp >> 1);
+                if (d0 >= D) break;
+                const int nd = (d0 + 1 < D) ? 2 : 1;
+                float mean2[2] = {meanv[jp], meanv[jp + 1]}, sd2[2] = {0.f, 0.f};
+                for (int e = 0; e < nd; ++e) {
+                    const int d = d0 + e;
+                    float mean = mean2[e];
+                    if (P.mean == DSDGP_MEAN_IDENTITY) mean += __ldcg(&a.Xin[(size_t)row * Din + d]);
+                    else if (P.mean == DSDGP_MEAN_LINEAR) {
+                        float ms = P.meanB[d];
+                        for (int q = 0; q < Din; ++q) ms = fmaf(__ldcg(&a.Xin[(size_t)row * Din + q]), __ldg(&P.meanW[q * D + d]), ms);
+                        mean += ms;
+                    }
+                    const float v = var0 - bnt + csq_p[d * 128 + t] + csq_p[(D + d) * 128 + t];
+                    a.Fmean[(size_t)row * D + d] = mean;
+                    a.Fvar[(size_t)row * D + d] = v;
+                    mean2[e] = mean;
+                    sd2[e] = sqrtf(fmaxf(v + jit, 1e-30f));
                 }
-                float v = var0 - bnt + csq_p[d * 128 + t] + csq_p[(D + d) * 128 + t];
-                a.Fmean[(size_t)row * D + d] = mean;
-                a.Fvar[(size_t)row * D + d] = v;
                 if (a.F) {
-                    float sd = sqrtf(fmaxf(v + jit, 1e-30f));
-                    if (a.S_rep == 1) {
-                        int ss = row / a.N, n = row % a.N;
-                        float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, ss + soff, n + noff, d);
-                        if (a.z_out) a.z_out[(size_t)row * D + d] = z;
-                        a.F[(size_t)row * D + d] = fmaf(z, sd, mean);
-                    } else {
-                        for (int ss = 0; ss < a.S_rep; ++ss) {
-                            size_t o = ((size_t)ss * a.N + row) * D + d;
-                            float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, ss + soff, row + noff, d);
-                            if (a.z_out) a.z_out[o] = z;
-                            a.F[o] = fmaf(z, sd, mean);
+                    const int nrep = a.S_rep;
+                    for (int ss = 0; ss < nrep; ++ss) {
+                        // row r = s N + n (S_rep == 1), or layer-1 dedup: row = n, one draw per sample ss
+                        const int sidx = nrep == 1 ? row / a.N : ss, n = nrep == 1 ? row % a.N : row;
+                        const size_t o = (nrep == 1 ? (size_t)row : (size_t)ss * a.N + row) * D + d0;
+                        float z2[2];
+                        if (a.z) { z2[0] = a.z[o]; z2[1] = nd == 2 ? a.z[o + 1] : 0.f; }
+                        else dsdgp_normal2(seed, P.idx, sidx + soff, n + noff, d0, z2[0], z2[1]);
+                        for (int e = 0; e < nd; ++e) {
+                            if (a.z_out) a.z_out[o + e] = z2[e];
+                            a.F[o + e] = fmaf(z2[e], sd2[e], mean2[e]);
                         }
                     }
                 }
@@ -438,13 +461,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_fwd_tc(LayerDev P, FwdA
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     __shared__ uint32_t tmem_slot_s;
     const int warp = threadIdx.x >> 5;
-    if (warp == 8) tmem_alloc(smem_u32(&tmem_slot_s), 512);
+    if (warp == TC_WARP_TMA) tmem_alloc(smem_u32(&tmem_slot_s), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot_s;
     fwd_tile_body<DINP, DOUTP>(P, a, blockIdx.x, sbase, sgen, tmem, false);
-    if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == TC_WARP_TMA) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ---- all layers in ONE persistent kernel.  Tasks (layer l, tile t) are numbered layer-major; CTA c runs tasks
@@ -461,7 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_chain_fwd_tc(const __grid_con
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     __shared__ uint32_t tmem_slot_s;
     const int warp = threadIdx.x >> 5;
-    if (warp == 8) tmem_alloc(smem_u32(&tmem_slot_s), 512);
+    if (warp == TC_WARP_TMA) tmem_alloc(smem_u32(&tmem_slot_s), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -490,10 +513,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_chain_fwd_tc(const __grid_con
             st_release_gpu(fc.flags + (size_t)l * fc.max_tiles + t, epoch);
         }
     }
-    if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == TC_WARP_TMA) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-static size_t tc_fwd_smem(int M, int Din, int D) { return 1024 + 131072 + 2 * (size_t)tcp::slot_bytes(M) + 256 + 1024 + sizeof(float) * ((size_t)M * Din + (size_t)M * D + 8); }
+static size_t tc_fwd_smem(int M, int Din, int D) { return 1024 + 131072 + 2 * (size_t)tcp::slot_bytes(M) + 256 + 2048 + sizeof(float) * ((size_t)M * Din + (size_t)M * D + 8); }
 
 bool tc_fwd_supported(const LayerDev& P) {
     return P.M <= 128 && P.M >= 8 && P.Din <= 16 && P.Dout <= 32 && P.wpack_fwd != nullptr &&

@@ -1,6 +1,7 @@
 // tcgen05 tensor-core path of one SVGP layer: backward over rows (data gradient + per-row quantities the row-reduction
-// GEMMs need).  Same tiling as the forward (128 rows on the UMMA M dimension, two threads per row, one TMA producer
-// warp, one MMA-issuing warp).  Per tile:
+// GEMMs need).  Same tiling as the forward (128 rows on the UMMA M dimension, FOUR threads per row = 16 row warps, one TMA
+// producer warp, one MMA-issuing warp): the tile is a chain of latency-bound SIMT phases, which 4 warps per scheduler hide
+// far better than 2 (profiles/r2_*).  Per tile:
 //   G2[d]: c_d = L_d^T u              1xTF32   (recomputed, as the SIMT path does)
 //   G5[d]: ubar += L_d (2 vbar_d c_d) 1xTF32   accumulated over d in TMEM
 //   G6   : t = Linv ubar              3xTF32   (non-white)      } w = K^-1 ubar needs the accuracy: the solve
@@ -14,8 +15,10 @@
 #define TC_ROWS 128
 #define TC_NSTAGE 2
 #define TC_CHUNK_BYTES 16384
-#define TC_THREADS 320
-#define TC_ROWTHREADS 256
+#define TC_THREADS 576
+#define TC_ROWTHREADS 512
+#define TC_WARP_TMA 16
+#define TC_WARP_MMA 17
 
 namespace {
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         mbar_init(bar_s6, TC_ROWTHREADS); mbar_init(bar_acc6, 1); mbar_init(bar_s7, TC_ROWTHREADS); mbar_init(bar_acc7, 1);
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (warp == TC_WARP_TMA) tmem_alloc(tmem_slot, 512);
     for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) Zs[e] = P.Z[e];
     for (int e = threadIdx.x; e < M * D; e += TC_THREADS) qmu_s[e] = P.q_mu[e];
     tc_fence_before();
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_gen;
 
-    if (warp == 8) {
+    if (warp == TC_WARP_TMA) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             const char* wsrc = reinterpret_cast<const char*>(P.wpack_fwd);
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             if (!WHITE) { load(tcp::blk_g1(0), tcp::PAT_LE); load(tcp::blk_g1(1), tcp::PAT_LE); }
             load(tcp::blk_g1p(0), tcp::PAT_GE); load(tcp::blk_g1p(1), tcp::PAT_GE);
         }
-    } else if (warp == 9) {
+    } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues ========
         int s = 0;
         uint32_t ph = 0;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         commit(bar_acc7);
     } else {
         // ===================== row warps =====================
-        const int t = threadIdx.x & 127, half = threadIdx.x >> 7, row = row0 + t;
+        const int t = threadIdx.x & 127, qt = threadIdx.x >> 7, row = row0 + t;      // qt: quarter 0..3 of the row's threads
         const bool valid = row < R;
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t rsw = (uint32_t)(t & 7);
@@ -193,12 +196,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         auto store_hi_lo = [&](uint32_t bhi, uint32_t blo, int k4, const float* v) {
             float4 hi, lo;
             hi.x = tf32_rna(v[0]); hi.y = tf32_rna(v[1]); hi.z = tf32_rna(v[2]); hi.w = tf32_rna(v[3]);
-            lo.x = tf32_rna(v[0] - hi.x); lo.y = tf32_rna(v[1] - hi.y); lo.z = tf32_rna(v[2] - hi.z); lo.w = tf32_rna(v[3] - hi.w);
+            lo.x = tf32_lo_trunc(v[0], hi.x); lo.y = tf32_lo_trunc(v[1], hi.y); lo.z = tf32_lo_trunc(v[2], hi.z); lo.w = tf32_lo_trunc(v[3], hi.w);
             a_store4(bhi, k4, hi);
             a_store4(blo, k4, lo);
         };
-        const int NH = ((NPAD >> 1) + 7) & ~7;
-        const int c_lo = half ? NH : 0, c_hi = half ? NPAD : NH;
+        // this quarter's accumulator columns [c_lo, c_hi), multiples of 8
+        const int nch8 = NPAD >> 3, cq = nch8 >> 2, cr = nch8 & 3;
+        const int c_lo = 8 * (qt * cq + min(qt, cr)), c_hi = c_lo + 8 * (cq + (qt < cr ? 1 : 0));
         const float jit = a.jitter;
         const unsigned long long seed = a.sa->seed;
         const int noff = a.sa->n_offset, soff = a.sa->s_offset;
@@ -208,16 +212,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
 #define BSTAMP() do { if (dbg) a.dbg[dbi++] = clock64(); } while (0)
         BSTAMP();   // 0
 
-        // ---- R0: x tile, mubar / vbar (this half: d = half, half+2, ...)
+        // ---- R0: x tile, mubar / vbar (this quarter: d = qt, qt+4, ...)
         float x[DINP], il[DINP];
 #pragma unroll
         for (int q = 0; q < DINP; ++q) {
             x[q] = (valid && q < Din) ? a.Xin[(size_t)row * Din + q] : 0.f;
             il[q] = q < Din ? 1.0f / P.ls[P.ard ? q : 0] : 0.f;
-            if (half == 0 && q < Din) xs_s[t * Din + q] = x[q];
+            if (qt == 0 && q < Din) xs_s[t * Din + q] = x[q];
         }
 #pragma unroll 1
-        for (int d = half; d < D; d += 2) {
+        for (int d = qt; d < D; d += 4) {
             float m = 0.f, v = 0.f;
             if (valid) {
                 if (a.fbar) {
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             mv_s[t * 2 * D + d] = m;
             mv_s[t * 2 * D + D + d] = v;
         }
-        // ---- R1: u (this half's columns) -> A_u as the G2 operand; loads are issued four chunks ahead of their use
+        // ---- R1: u (this quarter's columns) -> A_u as the G2 operand; loads are issued four chunks ahead of their use
         constexpr bool vec4 = true;               // M % 4 == 0 (tc_bwd_supported)
         auto load_u4 = [&](int c0) -> float4 {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                 q0 = n0; q1 = n1; q2 = n2; q3 = n3;
             }
         }
-        if (half) {          // zero the K padding beyond NPAD (columns NPAD .. 32 nkb) once
+        if (qt == 3) {       // zero the K padding beyond NPAD (columns NPAD .. 32 nkb) once
             const float z4[4] = {0.f, 0.f, 0.f, 0.f};
             for (int c0 = NPAD; c0 < nkb * 32; c0 += 4) { store_hi(A_u, c0, z4); store_hi(A_c, c0, z4); }
         }
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             vb[d] = d < D ? mv_s[t * 2 * D + D + d] : 0.f;
             vs += vb[d];
         }
-        // ---- R2 (deferred, interleaved below): r2_i for this half's inducing points -> TMEM scratch columns 384+
+        // ---- R2 (deferred, interleaved below): r2_i for this quarter's inducing points -> TMEM scratch columns 384+
         auto gram_chunk = [&](int c0) {
             float r2[8];
             {
@@ -448,7 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             }
         }
         BSTAMP();   // 32: R6 done
-        if (half == 0)
+        if (qt == 0)
 #pragma unroll
             for (int d = 0; d < DOUTP; ++d) s2 += vb[d];
         s2 = warp_sum(s2);
@@ -457,35 +461,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         named_bar_sync(1, TC_ROWTHREADS);
         if (threadIdx.x == 0) {
             float tot = 0.f;
-            for (int w8 = 0; w8 < 8; ++w8) tot += red_s[w8];
+            for (int w8 = 0; w8 < TC_ROWTHREADS / 32; ++w8) tot += red_s[w8];
             atomicAdd(P.gvar, tot);
         }
-        // ---- R7a: xbar (this half: q = half, half+2, ...)
+        // ---- R7a: xbar (this quarter: q = qt, qt+4, ...)
         if (a.xbar && valid) {
-            float accq[DINP];
+            constexpr int NQ = (DINP + 3) / 4;          // input dimensions per thread: q = qt + 4 j
+            float accq[NQ], xq[NQ], ilq[NQ];
 #pragma unroll
-            for (int q = 0; q < DINP; ++q) accq[q] = 0.f;
+            for (int j = 0; j < NQ; ++j) { accq[j] = 0.f; xq[j] = 0.f; ilq[j] = 0.f; }
+#pragma unroll
+            for (int q = 0; q < DINP; ++q)
+                if ((q & 3) == qt) { xq[q >> 2] = x[q]; ilq[q >> 2] = il[q]; }
             {
 #pragma unroll 4
                 for (int i = 0; i < M; ++i) {
                     const float g = g_s[t * MP + i];
-                    const float4* zr = reinterpret_cast<const float4*>(Zs + i * DINP);
 #pragma unroll
-                    for (int q4 = 0; q4 < DINP / 4; ++q4) {
-                        const float4 zv = zr[q4];
-                        const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int q = 4 * q4 + e;
-                            if ((q & 1) == half) accq[q] = fmaf(g, x[q] - zz[e], accq[q]);
-                        }
+                    for (int j = 0; j < NQ; ++j) {
+                        const int q = qt + 4 * j;
+                        const float z = q < DINP ? Zs[i * DINP + q] : 0.f;
+                        accq[j] = fmaf(g, xq[j] - z, accq[j]);
                     }
                 }
             }
 #pragma unroll
-            for (int q = 0; q < DINP; ++q) {
-                if (q < Din && (q & 1) == half) {
-                    float s = accq[q] * il[q] * il[q];
+            for (int j = 0; j < NQ; ++j) {
+                const int q = qt + 4 * j;
+                if (q < Din) {
+                    float s = accq[j] * ilq[j] * ilq[j];
                     if (P.mean == DSDGP_MEAN_IDENTITY) {
 #pragma unroll
                         for (int d = 0; d < DOUTP; ++d) if (d == q) s += mub[d];
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         BSTAMP();   // 33: R7a done
         // ---- R7b: Z / lengthscale partials: one (i, q) pair per thread at a time, walking the 128 rows
         {
-            const int i = threadIdx.x & 127, rh = threadIdx.x >> 7;      // inducing point, row half
+            const int i = threadIdx.x & 127, rh = threadIdx.x >> 7;      // inducing point, row quarter
             float sa[DINP], sb[DINP];
             if (i < M) {
                 float zi[DINP];
@@ -508,7 +512,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                 for (int q = 0; q < DINP; ++q) { sa[q] = 0.f; sb[q] = 0.f; zi[q] = q < Din ? Zs[i * Din + q] : 0.f; }
                 {
 #pragma unroll 4
-                    for (int r = rh * 64; r < rh * 64 + 64; ++r) {
+                    for (int r = rh * 32; r < rh * 32 + 32; ++r) {
                         const float g = g_s[r * MP + i];
                         const float4* xr = reinterpret_cast<const float4*>(xs_s + r * DINP);
 #pragma unroll
@@ -555,7 +559,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == TC_WARP_TMA) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // (DINP, DOUTP, KERN, WHITE) instances

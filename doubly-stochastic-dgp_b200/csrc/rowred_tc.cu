@@ -13,8 +13,9 @@
 #include "dsdgp_internal.cuh"
 #include "tc_common.cuh"
 
-#define RR_THREADS 288          // 8 row warps + 1 MMA warp
-#define RR_ROWTHREADS 256
+#define RR_THREADS 544          // 16 row warps (four threads per row) + 1 MMA warp
+#define RR_ROWTHREADS 512
+#define RR_WARP_MMA 16
 #define RR_TILE_BYTES 65536     // [4 blocks][128 rows][32 tf32]
 
 namespace {
@@ -74,18 +75,18 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
         mbar_init(bar_done, 1);
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (warp == RR_WARP_MMA) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_gen;
     if (my_tiles == 0) {       // nothing to do (more CTAs than row tiles)
         __syncthreads();
-        if (warp == 8) { __syncwarp(); tmem_dealloc(tmem, 512); }
+        if (warp == RR_WARP_MMA) { __syncwarp(); tmem_dealloc(tmem, 512); }
         return;
     }
 
-    if (warp == 8) {
+    if (warp == RR_WARP_MMA) {
         // ===================== MMA issuer =====================
         const uint32_t id_full = make_idesc_tf32(128, NPAD, 1, 1), id_q = make_idesc_tf32(128, 16, 1, 1);
         int bcount = 0;          // B operands consumed so far (buffer = bcount & 1, phase = (bcount >> 1) & 1)
@@ -115,8 +116,8 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
         if (elect_one_rr()) mma_commit(bar_done);
         __syncwarp();
     } else {
-        // ===================== row warps: two threads per row =====================
-        const int t = threadIdx.x & 127, half = threadIdx.x >> 7;
+        // ===================== row warps: four threads per row =====================
+        const int t = threadIdx.x & 127, qt = threadIdx.x >> 7;
         const uint32_t rsw = (uint32_t)(t & 3);                        // k-row inside the 4-row swizzle atom
         const uint32_t rowoff = (uint32_t)(t * 128);                   // rows are 128 B apart; atoms (4 rows) 512 B
         auto store4 = [&](uint32_t base, int k4, float4 v) {           // k4: feature index, multiple of 4
@@ -124,8 +125,12 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
             uint32_t off = (uint32_t)(k4 >> 5) * 16384u + rowoff + ((gran ^ rsw) << 5) + (uint32_t)((k4 & 7) << 2);
             *reinterpret_cast<float4*>(sgen + (base - sbase) + off) = v;
         };
-        const int NH = ((NPAD >> 1) + 7) & ~7;
-        const int c_lo = half ? NH : 0, c_hi = half ? NPAD : NH;      // this thread's feature range (<= 64 wide)
+        // this thread's feature range [c_lo, c_hi): a quarter of the NPAD features in units of 4 (<= 32 wide); the flush
+        // reads TMEM in units of 8 columns: [f_lo, f_hi)
+        const int n4 = NPAD >> 2, q4 = n4 >> 2, r4 = n4 & 3;
+        const int c_lo = 4 * (qt * q4 + min(qt, r4)), c_hi = c_lo + 4 * (q4 + (qt < r4 ? 1 : 0));
+        const int n8 = NPAD >> 3, q8 = n8 >> 2, r8 = n8 & 3;
+        const int f_lo = 8 * (qt * q8 + min(qt, r8)), f_hi = f_lo + 8 * (q8 + (qt < r8 ? 1 : 0));
         const float* Asrc = is_g ? W : U;
         int bcount = 0;
         for (int it = 0; it < n_it; ++it) {
@@ -145,15 +150,15 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                     if (is_g) {
                         const char* pw = reinterpret_cast<const char*>(W + (size_t)nrow * M + c_lo);
                         for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pw + o));
-                    } else if (half == 0) {
+                    } else if (qt == 0) {
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(vbar + (size_t)nrow * D)));
                     }
                 }
             }
             // this half's slice of the row(s), tf32-rounded, kept in registers
-            float4 uv[16];
+            float4 uv[8];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
+            for (int c = 0; c < 8; ++c) {
                 const int c0 = c_lo + 4 * c;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid && c0 < c_hi) {
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
             // ---- A operand
             if (it > 0) mbar_wait(bar_afree, (it - 1) & 1);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
+            for (int c = 0; c < 8; ++c) {
                 const int c0 = c_lo + 4 * c;
                 if (c0 < c_hi) {
                     float4 v = uv[c];
@@ -192,11 +197,11 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                         }
                     }
                     float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-                    if (sub == 1) hi = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
+                    if (sub == 1) hi = make_float4(tf32_lo_trunc(v.x, hi.x), tf32_lo_trunc(v.y, hi.y), tf32_lo_trunc(v.z, hi.z), tf32_lo_trunc(v.w, hi.w));
                     store4(A_t, c0, hi);
                 }
             }
-            if (half && it == 0) {      // zero the feature padding [NPAD, 128) of A and of both B buffers once
+            if (qt == 3 && it == 0) {   // zero the feature padding [NPAD, 128) of A and of both B buffers once
                 for (int c0 = NPAD; c0 < 128; c0 += 4) {
                     store4(A_t, c0, make_float4(0.f, 0.f, 0.f, 0.f));
                     store4(B_t, c0, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                 const bool isq = has_q && b == nd;
                 if (isq) {
                     // B[r][d] = mubar[r][d] (16 columns, zero padded)
-                    if (half == 0) {
+                    if (qt == 0) {
 #pragma unroll
                         for (int c0 = 0; c0 < 16; c0 += 4) {
                             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -229,12 +234,12 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                 } else {
                     const float sc = b == 0 ? scv[0] : b == 1 ? scv[1] : scv[2];
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
+                    for (int c = 0; c < 8; ++c) {
                         const int c0 = c_lo + 4 * c;
                         if (c0 < c_hi) {
                             float4 v = uv[c];
                             float4 hi = make_float4(tf32_rna(v.x * sc), tf32_rna(v.y * sc), tf32_rna(v.z * sc), tf32_rna(v.w * sc));
-                            if (is_g && b == 1) hi = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));   // U_lo
+                            if (is_g && b == 1) hi = make_float4(tf32_lo_trunc(v.x, hi.x), tf32_lo_trunc(v.y, hi.y), tf32_lo_trunc(v.z, hi.z), tf32_lo_trunc(v.w, hi.w));   // U_lo
                             store4(Bb, c0, hi);
                         }
                     }
@@ -255,14 +260,14 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
             else if (isq) { out = P.qmubar; ldo = D; ncols = D; }
             else { out = P.Pd + (size_t)(d0 + b) * M * M; ldo = M; ncols = M; }
             const uint32_t dcol = isq ? 384u : 128u * (uint32_t)b;
-            const int lo = isq ? (half ? 16 : 0) : c_lo, hi = isq ? 16 : c_hi;
+            const int lo = isq ? (qt ? 16 : 0) : f_lo, hi = isq ? 16 : f_hi;
             for (int c0 = lo; c0 < hi; c0 += 8) {
                 float v[8];
                 __syncwarp();
                 tmem_ld8(lane_addr + dcol + c0, v);
                 if (i < M) {
                     float* dst = &out[(size_t)i * ldo + c0];
-                    if ((ldo & 3) == 0 && c0 + 8 <= ncols) {       // 16-byte aligned: two vector reductions instead of eight scalar
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && c0 + 8 <= ncols) {       // 16-byte aligned: two vector reductions instead of eight scalar
                         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
                         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
                     } else {
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == RR_WARP_MMA) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 bool tc_rowred_supported(const LayerDev& P) { return P.M <= 128 && P.M >= 8 && P.Dout <= 16; }

@@ -153,10 +153,14 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) + ((k & 3) << 2));
 }
 
+// fp32 -> tf32, round to nearest / ties away (= cvt.rna.tf32.f32 for finite values).  ptxas expands the cvt into four
+// instructions (add, Inf/NaN test, select, mask); the operands here are finite, so add + mask suffice.  Measured: the
+// conversions were ~10 % of all warp instructions of the row kernels (profiles/r2_instruction_mix.md).
 __device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// low part of a 3xTF32 split where the last bit does not matter (gradients): x - hi is exact in fp32 and the tensor core
+// ignores the 13 low mantissa bits of a tf32 operand (truncation: error <= 2^-21 |x| instead of 2^-22 with rounding)
+__device__ __forceinline__ float tf32_lo_trunc(float x, float hi) { return x - hi; }
 
 }  // namespace tc

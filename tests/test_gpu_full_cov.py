@@ -60,8 +60,9 @@ def test_full_cov_public_entry_points_and_diag_consistency():
     assert np.all(np.isfinite(Fs[-1]))
     # layer 1 does not depend on the draws: full-cov diagonal == diagonal path
     dFs, dFm, dFv = m.predict_all_layers(prob['X'], 4)
-    assert_allclose(np.einsum('snnd->snd', Fv[0]), dFv[0], atol=5e-4, rtol=0)
-    assert_allclose(Fm[0], dFm[0], atol=5e-4, rtol=0)
+    # (fp64 full_cov pipeline vs fp32/TF32 row path on a cond ~ 3e4 problem: 1e-4 of the layer's scale)
+    assert_allclose(np.einsum('snnd->snd', Fv[0]), dFv[0], atol=1e-4 * max(1.0, np.abs(dFv[0]).max()), rtol=0)
+    assert_allclose(Fm[0], dFm[0], atol=1e-4 * max(1.0, np.abs(dFm[0]).max()), rtol=0)
 
 
 def test_standalone_layer_conditional_and_sample_full_cov():
