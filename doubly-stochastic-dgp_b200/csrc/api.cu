@@ -72,6 +72,7 @@ struct dsdgp_ctx {
     std::vector<unsigned char> kinds_base;   // structural kinds (host); device kinds = base, or 4 where set untrainable
     std::vector<unsigned char> kinds_host;
     double* ng_ws; size_t ng_ws_n; int* ng_status;   // natural-gradient workspace (lazily sized)
+    float* ng_stage; size_t ng_stage_n;               // staged (q_mu, q_sqrt) of the layers of one natural-gradient step
     float* sw_dev; int sw_n;                          // per-sample likelihood weights (DGP_Quad), sw_n == 0: uniform
     double* fc_ws; size_t fc_ws_n; float* fc_out; size_t fc_out_n;   // full_cov path: fp64 workspace, fp32 output staging
     std::vector<LayerOff> off;
@@ -222,7 +223,7 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
     CK(small_matrix_init());
     CK(natgrad_init());
     CK(full_cov_init());
-    c->ng_ws = nullptr; c->ng_ws_n = 0;
+    c->ng_ws = nullptr; c->ng_ws_n = 0; c->ng_stage = nullptr; c->ng_stage_n = 0;
     CK(dmalloc(&c->sw_dev, (size_t)desc->S_max)); c->sw_n = 0;
     c->fc_ws = nullptr; c->fc_ws_n = 0; c->fc_out = nullptr; c->fc_out_n = 0;
     CK(dmalloc(&c->ng_status, 1));
@@ -350,7 +351,7 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     float* fl[] = {c->params, c->grads, c->free_, c->adam_m, c->adam_v, c->sm32, c->accf, c->Xd, c->Yd};
     for (float* p : fl) cudaFree(p);
-    cudaFree(c->chain_flags); cudaFree(c->dbg_buf); cudaFree(c->ng_ws); cudaFree(c->ng_status); cudaFree(c->fc_ws); cudaFree(c->fc_out); cudaFree(c->sw_dev);
+    cudaFree(c->chain_flags); cudaFree(c->dbg_buf); cudaFree(c->ng_ws); cudaFree(c->ng_stage); cudaFree(c->ng_status); cudaFree(c->fc_ws); cudaFree(c->fc_out); cudaFree(c->sw_dev);
     cudaFree(c->kinds); cudaFree(c->sm64); cudaFree(c->sa_dev); cudaFree(c->acc); cudaFree(c->result_dev);
     for (int l = 0; l < c->desc.L; ++l) {
         float* pl[] = {c->U[l], c->Fmean[l], c->Fvar[l], c->F[l], c->zs[l], c->xbar[l], c->meanW[l], c->meanB[l], c->wpack[l],
@@ -548,8 +549,11 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         if (!(side && c->fin_per_layer)) launch_fin(c->ls, 0, L, c->acc, c->sa_dev, st, nl);
         PROF_END(2);
     }
-    launch_elbo_finish(c->acc, c->sa_dev, grad ? c->grads + c->off_likvar : nullptr, c->grads + c->n_params, st, nl);
+    // tail: single GPU = ONE kernel (ELBO scalar + result + likelihood-variance gradient + Adam); with a communicator the ELBO
+    // (hi, lo) pair has to be written behind the gradient before the all-reduce, the rest follows it in one kernel.
+    // Only the likelihood-variance slot of the gradient is written here, so ELBO-only calls (no gradient) take the 1-block path.
     if (c->comm) {
+        launch_elbo_finish(c->acc, c->sa_dev, grad ? c->grads + c->off_likvar : nullptr, c->grads + c->n_params, st, nl);
         PROF_BEGIN(3);
         int rc;
         if (grad) rc = g_nccl.AllReduce(c->grads, c->grads, c->n_params + 2, NCCL_FLOAT, NCCL_SUM, c->comm, st);
@@ -557,12 +561,10 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         if (rc) return set_err(DSDGP_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
         PROF_END(3);
     }
-    launch_result(c->acc, c->grads + c->n_params, c->comm != nullptr, c->result_dev, st, nl);
-    if (mode == MODE_TRAIN) {
-        PROF_BEGIN(4);
-        launch_adam(c->params, c->free_, c->adam_m, c->adam_v, c->grads, c->kinds, nullptr, c->n_params, c->sa_dev, st, nl);
-        PROF_END(4);
-    }
+    PROF_BEGIN(4);
+    launch_tail(c->params, c->free_, c->adam_m, c->adam_v, c->grads, c->kinds, c->n_params, c->sa_dev, c->acc,
+                grad ? c->off_likvar : (size_t)-1, c->comm != nullptr, mode == MODE_TRAIN, c->result_dev, st, nl);
+    PROF_END(4);
     CK(cudaGetLastError());
     return DSDGP_OK;
 }
@@ -820,7 +822,10 @@ static int elbo_common(dsdgp_ctx* c, int mode, const float* X, const float* Y, i
     rc = run_step(c, mode, N, S, num_data, zmask, seed);
     if (rc) return rc;
     if (mode == MODE_TRAIN && (flags & DSDGP_FLAG_NO_SYNC)) return DSDGP_OK;
-    return fetch_result(c, elbo);
+    rc = fetch_result(c, elbo);
+    // a failed factorisation skipped the update on the device (k_adam): the step did not happen for the bias correction either
+    if (rc == DSDGP_ERR_NOT_PD && mode == MODE_TRAIN && c->adam_t > 0) c->adam_t -= 1;
+    return rc;
 }
 
 int dsdgp_elbo(dsdgp_ctx* c, const float* X, const float* Y, int N, int S, double num_data, const float* const* zs,
@@ -884,12 +889,13 @@ int dsdgp_natgrad_step(dsdgp_ctx* c, const float* X, const float* Y, int N, int 
     if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
     if (!layers || n_layers < 1) return set_err(DSDGP_ERR_INVALID, "natgrad: empty layer list");
     if (!(gamma > 0.0) || !(gamma <= 1.0)) return set_err(DSDGP_ERR_INVALID, "natgrad: gamma=%g outside (0, 1]", gamma);
-    size_t need = 0;
+    size_t need = 0, need_stage = 0;
     for (int i = 0; i < n_layers; ++i) {
         if (layers[i] < 0 || layers[i] >= c->desc.L) return set_err(DSDGP_ERR_INVALID, "natgrad: layer %d out of range", layers[i]);
         for (int k = 0; k < i; ++k) if (layers[k] == layers[i]) return set_err(DSDGP_ERR_INVALID, "natgrad: layer %d listed twice", layers[i]);
         const dsdgp_layer_desc& d = c->desc.layers[layers[i]];
         need = max(need, natgrad_ws_doubles(d.M, d.D_out));
+        need_stage += (size_t)d.M * d.D_out + (size_t)d.D_out * d.M * d.M;
     }
     CK(cudaSetDevice(c->desc.device));
     if (need > c->ng_ws_n) {
@@ -899,11 +905,21 @@ int dsdgp_natgrad_step(dsdgp_ctx* c, const float* X, const float* Y, int N, int 
         CK(dmalloc(&c->ng_ws, need));
         c->ng_ws_n = need;
     }
+    if (need_stage > c->ng_stage_n) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->ng_stage) CK(cudaFree(c->ng_stage));
+        c->ng_stage = nullptr; c->ng_stage_n = 0;
+        CK(dmalloc(&c->ng_stage, need_stage));
+        c->ng_stage_n = need_stage;
+    }
     // ELBO + gradient pass: fills the row-reduced accumulators P_d, qmubar (and Kinv) the update is built from
     double e = 0.0;
     int rc = elbo_common(c, MODE_GRAD, X, Y, N, S, num_data, zs, seed, flags, &e);
     if (rc) return rc;
     CK(cudaMemsetAsync(c->ng_status, 0, sizeof(int), c->stream));
+    // every layer's new (q_mu, q_sqrt) is staged; the parameters are overwritten only if all factorisations of all layers
+    // succeeded, so a failing step leaves the model exactly as it was
+    size_t stage_off = 0;
     for (int i = 0; i < n_layers; ++i) {
         const int l = layers[i];
         const LayerDev& P = c->ls.l[l];
@@ -913,18 +929,31 @@ int dsdgp_natgrad_step(dsdgp_ctx* c, const float* X, const float* Y, int N, int 
             int e2 = g_nccl.AllReduce(P.Pd, P.Pd, (size_t)d.D_out * mm + mm + (size_t)d.M * d.D_out, NCCL_FLOAT, NCCL_SUM, c->comm, c->stream);
             if (e2) return set_err(DSDGP_ERR_NCCL, "natgrad ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e2) : "?");
         }
-        launch_natgrad_layer(P, gamma, c->ng_ws, c->ng_status, c->params + c->off[l].q_mu, c->params + c->off[l].q_sqrt,
-                             c->stream, &c->nlaunch);
+        float* mu_new = c->ng_stage + stage_off;
+        float* sq_new = mu_new + (size_t)d.M * d.D_out;
+        stage_off += (size_t)d.M * d.D_out + (size_t)d.D_out * mm;
+        launch_natgrad_layer(P, gamma, c->ng_ws, c->ng_status, mu_new, sq_new, c->stream, &c->nlaunch);
+    }
+    stage_off = 0;
+    for (int i = 0; i < n_layers; ++i) {
+        const int l = layers[i];
+        const dsdgp_layer_desc& d = c->desc.layers[l];
+        const size_t nmu = (size_t)d.M * d.D_out, nsq = (size_t)d.D_out * d.M * d.M;
+        const float* mu_new = c->ng_stage + stage_off;
+        const float* sq_new = mu_new + nmu;
+        stage_off += nmu + nsq;
+        launch_natgrad_commit(c->params + c->off[l].q_mu, mu_new, nmu, c->ng_status, c->stream, &c->nlaunch);
+        launch_natgrad_commit(c->params + c->off[l].q_sqrt, sq_new, nsq, c->ng_status, c->stream, &c->nlaunch);
         if (c->adam_on) {   // keep Adam's unconstrained copy of these (identity-transformed) fields in step
-            CK(cudaMemcpyAsync(c->free_ + c->off[l].q_mu, c->params + c->off[l].q_mu, (size_t)d.M * d.D_out * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-            CK(cudaMemcpyAsync(c->free_ + c->off[l].q_sqrt, c->params + c->off[l].q_sqrt, (size_t)d.D_out * mm * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+            launch_natgrad_commit(c->free_ + c->off[l].q_mu, mu_new, nmu, c->ng_status, c->stream, &c->nlaunch);
+            launch_natgrad_commit(c->free_ + c->off[l].q_sqrt, sq_new, nsq, c->ng_status, c->stream, &c->nlaunch);
         }
     }
     CK(cudaGetLastError());
     int st_host = 0;
     CK(cudaMemcpyAsync(&st_host, c->ng_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (st_host) return set_err(DSDGP_ERR_NOT_PD, "natgrad: a natural-parameter precision (or S) was not positive definite; (q_mu, q_sqrt) of the affected layer were left unchanged (gamma=%g too large for a non-conjugate layer?)", gamma);
+    if (st_host) return set_err(DSDGP_ERR_NOT_PD, "natgrad: a natural-parameter precision (or S) was not positive definite; no parameter of any layer was changed (gamma=%g too large for a non-conjugate layer?)", gamma);
     if (elbo) *elbo = e;
     return DSDGP_OK;
 }

@@ -237,8 +237,9 @@ cudaError_t rowred_tc_init();
 bool tc_rowred_supported(const LayerDev& P);
 void launch_bwd_rowred_tc(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
 cudaError_t small_matrix_init();
-void launch_adam(float* params, float* free_, float* m, float* v, const float* grads, const unsigned char* kinds,
-                 const int* tril_m, size_t n, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
+void launch_tail(float* params, float* free_, float* m, float* v, float* grads, const unsigned char* kinds, size_t n,
+                 const StepArgs* sa, Accum* acc, size_t off_likvar, int use_hi_lo, int do_adam, double* result,
+                 cudaStream_t st, long long* nlaunch);
 void launch_constrain_init(const float* params, float* free_, const unsigned char* kinds, size_t n, cudaStream_t st,
                            long long* nlaunch);
 void launch_predict_y(int lik, const float* Fmean, const float* Fvar, int R, int D, const float* lik_var, float* mean,
@@ -255,5 +256,6 @@ cudaError_t natgrad_init();
 size_t natgrad_ws_doubles(int M, int D);
 void launch_natgrad_layer(const LayerDev& P, double gamma, double* ws, int* status, float* q_mu, float* q_sqrt,
                           cudaStream_t st, long long* nlaunch);
+void launch_natgrad_commit(float* dst, const float* src, size_t n, const int* status, cudaStream_t st, long long* nlaunch);
 size_t fwd_smem_bytes(int M, int Din, int TR);
 size_t bwd_smem_bytes(int M, int Din, int TR);

@@ -21,19 +21,39 @@
 // weight packing (layout: tc_pack.cuh).  One thread per stored element; hi = tf32(x), lo = tf32(x - hi).
 // ----------------------------------------------------------------------------------------------
 // part 0: every block; 1: the four Linv blocks (need this step's factorisation); 2: the q_sqrt blocks (parameters only --
-// packed on the side branch of the step DAG while the factorisation runs)
+// packed on the side branch of the step DAG while the factorisation runs): G2 (L_d^T, forward) and S_d = L_d L_d^T (backward)
 __global__ void k_pack_fwd(LayerSet ls, int part) {
     const LayerDev& P = ls.l[blockIdx.y];
     if (!P.wpack_fwd) return;
-    const int M = P.M, D = P.Dout, nkb = tcp::nkb_of(M);
+    const int M = P.M, D = P.Dout, nkb = tcp::nkb_of(M), NPAD = tcp::npad_of(M);
     const uint32_t slot = tcp::slot_bytes(M);
-    const int nblk = tcp::num_blocks(D);
+    const int nblk = tcp::num_blocks(D) + D;            // triangular blocks, then the D square S_d operands
     const int per_blk = nkb * 128 * 32;                 // (kb, n, kk) index space; rows outside a band are skipped
     const int blk0 = part == 2 ? 4 : 0, blk1 = part == 1 ? 4 : nblk;
     const size_t total = (size_t)(blk1 - blk0) * per_blk;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int blk = blk0 + (int)(e / per_blk), w = (int)(e % per_blk), kb = w >> 12, n = (w >> 5) & 127, kk = w & 31, k = kb * 32 + kk;
-        const int pat = (blk < 2 || blk >= 4 + D) ? tcp::PAT_LE : tcp::PAT_GE;
+        if (blk >= 4 + D) {
+            // S_d[n][k] = sum_{j <= min(n,k)} L_d[n][j] L_d[k][j]  (symmetric: B[n][k] = S_d[k][n] = S_d[n][k])
+            if (n >= NPAD) continue;
+            const int d = blk - 4 - D;
+            float out = 0.f;
+            if (n < M && k < M) {
+                const float* Ln = P.q_sqrt + ((size_t)d * M + n) * M;
+                const float* Lk = P.q_sqrt + ((size_t)d * M + k) * M;
+                const int jm = min(n, k);
+                float s0 = 0.f, s1 = 0.f;
+                int j = 0;
+                for (; j + 1 <= jm; j += 2) { s0 = fmaf(Ln[j], Lk[j], s0); s1 = fmaf(Ln[j + 1], Lk[j + 1], s1); }
+                if (j <= jm) s0 = fmaf(Ln[j], Lk[j], s0);
+                out = tc::tf32_rna(s0 + s1);
+            }
+            char* dst = reinterpret_cast<char*>(P.wpack_fwd) + tcp::s_region_offset(M, D) + (size_t)d * tcp::sfull_bytes(M) +
+                        (size_t)kb * tcp::sfull_band_bytes(M) + tc::sw128_offset(n, kk);
+            *reinterpret_cast<float*>(dst) = out;
+            continue;
+        }
+        const int pat = blk < 2 ? tcp::PAT_LE : tcp::PAT_GE;
         const int r0 = tcp::band_row0(pat, kb), nr = tcp::band_rows(pat, M, kb);
         if (n < r0 || n >= r0 + nr) continue;
         float out = 0.f;
@@ -43,12 +63,9 @@ __global__ void k_pack_fwd(LayerSet ls, int part) {
                 const double v = (blk < 2) ? P.Linv64[(size_t)n * M + k] : P.Linv64[(size_t)k * M + n];   // G1: Linv[n][k] ; G1': Linv[k][n]
                 const float hi = tc::tf32_rna((float)v);
                 out = part ? tc::tf32_rna((float)(v - (double)hi)) : hi;
-            } else if (blk < 4 + D) {
+            } else {
                 const int d = blk - 4;
                 if (n <= k) out = tc::tf32_rna(P.q_sqrt[((size_t)d * M + k) * M + n]);                     // G2: L_d[k][n]
-            } else {
-                const int d = blk - 4 - D;
-                if (k <= n) out = tc::tf32_rna(P.q_sqrt[((size_t)d * M + n) * M + k]);                     // G5: L_d[n][k]
             }
         }
         char* dst = reinterpret_cast<char*>(P.wpack_fwd) + (size_t)blk * slot + tcp::band_offset(pat, M, kb) +
@@ -536,7 +553,7 @@ cudaError_t layer_tc_init() {
 
 size_t tc_fwd_pack_bytes(int M, int D, int white) {
     (void)white;
-    return (size_t)tcp::num_blocks(D) * tcp::slot_bytes(M);
+    return tcp::pack_bytes(M, D);
 }
 
 bool tc_chain_fwd_supported(const LayerSet& ls) {

@@ -1,24 +1,29 @@
 // tcgen05 tensor-core path of one SVGP layer: backward over rows (data gradient + per-row quantities the row-reduction
-// GEMMs need).  Same tiling as the forward (128 rows on the UMMA M dimension, FOUR threads per row = 16 row warps, one TMA
-// producer warp, one MMA-issuing warp): the tile is a chain of latency-bound SIMT phases, which 4 warps per scheduler hide
-// far better than 2 (profiles/r2_*).  Per tile:
-//   G2[d]: c_d = L_d^T u              1xTF32   (recomputed, as the SIMT path does)
-//   G5[d]: ubar += L_d (2 vbar_d c_d) 1xTF32   accumulated over d in TMEM
-//   G6   : t = Linv ubar              3xTF32   (non-white)      } w = K^-1 ubar needs the accuracy: the solve
-//   G7   : w = Linv^T t               3xTF32                    } amplifies operand rounding by ~sqrt(cond K)
-// then k̄, g = 2 k̄ dk/dr2, x̄, and the Z / lengthscale / variance partials exactly as k_layer_bwd (layer_simt.cu).
+// GEMMs need).  128 rows on the UMMA M dimension, FOUR threads per row (16 row warps), one TMA producer warp, one
+// MMA-issuing warp.  Per tile:
+//   GS[d]: y_d = S_d u,  S_d = L_d L_d^T   1xTF32   one product per output instead of c_d = L_d^T u followed by
+//                                                    L_d (2 vbar_d c_d): the row threads only accumulate
+//                                                    ubar += 2 vbar_d y_d in registers -- no per-d SIMT -> smem -> MMA
+//                                                    round trip (round 1: 30k of the tile's 88k cycles)
+//   G6   : t = Linv ubar                    3xTF32   (non-white)      } w = K^-1 ubar needs the accuracy: the solve
+//   G7   : w = Linv^T t                     3xTF32                    } amplifies operand rounding by ~sqrt(cond K)
+// then kbar, g = 2 kbar dk/dr2, xbar, and the Z / lengthscale / variance partials.
+// Weights stream from L2 as 32-wide k-block "bands" (<= 16 KB, one TMA bulk copy each) through a ring of sub-slots: four
+// dedicated ones plus, while the S_d products run, the four 16 KB blocks of the (then unused) second operand buffer, so
+// up to eight bands are in flight.
 // Math: tests/algo_mirror.py::layer_bwdA ; reference: TF autodiff of layers.py:178-219.
 #include "dsdgp_internal.cuh"
 #include "tc_common.cuh"
 #include "tc_pack.cuh"
 
 #define TC_ROWS 128
-#define TC_NSTAGE 2
 #define TC_CHUNK_BYTES 16384
 #define TC_THREADS 576
 #define TC_ROWTHREADS 512
 #define TC_WARP_TMA 16
 #define TC_WARP_MMA 17
+#define BW_NR 4                  // dedicated ring sub-slots (16 KB each)
+#define BW_NSA (BW_NR + 4)       // sub-slots while A_c is free (S_d phase)
 
 namespace {
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
@@ -32,13 +37,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
 
 // shared-memory plan (bytes from the 1024-aligned base)
 struct BwdSmem {
-    uint32_t A_u, A_c, Bring, bars, Zs, qmu, mv, xs, red, total;
+    uint32_t A_u, A_c, ring, bars, Zs, qmu, mv, xs, red, total;
 };
 __host__ __device__ inline BwdSmem bwd_smem_plan(int M, int Din, int D) {
     BwdSmem s;
-    s.A_u = 0; s.A_c = 65536; s.Bring = 131072;
-    s.bars = s.Bring + TC_NSTAGE * tcp::slot_bytes(M);
-    s.Zs = s.bars + 256;
+    s.A_u = 0; s.A_c = 65536; s.ring = 131072;
+    s.bars = s.ring + BW_NR * TC_CHUNK_BYTES;
+    s.Zs = s.bars + 512;
     s.qmu = s.Zs + 4 * ((M * Din + 3) & ~3);
     s.mv = s.qmu + 4 * ((M * D + 3) & ~3);
     s.xs = s.mv + 4 * 128 * 2 * D;
@@ -48,7 +53,7 @@ __host__ __device__ inline BwdSmem bwd_smem_plan(int M, int Din, int D) {
 }
 
 // DINP == D_in and DOUTP == D_out exactly, kernel type and whitening are compile-time: the kernel is I-cache sensitive
-// (measured 21% "no instruction" stalls with the generic 13k-instruction body), other shapes use layer_simt.cu.
+// (measured 21% "no instruction" stalls with a generic 13k-instruction body), other shapes use layer_simt.cu.
 template <int DINP, int DOUTP, int KERN, bool WHITE>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdArgs a) {
     using namespace tc;
@@ -58,35 +63,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     const int M = P.M;
     constexpr int Din = DINP, D = DOUTP;
     const BwdSmem sp = bwd_smem_plan(M, Din, D);
-    const uint32_t A_u = sbase + sp.A_u, A_c = sbase + sp.A_c, Bring = sbase + sp.Bring, bars = sbase + sp.bars;
-    const uint32_t bar_full = bars, bar_empty = bars + 32;
-    const uint32_t slotb = tcp::slot_bytes(M);
-    const uint32_t bar_au = bars + 64, bar_acc2f = bars + 72 /*[2]*/, bar_cready = bars + 88, bar_cfree = bars + 96;
-    const uint32_t bar_ubar = bars + 104, bar_s6 = bars + 112, bar_acc6 = bars + 120, bar_s7 = bars + 128, bar_acc7 = bars + 136;
-    const uint32_t tmem_slot = bars + 144;
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + sp.bars + 144);
-    float* Zs = reinterpret_cast<float*>(sgen + sp.Zs);
+    const uint32_t A_u = sbase + sp.A_u, A_c = sbase + sp.A_c, ring = sbase + sp.ring, bars = sbase + sp.bars;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * BW_NSA;                 // [BW_NSA] each
+    const uint32_t bar_au = bars + 16 * BW_NSA, bar_yfull = bar_au + 8 /*[2]*/, bar_yfree = bar_au + 24 /*[2]*/;
+    const uint32_t bar_s6 = bar_au + 40, bar_acc6 = bar_au + 48, bar_s7 = bar_au + 56, bar_acc7 = bar_au + 64;
+    const uint32_t tmem_slot = bar_au + 72;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + sp.bars + 16 * BW_NSA + 72);
+    float* Zs = reinterpret_cast<float*>(sgen + sp.Zs);         // [M][Din], scaled by 1/lengthscale
     float* qmu_s = reinterpret_cast<float*>(sgen + sp.qmu);
     float* mv_s = reinterpret_cast<float*>(sgen + sp.mv);       // [128][2D]: mubar (D) | vbar (D)
-    float* xs_s = reinterpret_cast<float*>(sgen + sp.xs);       // [128][Din]
+    float* xs_s = reinterpret_cast<float*>(sgen + sp.xs);       // [128][Din], scaled by 1/lengthscale
     float* red_s = reinterpret_cast<float*>(sgen + sp.red);     // [64]
     float* g_s = reinterpret_cast<float*>(sgen + sp.A_c);       // [128][MP] once A_c is dead
+    float* zred_s = reinterpret_cast<float*>(sgen + sp.A_u);    // [4][M][Din] once A_u is dead
     const int MP = M | 1;                                        // odd row stride: conflict-free column walks
 
     const int nkb = (M + 31) / 32, NPAD = (M + 15) & ~15;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * TC_ROWS, R = a.R;
+    const uint32_t band_full = 128u * (uint32_t)NPAD;           // one k-block of a square (S_d) operand
+    auto slot_addr = [&](int s) { return s < BW_NR ? ring + (uint32_t)s * TC_CHUNK_BYTES : A_c + (uint32_t)(s - BW_NR) * TC_CHUNK_BYTES; };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < BW_NSA; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_au, TC_ROWTHREADS);
-        mbar_init(bar_acc2f, 1); mbar_init(bar_acc2f + 8, 1);
-        mbar_init(bar_cready, TC_ROWTHREADS); mbar_init(bar_cfree, 1); mbar_init(bar_ubar, 1);
+        mbar_init(bar_yfull, 1); mbar_init(bar_yfull + 8, 1);
+        mbar_init(bar_yfree, TC_ROWTHREADS); mbar_init(bar_yfree + 8, TC_ROWTHREADS);
         mbar_init(bar_s6, TC_ROWTHREADS); mbar_init(bar_acc6, 1); mbar_init(bar_s7, TC_ROWTHREADS); mbar_init(bar_acc7, 1);
         fence_mbar_init();
     }
     if (warp == TC_WARP_TMA) tmem_alloc(tmem_slot, 512);
-    for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) Zs[e] = P.Z[e];
+    for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) Zs[e] = P.Z[e] * (1.0f / P.ls[P.ard ? e % Din : 0]);
     for (int e = threadIdx.x; e < M * D; e += TC_THREADS) qmu_s[e] = P.q_mu[e];
     tc_fence_before();
     __syncthreads();
@@ -94,88 +101,89 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     const uint32_t tmem = *tmem_slot_gen;
 
     if (warp == TC_WARP_TMA) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer: one bulk copy per band, in the order the MMA warp consumes them ============
         if (lane == 0) {
             const char* wsrc = reinterpret_cast<const char*>(P.wpack_fwd);
+            uint32_t par = 0;          // bit s: parity of the next use of sub-slot s
             int s = 0;
-            uint32_t ph = 1;
-            auto load = [&](int blk, int pat) {            // one band block = one bulk copy
-                const uint32_t bytes = tcp::block_bytes(pat, M);
-                mbar_wait(bar_empty + 8 * s, ph);
+            auto load = [&](const char* src, uint32_t bytes, int nslots) {
+                mbar_wait(bar_empty + 8 * s, ((par >> s) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
-                tma_bulk_g2s(Bring + s * slotb, wsrc + (size_t)blk * slotb, bytes, bar_full + 8 * s);
-                if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
+                tma_bulk_g2s(slot_addr(s), src, bytes, bar_full + 8 * s);
+                par ^= 1u << s;
+                if (++s == nslots) s = 0;
             };
-            load(tcp::blk_g2(0), tcp::PAT_GE);
-            if (D > 1) load(tcp::blk_g2(1), tcp::PAT_GE);
-            for (int d = 0; d < D; ++d) { load(tcp::blk_g5(D, d), tcp::PAT_LE); if (d + 2 < D) load(tcp::blk_g2(d + 2), tcp::PAT_GE); }
-            if (!WHITE) { load(tcp::blk_g1(0), tcp::PAT_LE); load(tcp::blk_g1(1), tcp::PAT_LE); }
-            load(tcp::blk_g1p(0), tcp::PAT_GE); load(tcp::blk_g1p(1), tcp::PAT_GE);
+            const char* ssrc = wsrc + tcp::s_region_offset(M, D);
+            for (int d = 0; d < D; ++d)
+                for (int kb = 0; kb < nkb; ++kb)
+                    load(ssrc + (size_t)d * tcp::sfull_bytes(M) + (size_t)kb * band_full, band_full, BW_NSA);
+            s = 0;
+            const uint32_t slotb = tcp::slot_bytes(M);
+            auto load_block = [&](int blk, int pat) {
+                for (int q = 0; q < nkb; ++q) {
+                    const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
+                    load(wsrc + (size_t)blk * slotb + tcp::band_offset(pat, M, kb), 128u * (uint32_t)tcp::band_rows(pat, M, kb), BW_NR);
+                }
+            };
+            if (!WHITE) { load_block(tcp::blk_g1(0), tcp::PAT_LE); load_block(tcp::blk_g1(1), tcp::PAT_LE); }
+            load_block(tcp::blk_g1p(0), tcp::PAT_GE); load_block(tcp::blk_g1p(1), tcp::PAT_GE);
         }
     } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues ========
+        uint32_t par = 0;
         int s = 0;
-        uint32_t ph = 0;
         const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         auto mkdesc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
-        // one band block: D (+)= A * B^T over all its k-blocks.  with_lo: also A_lo against the same block; fresh: the
-        // block starts a new accumulator
-        auto do_block = [&](uint32_t dcol, uint32_t Ahi, uint32_t Alo, int pat, bool with_lo, bool fresh) {
-            mbar_wait(bar_full + 8 * s, ph);
+        // one band: D[:, n0 .. n0+nrows) (+)= A[:, 32 kb .. ) * band^T.  with_lo: also A_lo against the same band
+        auto do_band = [&](uint32_t dcol, uint32_t Ahi, uint32_t Alo, int kb, int n0, int nrows, bool with_lo, bool fresh, int nslots) {
+            mbar_wait(bar_full + 8 * s, (par >> s) & 1u);
             tc_fence_after();
-            const uint32_t bslot = Bring + s * slotb;
-            uint32_t boff = 0;
+            const uint32_t bbase = slot_addr(s), abase = kb * TC_CHUNK_BYTES;
+            const int nks = min(4, (M - 32 * kb + 7) / 8);
+            const uint32_t id = make_idesc_tf32(128, nrows);
+            const uint32_t dc = tmem + dcol + (uint32_t)n0;
+            if (tc::elect_one()) {
 #pragma unroll 1
-            for (int q = 0; q < nkb; ++q) {
-                const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
-                const int nks = min(4, (M - 32 * kb + 7) / 8);
-                const int nrows = tcp::band_rows(pat, M, kb);
-                const uint32_t bbase = bslot + boff, abase = kb * TC_CHUNK_BYTES;
-                boff += 128u * (uint32_t)nrows;
-                const uint32_t id = make_idesc_tf32(128, nrows);
-                const uint32_t dc = tmem + dcol + (uint32_t)tcp::band_row0(pat, kb);
-                if (tc::elect_one()) {
-#pragma unroll 1
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint64_t bd = mkdesc(bbase + ks * 32);
-                        mma_tf32(dc, mkdesc(Ahi + abase + ks * 32), bd, id, (fresh && q == 0 && ks == 0) ? 0u : 1u);
-                        if (with_lo) mma_tf32(dc, mkdesc(Alo + abase + ks * 32), bd, id, 1u);
-                    }
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint64_t bd = mkdesc(bbase + ks * 32);
+                    mma_tf32(dc, mkdesc(Ahi + abase + ks * 32), bd, id, (fresh && ks == 0) ? 0u : 1u);
+                    if (with_lo) mma_tf32(dc, mkdesc(Alo + abase + ks * 32), bd, id, 1u);
                 }
-                __syncwarp();
+                mma_commit(bar_empty + 8 * s);
             }
-            if (tc::elect_one()) mma_commit(bar_empty + 8 * s);
             __syncwarp();
-            if (++s == TC_NSTAGE) { s = 0; ph ^= 1; }
+            par ^= 1u << s;
+            if (++s == nslots) s = 0;
         };
         auto commit = [&](uint32_t bar) { if (tc::elect_one()) mma_commit(bar); __syncwarp(); };
-        auto g2 = [&](int d) {
-            do_block(128u * (uint32_t)(d & 1), A_u, 0, tcp::PAT_GE, false, true);
-            commit(bar_acc2f + 8 * (d & 1));
+        // triangular band block: PAT_LE holds rows [32 kb, NPAD) of k-block kb, PAT_GE rows [0, min(NPAD, 32 kb + 32)); in
+        // both orders the FIRST band of a block spans all NPAD accumulator columns, so it is the one that clears them
+        auto do_block = [&](uint32_t dcol, int pat, bool with_lo, bool fresh) {
+            for (int q = 0; q < nkb; ++q) {
+                const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
+                do_band(dcol, A_c, A_u, kb, tcp::band_row0(pat, kb), tcp::band_rows(pat, M, kb), with_lo, fresh && q == 0, BW_NR);
+            }
         };
         mbar_wait(bar_au, 0);
         tc_fence_after();
-        g2(0);
-        if (D > 1) g2(1);
         for (int d = 0; d < D; ++d) {
-            mbar_wait(bar_cready, d & 1);
-            tc_fence_after();
-            do_block(256u, A_c, 0, tcp::PAT_LE, false, d == 0);
-            commit(bar_cfree);
-            if (d == D - 1) commit(bar_ubar);
-            if (d + 2 < D) g2(d + 2);
+            if (d >= 2) { mbar_wait(bar_yfree + 8 * (d & 1), ((d >> 1) - 1) & 1); tc_fence_after(); }
+            for (int kb = 0; kb < nkb; ++kb)
+                do_band(128u * (uint32_t)(d & 1), A_u, 0, kb, 0, NPAD, false, kb == 0, BW_NSA);
+            commit(bar_yfull + 8 * (d & 1));
         }
+        s = 0;
         if (!WHITE) {
             mbar_wait(bar_s6, 0);
             tc_fence_after();
-            do_block(0u, A_c, A_u, tcp::PAT_LE, true, true);
-            do_block(0u, A_c, A_u, tcp::PAT_LE, false, false);
+            do_block(0u, tcp::PAT_LE, true, true);
+            do_block(0u, tcp::PAT_LE, false, false);
             commit(bar_acc6);
         }
         mbar_wait(bar_s7, 0);
         tc_fence_after();
-        do_block(128u, A_c, A_u, tcp::PAT_GE, true, true);
-        do_block(128u, A_c, A_u, tcp::PAT_GE, false, false);
+        do_block(128u, tcp::PAT_GE, true, true);
+        do_block(128u, tcp::PAT_GE, false, false);
         commit(bar_acc7);
     } else {
         // ===================== row warps =====================
@@ -200,25 +208,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             a_store4(bhi, k4, hi);
             a_store4(blo, k4, lo);
         };
-        // this quarter's accumulator columns [c_lo, c_hi), multiples of 8
+        // this quarter's accumulator columns [c_lo, c_hi), multiples of 8, at most 32 wide
         const int nch8 = NPAD >> 3, cq = nch8 >> 2, cr = nch8 & 3;
         const int c_lo = 8 * (qt * cq + min(qt, cr)), c_hi = c_lo + 8 * (cq + (qt < cr ? 1 : 0));
+        const int nch = (c_hi - c_lo) >> 3;
         const float jit = a.jitter;
-        const unsigned long long seed = a.sa->seed;
-        const int noff = a.sa->n_offset, soff = a.sa->s_offset;
         const float var0 = P.var[0];
         const bool dbg = a.dbg && blockIdx.x == 0 && threadIdx.x == 0;
         int dbi = 0;
 #define BSTAMP() do { if (dbg) a.dbg[dbi++] = clock64(); } while (0)
         BSTAMP();   // 0
 
-        // ---- R0: x tile, mubar / vbar (this quarter: d = qt, qt+4, ...)
-        float x[DINP], il[DINP];
+        // ---- R0: x tile (scaled by 1/lengthscale), mubar / vbar (this quarter: d = qt, qt+4, ...)
+        float xs[DINP];
 #pragma unroll
         for (int q = 0; q < DINP; ++q) {
-            x[q] = (valid && q < Din) ? a.Xin[(size_t)row * Din + q] : 0.f;
-            il[q] = q < Din ? 1.0f / P.ls[P.ard ? q : 0] : 0.f;
-            if (qt == 0 && q < Din) xs_s[t * Din + q] = x[q];
+            xs[q] = (valid ? a.Xin[(size_t)row * Din + q] : 0.f) * (1.0f / P.ls[P.ard ? q : 0]);
+            if (qt == 0) xs_s[t * Din + q] = xs[q];
         }
 #pragma unroll 1
         for (int d = qt; d < D; d += 4) {
@@ -245,32 +251,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             mv_s[t * 2 * D + d] = m;
             mv_s[t * 2 * D + D + d] = v;
         }
-        // ---- R1: u (this quarter's columns) -> A_u as the G2 operand; loads are issued four chunks ahead of their use
-        constexpr bool vec4 = true;               // M % 4 == 0 (tc_bwd_supported)
-        auto load_u4 = [&](int c0) -> float4 {
+        // ---- R1: u (this quarter's columns) -> A_u as the operand of the S_d products; all loads issued up front
+        auto load_u4 = [&](int c0) -> float4 {       // M % 4 == 0 (tc_bwd_supported)
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid && c0 < c_hi && c0 + 4 <= M) v = *reinterpret_cast<const float4*>(a.U + (size_t)row * M + c0);
             return v;
         };
         {
-            float4 q0 = load_u4(c_lo), q1 = load_u4(c_lo + 4), q2 = load_u4(c_lo + 8), q3 = load_u4(c_lo + 12);
-#pragma unroll 1
-            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-                float4 n0 = load_u4(c0 + 16), n1 = load_u4(c0 + 20), n2 = load_u4(c0 + 24), n3 = load_u4(c0 + 28);
-                const float4 cur[4] = {q0, q1, q2, q3};
+            float4 uq[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (c0 + 4 * e < c_hi) {
-                        const float v[4] = {cur[e].x, cur[e].y, cur[e].z, cur[e].w};
-                        store_hi(A_u, c0 + 4 * e, v);
-                    }
+            for (int e = 0; e < 8; ++e) uq[e] = load_u4(c_lo + 4 * e);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (c_lo + 4 * e < c_hi) {
+                    const float v[4] = {uq[e].x, uq[e].y, uq[e].z, uq[e].w};
+                    store_hi(A_u, c_lo + 4 * e, v);
                 }
-                q0 = n0; q1 = n1; q2 = n2; q3 = n3;
             }
-        }
-        if (qt == 3) {       // zero the K padding beyond NPAD (columns NPAD .. 32 nkb) once
-            const float z4[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int c0 = NPAD; c0 < nkb * 32; c0 += 4) { store_hi(A_u, c0, z4); store_hi(A_c, c0, z4); }
         }
         fence_proxy_async();
         mbar_arrive(bar_au);
@@ -279,122 +276,112 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         float mub[DOUTP], vb[DOUTP], vs = 0.f;
 #pragma unroll
         for (int d = 0; d < DOUTP; ++d) {
-            mub[d] = d < D ? mv_s[t * 2 * D + d] : 0.f;
-            vb[d] = d < D ? mv_s[t * 2 * D + D + d] : 0.f;
+            mub[d] = mv_s[t * 2 * D + d];
+            vb[d] = mv_s[t * 2 * D + D + d];
             vs += vb[d];
         }
-        // ---- R2 (deferred, interleaved below): r2_i for this quarter's inducing points -> TMEM scratch columns 384+
+        // ---- R2 (interleaved below): r2_i for this quarter's inducing points -> TMEM scratch columns 384+
         auto gram_chunk = [&](int c0) {
             float r2[8];
-            {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int i = min(c0 + u, M - 1);
-                    const float4* zr = reinterpret_cast<const float4*>(Zs + i * DINP);
-                    float s = 0.f;
+            for (int u = 0; u < 8; ++u) {
+                const int i = min(c0 + u, M - 1);
+                const float4* zr = reinterpret_cast<const float4*>(Zs + i * DINP);
+                float s = 0.f;
 #pragma unroll
-                    for (int q4 = 0; q4 < DINP / 4; ++q4) {
-                        const float4 zv = zr[q4];
-                        float d0 = (x[4 * q4] - zv.x) * il[4 * q4], d1 = (x[4 * q4 + 1] - zv.y) * il[4 * q4 + 1];
-                        float d2 = (x[4 * q4 + 2] - zv.z) * il[4 * q4 + 2], d3 = (x[4 * q4 + 3] - zv.w) * il[4 * q4 + 3];
-                        s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d2, d2, s); s = fmaf(d3, d3, s);
-                    }
-                    r2[u] = s;
+                for (int q4 = 0; q4 < DINP / 4; ++q4) {
+                    const float4 zv = zr[q4];
+                    const float d0 = xs[4 * q4] - zv.x, d1 = xs[4 * q4 + 1] - zv.y;
+                    const float d2 = xs[4 * q4 + 2] - zv.z, d3 = xs[4 * q4 + 3] - zv.w;
+                    s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d2, d2, s); s = fmaf(d3, d3, s);
                 }
+                r2[u] = s;
             }
             __syncwarp();
             tmem_st8(lane_addr + 384 + c0, r2);
         };
-        const int nch = (c_hi - c_lo) >> 3;
-        // ---- R3: d loop -- cbar_d = 2 vbar_d c_d -> A_c
-        for (int d = 0; d < D; ++d) {
-            for (int j = d; j < nch; j += D) gram_chunk(c_lo + 8 * j);
-            BSTAMP();   // 2+3d: deferred gram done
-            mbar_wait(bar_acc2f + 8 * (d & 1), (d >> 1) & 1);
-            BSTAMP();   // 3+3d: G2[d] ready
-            if (d > 0) mbar_wait(bar_cfree, (d - 1) & 1);
-            BSTAMP();   // 4+3d: A_c free
+        // ---- R3: ubar (this quarter's columns, registers) += 2 vbar_d (S_d u)
+        float ub[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) ub[c] = 0.f;
+#pragma unroll
+        for (int d = 0; d < DOUTP; ++d) {
+            for (int j = d; j < nch; j += D) gram_chunk(c_lo + 8 * j);     // every chunk exactly once over d = 0..D-1
+            mbar_wait(bar_yfull + 8 * (d & 1), (d >> 1) & 1);
             tc_fence_after();
-            float sc = 0.f;
+            BSTAMP();   // 2+d: y_d ready
+            const float sc = 2.f * vb[d];
 #pragma unroll
-            for (int dd = 0; dd < DOUTP; ++dd) if (dd == d) sc = 2.f * vb[dd];
-            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
-                float v[8];
-                __syncwarp();
-                tmem_ld8(lane_addr + 128 * (d & 1) + c0, v);
+            for (int c8 = 0; c8 < 4; ++c8) {
+                if (c8 < nch) {
+                    float v[8];
+                    __syncwarp();
+                    tmem_ld8(lane_addr + 128 * (d & 1) + c_lo + 8 * c8, v);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] *= sc;
-                store_hi(A_c, c0, v);
-                store_hi(A_c, c0 + 4, v + 4);
+                    for (int u = 0; u < 8; ++u) ub[8 * c8 + u] = fmaf(sc, v[u], ub[8 * c8 + u]);
+                }
             }
             tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(bar_cready);
+            mbar_arrive(bar_yfree + 8 * (d & 1));
         }
-        // ---- R4: ubar = Ubar + sum_d mubar_d m_d - (vs k | 2 vs u)  -> operands of the solve
-        BSTAMP();   // 26: d loop done
-        mbar_wait(bar_ubar, 0);
-        tc_fence_after();
-        BSTAMP();   // 27: Ubar ready
+        // ---- R4: ubar += sum_d mubar_d m_d - (vs k | 2 vs u)  -> operands of the solve
+        BSTAMP();   // 2+D: S_d products consumed
         {
-            float4 ua = WHITE ? load_u4(c_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 ub4 = WHITE ? load_u4(c_lo + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
-                float4 na = ua, nb4 = ub4;
-                if (WHITE) { na = load_u4(c0 + 8); nb4 = load_u4(c0 + 12); }
-                float ub[8], r2[8];
-                __syncwarp();
-                tmem_ld8(lane_addr + 256 + c0, ub);
-                __syncwarp();
-                tmem_ld8(lane_addr + 384 + c0, r2);
-                const float uloc[8] = {ua.x, ua.y, ua.z, ua.w, ub4.x, ub4.y, ub4.z, ub4.w};
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int i = c0 + u;
-                    float acc = 0.f;
-                    if (i < M) {
-                        acc = ub[u];
-                        bool done = false;
-                        if constexpr (DOUTP % 4 == 0) {
-                            if (D == DOUTP) {
+            for (int c8 = 0; c8 < 4; ++c8) {
+                if (c8 < nch) {
+                    const int c0 = c_lo + 8 * c8;
+                    float r2[8];
+                    float4 ua[2];
+                    if (!WHITE) {
+                        __syncwarp();
+                        tmem_ld8(lane_addr + 384 + c0, r2);
+                    } else { ua[0] = load_u4(c0); ua[1] = load_u4(c0 + 4); }
+                    float o8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = c0 + u;
+                        float acc = 0.f;
+                        if (i < M) {
+                            acc = ub[8 * c8 + u];
+                            if constexpr (DOUTP % 4 == 0) {
                                 const float4* qr = reinterpret_cast<const float4*>(qmu_s + i * DOUTP);
 #pragma unroll
                                 for (int d4 = 0; d4 < DOUTP / 4; ++d4) {
-                                    float4 qv = qr[d4];
+                                    const float4 qv = qr[d4];
                                     acc = fmaf(mub[4 * d4], qv.x, acc); acc = fmaf(mub[4 * d4 + 1], qv.y, acc);
                                     acc = fmaf(mub[4 * d4 + 2], qv.z, acc); acc = fmaf(mub[4 * d4 + 3], qv.w, acc);
                                 }
-                                done = true;
+                            } else {
+#pragma unroll
+                                for (int d = 0; d < DOUTP; ++d) acc = fmaf(mub[d], qmu_s[i * D + d], acc);
+                            }
+                            if (WHITE) {
+                                const float4 uu = ua[u >> 2];
+                                const float ue = (u & 3) == 0 ? uu.x : (u & 3) == 1 ? uu.y : (u & 3) == 2 ? uu.z : uu.w;
+                                acc -= 2.f * vs * ue;
+                            } else {
+                                float k, kp;
+                                kern_eval_fast(KERN, r2[u], var0, k, kp);
+                                acc -= vs * k;
                             }
                         }
-                        if (!done) {
-#pragma unroll
-                            for (int d = 0; d < DOUTP; ++d) if (d < D) acc = fmaf(mub[d], qmu_s[i * D + d], acc);
-                        }
-                        if (WHITE) acc -= 2.f * vs * uloc[u];
-                        else {
-                            float k, kp;
-                            kern_eval_fast(KERN, r2[u], var0, k, kp);
-                            acc -= vs * k;
-                        }
+                        o8[u] = acc;
                     }
-                    ub[u] = acc;
+                    store_hi_lo(A_c, A_u, c0, o8);
+                    store_hi_lo(A_c, A_u, c0 + 4, o8 + 4);
                 }
-                store_hi_lo(A_c, A_u, c0, ub);
-                store_hi_lo(A_c, A_u, c0 + 4, ub + 4);
-                ua = na; ub4 = nb4;
             }
         }
         tc_fence_before();
         fence_proxy_async();
         if (!WHITE) {
             mbar_arrive(bar_s6);
-            BSTAMP();   // 28: R4 done
+            BSTAMP();   // R4 done
             // ---- R5: t = Linv ubar -> operands of the second triangular product
             mbar_wait(bar_acc6, 0);
             tc_fence_after();
-            BSTAMP();   // 29: G6 done
+            BSTAMP();   // G6 done
             for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
                 float v[8];
                 __syncwarp();
@@ -406,27 +393,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             fence_proxy_async();
         }
         mbar_arrive(bar_s7);
-        BSTAMP();   // 30: R5 done
-        // ---- R6: w -> W (global), kbar, g = 2 kbar dk/dr2 -> g_s ; s2 partial
+        BSTAMP();   // R5 done
+        // ---- R6: w -> W (global), kbar, g = 2 kbar dk/dr2 -> g_s ; s2 partial ; (isotropic) lengthscale partial
+        float4 uq6[8];
+        if (!WHITE) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) uq6[e] = load_u4(c_lo + 4 * e);      // in flight while G7 runs
+        }
         mbar_wait(bar_acc7, 0);
         tc_fence_after();
-        BSTAMP();   // 31: G7 done
-        float s2 = 0.f;
+        BSTAMP();   // G7 done
+        float s2 = 0.f, lsum = 0.f;
         const float inv_var = 1.0f / var0;
-        {
-            float4 ua = !WHITE ? load_u4(c_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 ub4 = !WHITE ? load_u4(c_lo + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
-                float4 na = ua, nb4 = ub4;
-                if (!WHITE) { na = load_u4(c0 + 8); nb4 = load_u4(c0 + 12); }
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+            if (c8 < nch) {
+                const int c0 = c_lo + 8 * c8;
                 float w[8], r2[8];
                 __syncwarp();
                 tmem_ld8(lane_addr + 128 + c0, w);
                 __syncwarp();
                 tmem_ld8(lane_addr + 384 + c0, r2);
                 if (valid) {
-                    if (c0 + 8 <= M && vec4) {
+                    if (c0 + 8 <= M) {
                         float4* dst = reinterpret_cast<float4*>(a.W + (size_t)row * M + c0);
                         dst[0] = make_float4(w[0], w[1], w[2], w[3]);
                         dst[1] = make_float4(w[4], w[5], w[6], w[7]);
@@ -435,82 +424,88 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                         for (int u = 0; u < 8; ++u) if (c0 + u < M) a.W[(size_t)row * M + c0 + u] = w[u];
                     }
                 }
-                const float uloc[8] = {ua.x, ua.y, ua.z, ua.w, ub4.x, ub4.y, ub4.z, ub4.w};
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int i = c0 + u;
                     if (i < M) {
                         float kb_ = w[u];
-                        if (!WHITE) kb_ -= vs * uloc[u];
+                        if (!WHITE) {
+                            const float4 uu = uq6[2 * c8 + (u >> 2)];
+                            const float ue = (u & 3) == 0 ? uu.x : (u & 3) == 1 ? uu.y : (u & 3) == 2 ? uu.z : uu.w;
+                            kb_ -= vs * ue;
+                        }
                         float k, kp;
                         kern_eval_fast(KERN, r2[u], var0, k, kp);
                         s2 = fmaf(kb_ * k, inv_var, s2);
-                        g_s[t * MP + i] = 2.f * kb_ * kp;
+                        const float g = 2.f * kb_ * kp;
+                        lsum = fmaf(g, r2[u], lsum);
+                        g_s[t * MP + i] = g;
                     }
                 }
-                ua = na; ub4 = nb4;
             }
         }
-        BSTAMP();   // 32: R6 done
+        BSTAMP();   // R6 done
         if (qt == 0)
 #pragma unroll
             for (int d = 0; d < DOUTP; ++d) s2 += vb[d];
         s2 = warp_sum(s2);
-        if (lane == 0) red_s[warp] = s2;
-        if (threadIdx.x < 32) red_s[32 + threadIdx.x] = 0.f;     // lengthscale accumulators
-        named_bar_sync(1, TC_ROWTHREADS);
+        lsum = warp_sum(lsum);
+        if (lane == 0) { red_s[warp] = s2; red_s[16 + warp] = lsum; }
+        if (threadIdx.x < 32) red_s[32 + threadIdx.x] = 0.f;     // ARD lengthscale accumulators
+        named_bar_sync(1, TC_ROWTHREADS);                        // g_s, red_s complete; A_u is dead (G7 has completed)
         if (threadIdx.x == 0) {
-            float tot = 0.f;
-            for (int w8 = 0; w8 < TC_ROWTHREADS / 32; ++w8) tot += red_s[w8];
+            float tot = 0.f, ltot = 0.f;
+            for (int w8 = 0; w8 < TC_ROWTHREADS / 32; ++w8) { tot += red_s[w8]; ltot += red_s[16 + w8]; }
             atomicAdd(P.gvar, tot);
+            // isotropic lengthscale: d r2 / d l = -2 r2 / l  ->  d/dl = -(1/l) sum g r2
+            if (!P.ard) atomicAdd(P.gls, -ltot / P.ls[0]);
         }
-        // ---- R7a: xbar (this quarter: q = qt, qt+4, ...)
+        // ---- R7a: xbar (this quarter: q = qt, qt+4, ...):  xbar_q = (1/l_q) sum_i g_i (xs_q - zs_iq) + mean-function term
         if (a.xbar && valid) {
-            constexpr int NQ = (DINP + 3) / 4;          // input dimensions per thread: q = qt + 4 j
-            float accq[NQ], xq[NQ], ilq[NQ];
+            constexpr int NQ = (DINP + 3) / 4;
+            float accq[NQ], xq[NQ];
 #pragma unroll
-            for (int j = 0; j < NQ; ++j) { accq[j] = 0.f; xq[j] = 0.f; ilq[j] = 0.f; }
-#pragma unroll
-            for (int q = 0; q < DINP; ++q)
-                if ((q & 3) == qt) { xq[q >> 2] = x[q]; ilq[q >> 2] = il[q]; }
-            {
+            for (int j = 0; j < NQ; ++j) { accq[j] = 0.f; xq[j] = xs_s[t * Din + min(qt + 4 * j, Din - 1)]; }
 #pragma unroll 4
-                for (int i = 0; i < M; ++i) {
-                    const float g = g_s[t * MP + i];
+            for (int i = 0; i < M; ++i) {
+                const float g = g_s[t * MP + i];
 #pragma unroll
-                    for (int j = 0; j < NQ; ++j) {
-                        const int q = qt + 4 * j;
-                        const float z = q < DINP ? Zs[i * DINP + q] : 0.f;
-                        accq[j] = fmaf(g, xq[j] - z, accq[j]);
-                    }
+                for (int j = 0; j < NQ; ++j) {
+                    const int q = qt + 4 * j;
+                    const float z = q < DINP ? Zs[i * DINP + q] : 0.f;
+                    accq[j] = fmaf(g, xq[j] - z, accq[j]);
                 }
             }
 #pragma unroll
             for (int j = 0; j < NQ; ++j) {
                 const int q = qt + 4 * j;
                 if (q < Din) {
-                    float s = accq[j] * ilq[j] * ilq[j];
+                    float s = accq[j] * (1.0f / P.ls[P.ard ? q : 0]);
                     if (P.mean == DSDGP_MEAN_IDENTITY) {
 #pragma unroll
                         for (int d = 0; d < DOUTP; ++d) if (d == q) s += mub[d];
                     } else if (P.mean == DSDGP_MEAN_LINEAR) {
 #pragma unroll
-                        for (int d = 0; d < DOUTP; ++d) if (d < D) s = fmaf(mub[d], __ldg(&P.meanW[q * D + d]), s);
+                        for (int d = 0; d < DOUTP; ++d) s = fmaf(mub[d], __ldg(&P.meanW[q * D + d]), s);
                     }
                     a.xbar[(size_t)row * Din + q] = s;
                 }
             }
         }
-        BSTAMP();   // 33: R7a done
-        // ---- R7b: Z / lengthscale partials: one (i, q) pair per thread at a time, walking the 128 rows
+        BSTAMP();   // R7a done
+        // ---- R7b: Z / (ARD) lengthscale partials: thread (i, rh) walks rows [32 rh, 32 rh + 32); the four row quarters are
+        // reduced in shared memory so that a tile issues ONE global atomic per (i, q) (round 1: four; the same M*Din addresses
+        // are hit by every tile of the layer, and the contention showed up as the tile's slowest phase)
         {
             const int i = threadIdx.x & 127, rh = threadIdx.x >> 7;      // inducing point, row quarter
             float sa[DINP], sb[DINP];
+#pragma unroll
+            for (int q = 0; q < DINP; ++q) { sa[q] = 0.f; sb[q] = 0.f; }
             if (i < M) {
                 float zi[DINP];
 #pragma unroll
-                for (int q = 0; q < DINP; ++q) { sa[q] = 0.f; sb[q] = 0.f; zi[q] = q < Din ? Zs[i * Din + q] : 0.f; }
-                {
+                for (int q = 0; q < DINP; ++q) zi[q] = Zs[i * Din + q];
+                if (P.ard) {
 #pragma unroll 4
                     for (int r = rh * 32; r < rh * 32 + 32; ++r) {
                         const float g = g_s[r * MP + i];
@@ -527,35 +522,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                             }
                         }
                     }
+                } else {
+                    // sum_r g_r (xs_rq - zs_iq) = sum_r g_r xs_rq - zs_iq sum_r g_r
+                    float gs = 0.f;
+#pragma unroll 4
+                    for (int r = rh * 32; r < rh * 32 + 32; ++r) {
+                        const float g = g_s[r * MP + i];
+                        const float4* xr = reinterpret_cast<const float4*>(xs_s + r * DINP);
+                        gs += g;
+#pragma unroll
+                        for (int q4 = 0; q4 < DINP / 4; ++q4) {
+                            const float4 xv = xr[q4];
+                            sa[4 * q4] = fmaf(g, xv.x, sa[4 * q4]); sa[4 * q4 + 1] = fmaf(g, xv.y, sa[4 * q4 + 1]);
+                            sa[4 * q4 + 2] = fmaf(g, xv.z, sa[4 * q4 + 2]); sa[4 * q4 + 3] = fmaf(g, xv.w, sa[4 * q4 + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < DINP; ++q) sa[q] = fmaf(-gs, zi[q], sa[q]);
                 }
+#pragma unroll
+                for (int q = 0; q < DINP; ++q) zred_s[(rh * M + i) * Din + q] = sa[q];
+            }
+            if (P.ard) {
+                // one shared atomic per warp and input dimension
 #pragma unroll
                 for (int q = 0; q < DINP; ++q) {
-                    if (q < Din) {
-                        const float ilq = il[q];
-                        atomicAdd(&P.gZ[i * Din + q], -sa[q] * ilq * ilq);
-                        sb[q] = -sb[q] * ilq * ilq * ilq;
-                    } else sb[q] = 0.f;
-                }
-                if (!P.ard) {
-#pragma unroll
-                    for (int q = 1; q < DINP; ++q) sb[0] += sb[q];
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < DINP; ++q) sb[q] = 0.f;
-            }
-            // one shared atomic per warp (per input dimension when ARD)
-#pragma unroll
-            for (int q = 0; q < DINP; ++q) {
-                if (q < (P.ard ? Din : 1)) {
-                    float tsum = warp_sum(sb[q]);
+                    const float tsum = warp_sum(sb[q]);
                     if (lane == 0) atomicAdd(&red_s[32 + q], tsum);
                 }
             }
         }
-        BSTAMP();   // 34: R7b done
+        BSTAMP();   // R7b done
         named_bar_sync(1, TC_ROWTHREADS);
-        if (threadIdx.x < (P.ard ? Din : 1)) atomicAdd(&P.gls[threadIdx.x], red_s[32 + threadIdx.x]);
+        for (int e = threadIdx.x; e < M * Din; e += TC_ROWTHREADS) {
+            const float il = 1.0f / P.ls[P.ard ? e % Din : 0];
+            const float v = (zred_s[e] + zred_s[M * Din + e]) + (zred_s[2 * M * Din + e] + zred_s[3 * M * Din + e]);
+            atomicAdd(&P.gZ[e], -v * il);
+        }
+        if (P.ard && threadIdx.x < Din) atomicAdd(&P.gls[threadIdx.x], -red_s[32 + threadIdx.x] / P.ls[threadIdx.x]);
     }
     tc_fence_before();
     __syncthreads();

@@ -234,15 +234,36 @@ void launch_predict_density(int lik, const float* Fmean, const float* Fvar, cons
 #define POS_LOWER 1e-6f
 __device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
 
+// One kernel for the tail of a training step: ELBO scalar -> result, likelihood-variance gradient, Adam.
+//   use_hi_lo == 0 (single GPU): thread 0 finishes the ELBO from the fp64 accumulators (what k_elbo_finish + k_result did);
+//   use_hi_lo == 1 (communicator): k_elbo_finish ran before the all-reduce, the summed (hi, lo) pair sits behind the gradient.
+// A failed Cholesky (acc->status != 0: prepA substituted a unit pivot, the gradients are garbage) leaves parameters, the
+// unconstrained copy and both moments untouched -- TF would have raised before any update (dgp.py:92-98 under minimize).
 __global__ void k_adam(float* __restrict__ params, float* __restrict__ free_, float* __restrict__ m, float* __restrict__ v,
-                       const float* __restrict__ grads, const unsigned char* __restrict__ kinds, size_t n,
-                       const StepArgs* sa) {
+                       float* __restrict__ grads, const unsigned char* __restrict__ kinds, size_t n,
+                       const StepArgs* sa, Accum* acc, size_t off_likvar, int use_hi_lo, int do_adam, double* result) {
+    const int status = acc->status;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double e;
+        if (use_hi_lo) e = (double)grads[n] + (double)grads[n + 1];
+        else {
+            e = acc->lik - sa->kl_weight * acc->kl;
+            acc->elbo = e;
+            const float hi = (float)e;
+            grads[n] = hi; grads[n + 1] = (float)(e - (double)hi);
+        }
+        if (!use_hi_lo && off_likvar != (size_t)-1) grads[off_likvar] = (float)acc->glikvar;      // (k_elbo_finish's job)
+        result[0] = e;
+        result[1] = (double)status;
+    }
+    if (!do_adam || status != 0) return;
     const float lr_t = (float)sa->lr_t, b1 = (float)sa->beta1, b2 = (float)sa->beta2, eps = (float)sa->eps;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         unsigned char k = kinds[i];
         if (k >= 3) continue;
+        const float gi = (!use_hi_lo && i == off_likvar) ? (float)acc->glikvar : grads[i];   // (thread 0 may not have stored it yet)
         float f = free_[i];
-        float g = -grads[i];                       // objective = -ELBO
+        float g = -gi;                              // objective = -ELBO
         if (k == 1) g *= 1.f / (1.f + __expf(-f));  // d softplus
         float mi = b1 * m[i] + (1.f - b1) * g;
         float vi = b2 * v[i] + (1.f - b2) * g * g;
@@ -252,10 +273,12 @@ __global__ void k_adam(float* __restrict__ params, float* __restrict__ free_, fl
     }
 }
 
-void launch_adam(float* params, float* free_, float* m, float* v, const float* grads, const unsigned char* kinds,
-                 const int*, size_t n, const StepArgs* sa, cudaStream_t st, long long* nl) {
-    int nb = (int)min((size_t)592, (n + 255) / 256);
-    k_adam<<<nb, 256, 0, st>>>(params, free_, m, v, grads, kinds, n, sa);
+// do_adam == 0: only the ELBO / result / likelihood-variance-gradient part (ELBO and gradient calls)
+void launch_tail(float* params, float* free_, float* m, float* v, float* grads, const unsigned char* kinds, size_t n,
+                 const StepArgs* sa, Accum* acc, size_t off_likvar, int use_hi_lo, int do_adam, double* result,
+                 cudaStream_t st, long long* nl) {
+    int nb = do_adam ? (int)min((size_t)592, (n + 255) / 256) : 1;
+    k_adam<<<nb, 256, 0, st>>>(params, free_, m, v, grads, kinds, n, sa, acc, off_likvar, use_hi_lo, do_adam, result);
     *nl += 1;
 }
 

@@ -139,7 +139,7 @@ __global__ void k_ng_store(LayerDev P, const double* __restrict__ Lnew, float* q
 
 size_t natgrad_ws_doubles(int M, int D) { return (size_t)3 * D * M * M + (size_t)D * M; }
 
-// ws: natgrad_ws_doubles(M, D) doubles.  q_mu / q_sqrt: the layer's slots of the flat parameter buffer (written in place).
+// ws: natgrad_ws_doubles(M, D) doubles.  q_mu / q_sqrt: staging buffers (M x D, D x M x M) committed by launch_natgrad_commit.
 void launch_natgrad_layer(const LayerDev& P, double gamma, double* ws, int* status, float* q_mu, float* q_sqrt,
                           cudaStream_t st, long long* nl) {
     const int M = P.M, D = P.Dout;
@@ -166,6 +166,17 @@ void launch_natgrad_layer(const LayerDev& P, double gamma, double* ws, int* stat
     k_ng_cholinv<<<D, 1024, smb, st>>>(W2, W1, M, use_smem, status);      // W2 = chol(S')
     k_ng_store<<<gmm, 256, 0, st>>>(P, W2, q_sqrt, status);
     *nl += 7;
+}
+
+// dst[0..n) = src[0..n) unless *status != 0: commits the staged (q_mu, q_sqrt) of a natural-gradient step only if EVERY
+// factorisation of EVERY updated layer succeeded (api.cu: dsdgp_natgrad_step), so a failing step changes nothing.
+__global__ void k_ng_commit(float* __restrict__ dst, const float* __restrict__ src, size_t n, const int* status) {
+    if (*status) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+void launch_natgrad_commit(float* dst, const float* src, size_t n, const int* status, cudaStream_t st, long long* nl) {
+    k_ng_commit<<<(unsigned)min((size_t)592, (n + 255) / 256), 256, 0, st>>>(dst, src, n, status);
+    *nl += 1;
 }
 
 cudaError_t natgrad_init() {

@@ -164,12 +164,11 @@ class Context:
         return self._get(self.lib.dsdgp_get_grad, layer, field, shape)
 
     def propagate(self, X, S, zs=None, seed=0, want=(True, True, True), flags=0):
-        X = f32(X)
+        X, _ = self._xy(X)
         N = X.shape[0]
         L = self.L
         douts = [self.desc.layers[l].D_out for l in range(L)]
-        zs32 = None if zs is None else [None if z is None else f32(z) for z in zs]
-        zarr, _ = _ptr_array(zs32, L)
+        zarr, keep = self._zs(zs, S, N)
         outs = []
         arrs = []
         for w in want:
@@ -184,10 +183,10 @@ class Context:
 
     def propagate_full_cov(self, X, S, zs=None, seed=0):
         """full_cov=True propagate: Fs, Fmeans lists of (S,N,D_l); Fvars list of (S,N,N,D_l)."""
-        X = f32(X)
+        X, _ = self._xy(X)
         N, L = X.shape[0], self.L
         douts = [self.desc.layers[l].D_out for l in range(L)]
-        zarr, keep = self._zs(zs)
+        zarr, keep = self._zs(zs, S, N)
         Fs = [np.empty((S, N, d), dtype=np.float32) for d in douts]
         Fm = [np.empty((S, N, d), dtype=np.float32) for d in douts]
         Fv = [np.empty((S, N, N, d), dtype=np.float32) for d in douts]
@@ -195,26 +194,60 @@ class Context:
         check(self.lib.dsdgp_propagate_full_cov(self.h, _ptr(X), N, S, zarr, seed, a0, a1, a2, 0))
         return Fs, Fm, Fv
 
-    def _zs(self, zs):
-        zs32 = None if zs is None else [None if z is None else f32(z) for z in zs]
+    def _zs(self, zs, S=None, N=None):
+        """Per-layer draws -> (void*[L], keep-alive list).  Host arrays are broadcast to (S, N, D_out_l) like the reference's
+        `mean + z * sqrt(var)` (utils.py:41; DGP_Quad passes (S,1,D) nodes, dgp.py:147-148) or rejected: the C side copies
+        exactly S*N*D_out_l floats per layer, so a short buffer must never reach it.  ints are device pointers."""
+        if zs is None:
+            return None, None
+        if len(zs) > self.L:
+            raise ValueError(f"zs has {len(zs)} entries for {self.L} layers")
+        zs32 = []
+        for l, z in enumerate(zs):
+            if z is None or isinstance(z, int):
+                zs32.append(z)
+                continue
+            z = np.asarray(z)
+            if S is not None:
+                want = (S, N, self.desc.layers[l].D_out)
+                if z.shape != want:
+                    try:
+                        z = np.broadcast_to(z, want)
+                    except ValueError:
+                        raise ValueError(f"zs[{l}] has shape {z.shape}, not broadcastable to (S, N, D_out) = {want}") from None
+            zs32.append(f32(z))
         zarr, _ = _ptr_array(zs32, self.L)
         return zarr, zs32
 
+    def _xy(self, X, Y=None):
+        """float32 C-contiguous copies of host X (N, D_in) and Y (N, D_y) with the shapes the C side will read."""
+        X = f32(X)
+        if X.ndim != 2 or X.shape[1] != self.desc.layers[0].D_in:
+            raise ValueError(f"X has shape {X.shape}, expected (N, {self.desc.layers[0].D_in})")
+        if Y is None:
+            return X, None
+        Y = f32(Y)
+        if Y.ndim == 1:
+            Y = Y.reshape(-1, 1)
+        if Y.shape != (X.shape[0], self.desc.D_y):
+            raise ValueError(f"Y has shape {Y.shape}, expected ({X.shape[0]}, {self.desc.D_y})")
+        return X, Y
+
     def predict_y(self, X, S, zs=None, seed=0):
         """likelihood.predict_mean_and_var of the last layer, per sample: two (S,N,D_last) arrays."""
-        X = f32(X)
+        X, _ = self._xy(X)
         N, D = X.shape[0], self.desc.layers[self.L - 1].D_out
-        zarr, keep = self._zs(zs)
+        zarr, keep = self._zs(zs, S, N)
         mean, var = np.empty((S, N, D), dtype=np.float32), np.empty((S, N, D), dtype=np.float32)
         check(self.lib.dsdgp_predict_y(self.h, _ptr(X), N, S, zarr, seed, _ptr(mean), _ptr(var), 0))
         return mean, var
 
     def predict_density(self, X, Y, S, zs=None, seed=0):
         """logsumexp_S(likelihood.predict_density - log S): (N,D_y) Gaussian, (N,1) MultiClass."""
-        X, Y = f32(X), f32(Y)
+        X, Y = self._xy(X, Y)
         N = X.shape[0]
         Do = self.desc.D_y if self.desc.likelihood == 0 else 1
-        zarr, keep = self._zs(zs)
+        zarr, keep = self._zs(zs, S, N)
         out = np.empty((N, Do), dtype=np.float32)
         check(self.lib.dsdgp_predict_density(self.h, _ptr(X), _ptr(Y), N, S, zarr, seed, _ptr(out), 0))
         return out
@@ -222,9 +255,8 @@ class Context:
     def _elbo(self, fn, X, Y, S, num_data, zs, seed, flags):
         if isinstance(X, int):
             raise TypeError("device-pointer calls need explicit N: use elbo_dev")
-        X, Y = f32(X), f32(Y)
-        zs32 = None if zs is None else [None if z is None else f32(z) for z in zs]
-        zarr, _ = _ptr_array(zs32, self.L)
+        X, Y = self._xy(X, Y)
+        zarr, keep = self._zs(zs, S, X.shape[0])
         e = C.c_double()
         check(fn(self.h, _ptr(X), _ptr(Y), X.shape[0], S, float(num_data), zarr, seed, flags, C.byref(e)))
         return e.value
@@ -241,8 +273,11 @@ class Context:
     def train_step(self, X, Y, N, S, num_data, seed, flags=0, want_elbo=True, zs=None):
         """X, Y: float32 host arrays (pinned for the e2e path) or int device pointers (with FLAG_DEVICE_PTRS)."""
         e = C.c_double()
-        zs32 = None if zs is None else [None if z is None else (z if isinstance(z, int) else f32(z)) for z in zs]
-        zarr, _ = _ptr_array(zs32, self.L)
+        if not isinstance(X, int):
+            X, Y = self._xy(X, Y)
+            if X.shape[0] != N:
+                raise ValueError(f"X has {X.shape[0]} rows, N={N}")
+        zarr, keep = self._zs(zs, S, N)
         check(self.lib.dsdgp_train_step(self.h, _ptr(X), _ptr(Y), N, S, float(num_data), zarr, seed, flags,
                                         C.byref(e) if want_elbo else None))
         return e.value if want_elbo else None
@@ -261,8 +296,11 @@ class Context:
     def natgrad_step(self, X, Y, N, S, num_data, seed, layers, gamma, flags=0, zs=None):
         """ELBO + gradient pass, then the natural-gradient update of (q_mu, q_sqrt) of `layers`; returns the ELBO."""
         e = C.c_double()
-        zs32 = None if zs is None else [None if z is None else (z if isinstance(z, int) else f32(z)) for z in zs]
-        zarr, _ = _ptr_array(zs32, self.L)
+        if not isinstance(X, int):
+            X, Y = self._xy(X, Y)
+            if X.shape[0] != N:
+                raise ValueError(f"X has {X.shape[0]} rows, N={N}")
+        zarr, keep = self._zs(zs, S, N)
         ids = (C.c_int * len(layers))(*[int(l) for l in layers])
         check(self.lib.dsdgp_natgrad_step(self.h, _ptr(X), _ptr(Y), N, S, float(num_data), zarr, seed, flags, ids,
                                           len(layers), float(gamma), C.byref(e)))

@@ -193,7 +193,18 @@ class DGP_Base(Parameterized):
 
     @staticmethod
     def _cut(zs, s0, s1, n0, n1):
-        return None if zs is None else [None if z is None else np.asarray(z)[s0:s1, n0:n1] for z in zs]
+        """The [s0:s1, n0:n1] block of every layer's draws; axes of length 1 broadcast (DGP_Quad's (S,1,D) nodes)."""
+        if zs is None:
+            return None
+        out = []
+        for z in zs:
+            if z is not None:
+                z = np.asarray(z)
+                if z.ndim != 3:
+                    raise ValueError(f"zs entries must be (S, N, D) arrays, got shape {z.shape}")
+                z = z[(slice(None) if z.shape[0] == 1 else slice(s0, s1)), (slice(None) if z.shape[1] == 1 else slice(n0, n1))]
+            out.append(z)
+        return out
 
     def propagate(self, X, full_cov=False, S=1, zs=None):
         """dgp.py:61-76 -> (Fs, Fmeans, Fvars), lists of (S,N,D_l) float64 arrays ((S,N,N,D_l) variances with full_cov)."""
@@ -308,9 +319,13 @@ class DGP_Base(Parameterized):
             X, Y = self._minibatch()
         ctx = self._ensure_ctx(X.shape[0], self.num_samples)
         zs = self._default_zs(X.shape[0]) if zs is None else zs
-        e = ctx.train_step(_lib.f32(X), _lib.f32(Y), X.shape[0], self.num_samples, self.num_data, self._next_seed(),
-                           zs=zs)
-        self._device_newer = True
+        try:
+            e = ctx.train_step(_lib.f32(X), _lib.f32(Y), X.shape[0], self.num_samples, self.num_data, self._next_seed(),
+                               zs=zs)
+        finally:
+            # (a step that fails with NOT_PD leaves the device parameters untouched -- csrc/lik_adam.cu k_adam -- but the
+            # host copy is re-read either way)
+            self._device_newer = True
         return e
 
     def natgrad_step(self, var_list=None, gamma=1.0, X=None, Y=None, zs=None):
@@ -322,9 +337,11 @@ class DGP_Base(Parameterized):
             X, Y = self._minibatch()
         ctx = self._ensure_ctx(X.shape[0], self.num_samples)
         zs = self._default_zs(X.shape[0]) if zs is None else zs
-        e = ctx.natgrad_step(_lib.f32(X), _lib.f32(Y), X.shape[0], self.num_samples, self.num_data, self._next_seed(),
-                             ids, gamma, zs=zs)
-        self._device_newer = True
+        try:
+            e = ctx.natgrad_step(_lib.f32(X), _lib.f32(Y), X.shape[0], self.num_samples, self.num_data, self._next_seed(),
+                                 ids, gamma, zs=zs)
+        finally:
+            self._device_newer = True
         return e
 
     def _natgrad_layers(self, var_list):
