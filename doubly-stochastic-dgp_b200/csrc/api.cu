@@ -519,6 +519,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             b.mubar = c->mubar[l]; b.vbar = c->vbar[l]; b.W = c->Wbuf[l];
             b.xbar = (l == 0) ? nullptr : c->xbar[l];
             b.dbg = (c->dbg_layer == 100 + l) ? c->dbg_buf : nullptr;
+            b.dbg_rr = (c->dbg_layer == 200 + l) ? c->dbg_buf : nullptr;
             PROF_BEGIN(6 + 3 * l);
             if (c->path == 1 && tc_bwd_supported(c->ls.l[l])) launch_bwd_rows_tc(c->ls.l[l], b, st, nl);
             else launch_bwd_rows(c->ls.l[l], b, c->num_sms, st, nl);
@@ -1061,6 +1062,8 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     }
     else if (n == "dbg_layer") {
         c->dbg_layer = (int)value;
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemset(c->dbg_buf, 0, 64 * sizeof(long long)));
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     } else if (n == "dbg_prep") {

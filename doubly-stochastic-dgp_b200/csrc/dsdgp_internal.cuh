@@ -206,6 +206,7 @@ struct BwdArgs {
     float jitter;
     const StepArgs* sa;
     long long* dbg;       // optional clock64() stamps of CTA 0 (diagnostics), else NULL
+    long long* dbg_rr;    // the same for the row-reduction kernel
 };
 
 void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* sa, cudaStream_t st, cudaStream_t st_kl,

@@ -22,8 +22,8 @@
 #define TC_ROWTHREADS 512
 #define TC_WARP_TMA 16
 #define TC_WARP_MMA 17
-#define BW_NR 4                  // dedicated ring sub-slots (16 KB each)
-#define BW_NSA (BW_NR + 4)       // sub-slots while A_c is free (S_d phase)
+#define BW_NR_MAX 5              // dedicated ring sub-slots (one full band = 128 * NPAD bytes each), as many as fit
+#define BW_NS_MAX (BW_NR_MAX + 4) // + the sub-slots carved out of A_c while it is free (S_d phase)
 
 namespace {
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
@@ -37,18 +37,27 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
 
 // shared-memory plan (bytes from the 1024-aligned base)
 struct BwdSmem {
-    uint32_t A_u, A_c, ring, bars, Zs, qmu, mv, xs, red, total;
+    uint32_t A_u, A_c, ring, bars, Zs, ZsT, qmu, mv, xs, red, total;
+    int nr, nsa;           // ring sub-slots: dedicated, and in total while A_c is free
 };
 __host__ __device__ inline BwdSmem bwd_smem_plan(int M, int Din, int D) {
     BwdSmem s;
+    const uint32_t band = 128u * (uint32_t)tcp::npad_of(M);
+    const uint32_t misc = 512 + 4 * ((M * Din + 3) & ~3) + 4 * Din * ((M + 3) & ~3) + 4 * ((M * D + 3) & ~3) +
+                          4 * 128 * 2 * D + 4 * 128 * Din + 4 * 96;
+    // as many dedicated sub-slots as fit next to the two 64 KB operand buffers (at least 2)
+    int nr = (int)((227u * 1024u - 1024u - 131072u - misc) / band);
+    nr = nr > BW_NR_MAX ? BW_NR_MAX : nr < 2 ? 2 : nr;
+    s.nr = nr; s.nsa = nr + (int)(65536u / band);
     s.A_u = 0; s.A_c = 65536; s.ring = 131072;
-    s.bars = s.ring + BW_NR * TC_CHUNK_BYTES;
+    s.bars = s.ring + (uint32_t)nr * band;
     s.Zs = s.bars + 512;
-    s.qmu = s.Zs + 4 * ((M * Din + 3) & ~3);
+    s.ZsT = s.Zs + 4 * ((M * Din + 3) & ~3);
+    s.qmu = s.ZsT + 4 * Din * ((M + 3) & ~3);
     s.mv = s.qmu + 4 * ((M * D + 3) & ~3);
     s.xs = s.mv + 4 * 128 * 2 * D;
     s.red = s.xs + 4 * 128 * Din;
-    s.total = s.red + 4 * 64;
+    s.total = s.red + 4 * 96;      // [0,32) warp partials, [32,64) ARD lengthscale sums, [64,96) 1/lengthscale
     return s;
 }
 
@@ -64,25 +73,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     constexpr int Din = DINP, D = DOUTP;
     const BwdSmem sp = bwd_smem_plan(M, Din, D);
     const uint32_t A_u = sbase + sp.A_u, A_c = sbase + sp.A_c, ring = sbase + sp.ring, bars = sbase + sp.bars;
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * BW_NSA;                 // [BW_NSA] each
-    const uint32_t bar_au = bars + 16 * BW_NSA, bar_yfull = bar_au + 8 /*[2]*/, bar_yfree = bar_au + 24 /*[2]*/;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * BW_NS_MAX;              // [BW_NS_MAX] each
+    const int BW_NR = sp.nr, BW_NSA = sp.nsa;
+    const uint32_t bar_au = bars + 16 * BW_NS_MAX, bar_yfull = bar_au + 8 /*[2]*/, bar_yfree = bar_au + 24 /*[2]*/;
     const uint32_t bar_s6 = bar_au + 40, bar_acc6 = bar_au + 48, bar_s7 = bar_au + 56, bar_acc7 = bar_au + 64;
     const uint32_t tmem_slot = bar_au + 72;
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + sp.bars + 16 * BW_NSA + 72);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + sp.bars + 16 * BW_NS_MAX + 72);
     float* Zs = reinterpret_cast<float*>(sgen + sp.Zs);         // [M][Din], scaled by 1/lengthscale
+    float* ZsT = reinterpret_cast<float*>(sgen + sp.ZsT);       // [Din][M4] the same, transposed (M4 = M rounded up to 4)
     float* qmu_s = reinterpret_cast<float*>(sgen + sp.qmu);
     float* mv_s = reinterpret_cast<float*>(sgen + sp.mv);       // [128][2D]: mubar (D) | vbar (D)
     float* xs_s = reinterpret_cast<float*>(sgen + sp.xs);       // [128][Din], scaled by 1/lengthscale
-    float* red_s = reinterpret_cast<float*>(sgen + sp.red);     // [64]
+    float* red_s = reinterpret_cast<float*>(sgen + sp.red);     // [96]
+    float* il_s = red_s + 64;                                   // [Din] 1/lengthscale
     float* g_s = reinterpret_cast<float*>(sgen + sp.A_c);       // [128][MP] once A_c is dead
     float* zred_s = reinterpret_cast<float*>(sgen + sp.A_u);    // [4][M][Din] once A_u is dead
-    const int MP = M | 1;                                        // odd row stride: conflict-free column walks
+    // row stride of g_s: a multiple of 4 (16-byte row-wise accesses) with MP/4 odd, so that eight consecutive rows start in
+    // eight different 16-byte bank groups; column walks (consecutive i) are conflict-free for any stride
+    const int MP = ((M >> 2) & 1) ? M : M + 4;
 
     const int nkb = (M + 31) / 32, NPAD = (M + 15) & ~15;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * TC_ROWS, R = a.R;
     const uint32_t band_full = 128u * (uint32_t)NPAD;           // one k-block of a square (S_d) operand
-    auto slot_addr = [&](int s) { return s < BW_NR ? ring + (uint32_t)s * TC_CHUNK_BYTES : A_c + (uint32_t)(s - BW_NR) * TC_CHUNK_BYTES; };
+    auto slot_addr = [&](int s) { return s < BW_NR ? ring + (uint32_t)s * band_full : A_c + (uint32_t)(s - BW_NR) * band_full; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < BW_NSA; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -93,7 +107,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         fence_mbar_init();
     }
     if (warp == TC_WARP_TMA) tmem_alloc(tmem_slot, 512);
-    for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) Zs[e] = P.Z[e] * (1.0f / P.ls[P.ard ? e % Din : 0]);
+    const int M4 = (M + 3) & ~3;
+    for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) {
+        const float zv = P.Z[e] * (1.0f / P.ls[P.ard ? e % Din : 0]);
+        Zs[e] = zv;
+        ZsT[(e % Din) * M4 + e / Din] = zv;
+    }
+    if (threadIdx.x < Din) il_s[threadIdx.x] = 1.0f / P.ls[P.ard ? threadIdx.x : 0];
     for (int e = threadIdx.x; e < M * D; e += TC_THREADS) qmu_s[e] = P.q_mu[e];
     tc_fence_before();
     __syncthreads();
@@ -114,9 +134,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                 if (++s == nslots) s = 0;
             };
             const char* ssrc = wsrc + tcp::s_region_offset(M, D);
+            // Only the first two bands are requested before the row threads have fetched the tile's inputs: every CTA of a wave
+            // starts at the same time, and a full ring of weight requests ahead of the (smaller, but latency-critical) u / x /
+            // mubar loads made those wait ~8k cycles for L2 bandwidth (profiles/r2_bwd_tile_stamps.md)
+            int nband = 0;
             for (int d = 0; d < D; ++d)
-                for (int kb = 0; kb < nkb; ++kb)
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (nband++ == 2) mbar_wait(bar_au, 0);
                     load(ssrc + (size_t)d * tcp::sfull_bytes(M) + (size_t)kb * band_full, band_full, BW_NSA);
+                }
             s = 0;
             const uint32_t slotb = tcp::slot_bytes(M);
             auto load_block = [&](int blk, int pat) {
@@ -219,59 +245,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
 #define BSTAMP() do { if (dbg) a.dbg[dbi++] = clock64(); } while (0)
         BSTAMP();   // 0
 
-        // ---- R0: x tile (scaled by 1/lengthscale), mubar / vbar (this quarter: d = qt, qt+4, ...)
-        float xs[DINP];
-#pragma unroll
-        for (int q = 0; q < DINP; ++q) {
-            xs[q] = (valid ? a.Xin[(size_t)row * Din + q] : 0.f) * (1.0f / P.ls[P.ard ? q : 0]);
-            if (qt == 0) xs_s[t * Din + q] = xs[q];
-        }
-#pragma unroll 1
-        for (int d = qt; d < D; d += 4) {
-            float m = 0.f, v = 0.f;
-            if (valid) {
-                if (a.fbar) {
-                    // z: the draws of the forward pass (injected, or the Philox draws it stored)
-                    const float sd = sqrtf(fmaxf(a.Fvar[(size_t)row * D + d] + jit, 1e-30f));
-                    float sz = 0.f;
-#pragma unroll 1
-                    for (int ss = 0; ss < a.S_rep; ++ss) {
-                        const size_t o = ((size_t)ss * a.N * (a.S_rep > 1) + row) * D + d;
-                        const float fb = a.fbar[o];
-                        m += fb; sz = fmaf(fb, a.z[o], sz);
-                    }
-                    v = sz / (2.f * sd);
-                    a.mubar[(size_t)row * D + d] = m;
-                    a.vbar[(size_t)row * D + d] = v;
-                } else {
-                    m = a.mubar[(size_t)row * D + d];
-                    v = a.vbar[(size_t)row * D + d];
-                }
-            }
-            mv_s[t * 2 * D + d] = m;
-            mv_s[t * 2 * D + D + d] = v;
-        }
-        // ---- R1: u (this quarter's columns) -> A_u as the operand of the S_d products; all loads issued up front
+        // ---- R0 / R1: every global load of the tile's inputs is issued before the first dependent instruction: a dependent
+        // round trip costs ~2k cycles here (measured: x 2.1k, mubar/vbar 1.9k per d, u 2-5k when they were serialised)
         auto load_u4 = [&](int c0) -> float4 {       // M % 4 == 0 (tc_bwd_supported)
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid && c0 < c_hi && c0 + 4 <= M) v = *reinterpret_cast<const float4*>(a.U + (size_t)row * M + c0);
             return v;
         };
-        {
-            float4 uq[8];
+        float4 uq[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) uq[e] = load_u4(c_lo + 4 * e);
+        for (int e = 0; e < 8; ++e) uq[e] = load_u4(c_lo + 4 * e);
+        float xs[DINP];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                if (c_lo + 4 * e < c_hi) {
-                    const float v[4] = {uq[e].x, uq[e].y, uq[e].z, uq[e].w};
-                    store_hi(A_u, c_lo + 4 * e, v);
+        for (int q = 0; q < DINP; ++q) xs[q] = valid ? a.Xin[(size_t)row * Din + q] : 0.f;
+        // mubar / vbar (this quarter: d = qt, qt+4, ...)
+        constexpr int NDQ = (DOUTP + 3) / 4;
+        float fv[NDQ], fm[NDQ], fz[NDQ];
+        const bool single = a.S_rep == 1;
+#pragma unroll
+        for (int j = 0; j < NDQ; ++j) {
+            const int d = qt + 4 * j;
+            fv[j] = 0.f; fm[j] = 0.f; fz[j] = 0.f;
+            if (valid && d < D) {
+                const size_t o = (size_t)row * D + d;
+                if (a.fbar) {
+                    fv[j] = a.Fvar[o];
+                    if (single) { fm[j] = a.fbar[o]; fz[j] = a.z[o]; }
+                } else { fm[j] = a.mubar[o]; fv[j] = a.vbar[o]; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < DINP; ++q) {
+            xs[q] *= il_s[q];
+            if (qt == 0) xs_s[t * Din + q] = xs[q];
+        }
+        BSTAMP();   // 1: inputs loaded
+#pragma unroll
+        for (int j = 0; j < NDQ; ++j) {
+            const int d = qt + 4 * j;
+            if (d < D) {
+                float m = 0.f, v = 0.f;
+                if (valid) {
+                    if (a.fbar) {
+                        // z: the draws of the forward pass (injected, or the Philox draws it stored)
+                        const float sd = sqrtf(fmaxf(fv[j] + jit, 1e-30f));
+                        float sz;
+                        if (single) { m = fm[j]; sz = fm[j] * fz[j]; }
+                        else {
+                            sz = 0.f;
+#pragma unroll 1
+                            for (int ss = 0; ss < a.S_rep; ++ss) {      // layer-1 dedup: the row's S samples
+                                const size_t o = ((size_t)ss * a.N + row) * D + d;
+                                const float fb = a.fbar[o];
+                                m += fb; sz = fmaf(fb, a.z[o], sz);
+                            }
+                        }
+                        v = sz / (2.f * sd);
+                        a.mubar[(size_t)row * D + d] = m;
+                        a.vbar[(size_t)row * D + d] = v;
+                    } else { m = fm[j]; v = fv[j]; }
                 }
+                mv_s[t * 2 * D + d] = m;
+                mv_s[t * 2 * D + D + d] = v;
+            }
+        }
+        BSTAMP();   // 2: mubar / vbar done
+        // ---- R1: u (this quarter's columns) -> A_u as the operand of the S_d products
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (c_lo + 4 * e < c_hi) {
+                const float v[4] = {uq[e].x, uq[e].y, uq[e].z, uq[e].w};
+                store_hi(A_u, c_lo + 4 * e, v);
             }
         }
         fence_proxy_async();
         mbar_arrive(bar_au);
-        BSTAMP();   // 1: R0+R1 done
+        BSTAMP();   // 3: R0+R1 done
         named_bar_sync(1, TC_ROWTHREADS);          // mv_s / xs_s visible
         float mub[DOUTP], vb[DOUTP], vs = 0.f;
 #pragma unroll
@@ -439,9 +488,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                         s2 = fmaf(kb_ * k, inv_var, s2);
                         const float g = 2.f * kb_ * kp;
                         lsum = fmaf(g, r2[u], lsum);
-                        g_s[t * MP + i] = g;
-                    }
+                        w[u] = g;
+                    } else w[u] = 0.f;
                 }
+                // (M % 4 == 0: whole float4s are either inside the row or outside it)
+                if (c0 + 4 <= M) *reinterpret_cast<float4*>(g_s + t * MP + c0) = make_float4(w[0], w[1], w[2], w[3]);
+                if (c0 + 8 <= M) *reinterpret_cast<float4*>(g_s + t * MP + c0 + 4) = make_float4(w[4], w[5], w[6], w[7]);
             }
         }
         BSTAMP();   // R6 done
@@ -458,7 +510,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             for (int w8 = 0; w8 < TC_ROWTHREADS / 32; ++w8) { tot += red_s[w8]; ltot += red_s[16 + w8]; }
             atomicAdd(P.gvar, tot);
             // isotropic lengthscale: d r2 / d l = -2 r2 / l  ->  d/dl = -(1/l) sum g r2
-            if (!P.ard) atomicAdd(P.gls, -ltot / P.ls[0]);
+            if (!P.ard) atomicAdd(P.gls, -ltot * il_s[0]);
         }
         // ---- R7a: xbar (this quarter: q = qt, qt+4, ...):  xbar_q = (1/l_q) sum_i g_i (xs_q - zs_iq) + mean-function term
         if (a.xbar && valid) {
@@ -466,21 +518,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             float accq[NQ], xq[NQ];
 #pragma unroll
             for (int j = 0; j < NQ; ++j) { accq[j] = 0.f; xq[j] = xs_s[t * Din + min(qt + 4 * j, Din - 1)]; }
-#pragma unroll 4
-            for (int i = 0; i < M; ++i) {
-                const float g = g_s[t * MP + i];
+#pragma unroll 2
+            for (int i4 = 0; i4 < M; i4 += 4) {
+                const float4 g4 = *reinterpret_cast<const float4*>(g_s + t * MP + i4);
 #pragma unroll
                 for (int j = 0; j < NQ; ++j) {
-                    const int q = qt + 4 * j;
-                    const float z = q < DINP ? Zs[i * DINP + q] : 0.f;
-                    accq[j] = fmaf(g, xq[j] - z, accq[j]);
+                    const int q = min(qt + 4 * j, DINP - 1);
+                    const float4 z4 = *reinterpret_cast<const float4*>(ZsT + q * M4 + i4);
+                    accq[j] = fmaf(g4.x, xq[j] - z4.x, accq[j]); accq[j] = fmaf(g4.y, xq[j] - z4.y, accq[j]);
+                    accq[j] = fmaf(g4.z, xq[j] - z4.z, accq[j]); accq[j] = fmaf(g4.w, xq[j] - z4.w, accq[j]);
                 }
             }
 #pragma unroll
             for (int j = 0; j < NQ; ++j) {
                 const int q = qt + 4 * j;
                 if (q < Din) {
-                    float s = accq[j] * (1.0f / P.ls[P.ard ? q : 0]);
+                    float s = accq[j] * il_s[q];
                     if (P.mean == DSDGP_MEAN_IDENTITY) {
 #pragma unroll
                         for (int d = 0; d < DOUTP; ++d) if (d == q) s += mub[d];
@@ -555,11 +608,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         BSTAMP();   // R7b done
         named_bar_sync(1, TC_ROWTHREADS);
         for (int e = threadIdx.x; e < M * Din; e += TC_ROWTHREADS) {
-            const float il = 1.0f / P.ls[P.ard ? e % Din : 0];
+            const float il = il_s[e % Din];
             const float v = (zred_s[e] + zred_s[M * Din + e]) + (zred_s[2 * M * Din + e] + zred_s[3 * M * Din + e]);
             atomicAdd(&P.gZ[e], -v * il);
         }
-        if (P.ard && threadIdx.x < Din) atomicAdd(&P.gls[threadIdx.x], -red_s[32 + threadIdx.x] / P.ls[threadIdx.x]);
+        if (P.ard && threadIdx.x < Din) atomicAdd(&P.gls[threadIdx.x], -red_s[32 + threadIdx.x] * il_s[threadIdx.x]);
     }
     tc_fence_before();
     __syncthreads();

@@ -40,7 +40,7 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mnmajor(uint32_t smem_addr, 
 __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, const float* __restrict__ U,
                                                                  const float* __restrict__ W, const float* __restrict__ mubar,
                                                                  const float* __restrict__ vbar, int R, int ngroups_d,
-                                                                 int nsplit_p, int nsplit_g) {
+                                                                 int nsplit_p, int nsplit_g, long long* dbgp) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw_r[];
     const uint32_t sbase = (smem_u32(smem_raw_r) + 1023u) & ~1023u;
@@ -133,6 +133,10 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
         const int f_lo = 8 * (qt * q8 + min(qt, r8)), f_hi = f_lo + 8 * (q8 + (qt < r8 ? 1 : 0));
         const float* Asrc = is_g ? W : U;
         int bcount = 0;
+        const bool dbg = dbgp && blockIdx.x == 0 && threadIdx.x == 0;
+        int dbi = 0;
+#define RSTAMP() do { if (dbg && dbi < 38) dbgp[dbi++] = clock64(); } while (0)
+        RSTAMP();
         for (int it = 0; it < n_it; ++it) {
             const int tit = is_g ? (it >> 1) : it, sub = is_g ? (it & 1) : 0;
             const int tile = split + tit * gsz;
@@ -177,8 +181,10 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
 #pragma unroll
                 for (int b = 0; b < 3; ++b) scv[b] = (valid && b < nd) ? vbar[(size_t)row * D + d0 + b] : 0.f;
             }
+            RSTAMP();     // loads issued / landed
             // ---- A operand
             if (it > 0) mbar_wait(bar_afree, (it - 1) & 1);
+            RSTAMP();     // A free
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int c0 = c_lo + 4 * c;
@@ -210,6 +216,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
             }
             fence_proxy_async();
             mbar_arrive(bar_aready);
+            RSTAMP();     // A stored
             // ---- B operands
             for (int b = 0; b < nbi; ++b, ++bcount) {
                 const int buf = bcount & 1;
@@ -248,9 +255,11 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                 mbar_arrive(bar_bready + 8 * buf);
             }
         }
-        // ---- flush: TMEM lane i = output row i; this half's columns
+        RSTAMP();         // all operands stored
+        // ---- flush: TMEM lane i = output row i; this quarter's columns
         mbar_wait(bar_done, 0);
         tc_fence_after();
+        RSTAMP();         // MMAs done
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const int i = t;
         for (int b = 0; b < nb; ++b) {
@@ -279,6 +288,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
             }
         }
     }
+    if (dbgp && blockIdx.x == 0 && threadIdx.x == 0) dbgp[39] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == RR_WARP_MMA) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
@@ -297,6 +307,6 @@ void launch_bwd_rowred_tc(const LayerDev& P, const BwdArgs& a, int num_sms, cuda
     int nsplit_p = max(1, min(ntiles, (int)(num_sms / (ngroups_d + 1.5))));
     int nsplit_g = max(1, min(ntiles, num_sms - ngroups_d * nsplit_p));
     k_layer_rowred_tc<<<ngroups_d * nsplit_p + nsplit_g, RR_THREADS, 3 * RR_TILE_BYTES + 1024 + 256, st>>>(
-        P, a.U, a.W, a.mubar, a.vbar, a.R, ngroups_d, nsplit_p, nsplit_g);
+        P, a.U, a.W, a.mubar, a.vbar, a.R, ngroups_d, nsplit_p, nsplit_g, a.dbg_rr);
     *nl += 1;
 }
