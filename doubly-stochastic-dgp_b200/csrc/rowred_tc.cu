@@ -12,6 +12,7 @@
 // Math: tests/algo_mirror.py::layer_bwdB.
 #include "dsdgp_internal.cuh"
 #include "tc_common.cuh"
+#include <type_traits>
 
 #define RR_THREADS 544          // 16 row warps (four threads per row) + 1 MMA warp
 #define RR_ROWTHREADS 512
@@ -116,102 +117,126 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
         if (elect_one_rr()) mma_commit(bar_done);
         __syncwarp();
     } else {
-        // ===================== row warps: four threads per row =====================
-        const int t = threadIdx.x & 127, qt = threadIdx.x >> 7;
-        const uint32_t rsw = (uint32_t)(t & 3);                        // k-row inside the 4-row swizzle atom
-        const uint32_t rowoff = (uint32_t)(t * 128);                   // rows are 128 B apart; atoms (4 rows) 512 B
-        auto store4 = [&](uint32_t base, int k4, float4 v) {           // k4: feature index, multiple of 4
-            uint32_t gran = (uint32_t)((k4 & 31) >> 3);                // 32-byte granule inside the 128-byte row
-            uint32_t off = (uint32_t)(k4 >> 5) * 16384u + rowoff + ((gran ^ rsw) << 5) + (uint32_t)((k4 & 7) << 2);
+        // ===================== row warps: warp w owns rows 8w .. 8w+7 of every row tile, lane l owns features 4l .. 4l+3 ========
+        // (round 1 had one thread per row: its 16-byte loads from rows 4M bytes apart cost one L1 wavefront per row and chunk,
+        // and its MN-major stores -- rows 128 B apart -- were 8-way bank conflicts: half of all shared-memory wavefronts.  With
+        // lanes along the feature dimension a row is read as one coalesced 4M-byte segment and a warp's store covers whole
+        // 128-byte rows of the operand image.)
+        const int lane = threadIdx.x & 31;
+        float* vs_w = reinterpret_cast<float*>(sgen + 3 * RR_TILE_BYTES + 256) + warp * 256;      // [8][D] vbar, D <= 16
+        float* ms_w = vs_w + 128;                                                              // [8][D] mubar
+        const int f0 = 4 * lane;
+        const bool fact = f0 < NPAD;                                   // lanes beyond the padded width only zero the padding
+        const bool vec = (M & 3) == 0;
+        const uint32_t foff = (uint32_t)(f0 >> 5) * 16384u + (uint32_t)((f0 & 7) << 2);
+        const uint32_t gran = (uint32_t)((f0 & 31) >> 3);
+        auto store4 = [&](uint32_t base, int r, float4 v) {            // r: row inside the tile (k index of the GEMM)
+            const uint32_t off = foff + (uint32_t)r * 128u + ((gran ^ (uint32_t)(r & 3)) << 5);
             *reinterpret_cast<float4*>(sgen + (base - sbase) + off) = v;
         };
-        // this thread's feature range [c_lo, c_hi): a quarter of the NPAD features in units of 4 (<= 32 wide); the flush
-        // reads TMEM in units of 8 columns: [f_lo, f_hi)
-        const int n4 = NPAD >> 2, q4 = n4 >> 2, r4 = n4 & 3;
-        const int c_lo = 4 * (qt * q4 + min(qt, r4)), c_hi = c_lo + 4 * (q4 + (qt < r4 ? 1 : 0));
-        const int n8 = NPAD >> 3, q8 = n8 >> 2, r8 = n8 & 3;
-        const int f_lo = 8 * (qt * q8 + min(qt, r8)), f_hi = f_lo + 8 * (q8 + (qt < r8 ? 1 : 0));
-        const float* Asrc = is_g ? W : U;
+        auto load4s = [&](uint32_t base, int r) -> float4 {            // the same element of an operand image
+            const uint32_t off = foff + (uint32_t)r * 128u + ((gran ^ (uint32_t)(r & 3)) << 5);
+            return *reinterpret_cast<const float4*>(sgen + (base - sbase) + off);
+        };
+        auto load_row4 = [&](const float* __restrict__ src, int grow) -> float4 {     // features f0..f0+3 of global row grow
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow < R && f0 < M) {
+                const float* p = src + (size_t)grow * M + f0;
+                if (vec) v = *reinterpret_cast<const float4*>(p);
+                else {
+                    v.x = p[0];
+                    if (f0 + 1 < M) v.y = p[1];
+                    if (f0 + 2 < M) v.z = p[2];
+                    if (f0 + 3 < M) v.w = p[3];
+                }
+            }
+            return v;
+        };
         int bcount = 0;
         const bool dbg = dbgp && blockIdx.x == 0 && threadIdx.x == 0;
         int dbi = 0;
 #define RSTAMP() do { if (dbg && dbi < 38) dbgp[dbi++] = clock64(); } while (0)
         RSTAMP();
+        // the loop over row tiles, compiled twice (P groups / G group) so that neither variant carries the other's registers
+        auto tiles_loop = [&](auto GC) {
+        constexpr bool G = decltype(GC)::value;
+        // P groups: the rows of the NEXT tile (and its vbar / mubar slice) are loaded into registers while the current tile is
+        // converted and multiplied -- a dependent global round trip costs 2-4k cycles here, about one tile's worth of work.
+        // G group: nx holds the current tile's W rows (both operands are needed at once; its loads rely on the L1 prefetch).
+        float4 nx[8];
+        float vnx[4], mnx[4];
+        auto load_slice = [&](int r0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = lane + 32 * k;
+                const bool ok = idx < 8 * D && r0 + idx / D < R;
+                vnx[k] = ok ? vbar[(size_t)r0 * D + idx] : 0.f;
+                mnx[k] = (ok && has_q) ? mubar[(size_t)r0 * D + idx] : 0.f;
+            }
+        };
+        if (!G) {
+            const int r0 = split * 128 + 8 * warp;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nx[j] = fact ? load_row4(U, r0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            load_slice(r0);
+        }
         for (int it = 0; it < n_it; ++it) {
-            const int tit = is_g ? (it >> 1) : it, sub = is_g ? (it & 1) : 0;
+            const int tit = G ? (it >> 1) : it, sub = G ? (it & 1) : 0;
             const int tile = split + tit * gsz;
-            const int row = tile * 128 + t;
-            const bool valid = row < R;
-            const int nbi = is_g ? (sub ? 1 : 2) : nb;
-            // pull the next tile's row slices towards L1 while this tile is converted and multiplied: the row threads are
-            // long-scoreboard bound on exactly these loads (46% of the stall samples, profiles/r1b_big3_ncu_stalls.txt)
-            if (tit + 1 < my_tiles && sub == 0) {
-                const int nrow = row + 128 * gsz;
-                if (nrow < R) {
-                    const char* pu = reinterpret_cast<const char*>(U + (size_t)nrow * M + c_lo);
-                    const int nbytes = 4 * (min(c_hi, M) - c_lo);      // stay inside the row (c_hi is padded to 16 features)
-                    for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pu + o));
-                    if (is_g) {
-                        const char* pw = reinterpret_cast<const char*>(W + (size_t)nrow * M + c_lo);
-                        for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pw + o));
-                    } else if (qt == 0) {
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(vbar + (size_t)nrow * D)));
-                    }
-                }
-            }
-            // this half's slice of the row(s), tf32-rounded, kept in registers
+            const int row0 = tile * 128 + 8 * warp;
+            const int nbi = G ? (sub ? 1 : 2) : nb;
             float4 uv[8];
+            if (G) {
+                if (tit + 1 < my_tiles && sub == 0 && (lane & 7) == 0 && f0 < M) {      // one lane per 128-byte line of a row
+                    const int nrow0 = row0 + 128 * gsz;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int c0 = c_lo + 4 * c;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid && c0 < c_hi) {
-                    if (c0 + 4 <= M && (M & 3) == 0) v = *reinterpret_cast<const float4*>(U + (size_t)row * M + c0);
-                    else {
-                        if (c0 < M) v.x = U[(size_t)row * M + c0];
-                        if (c0 + 1 < M) v.y = U[(size_t)row * M + c0 + 1];
-                        if (c0 + 2 < M) v.z = U[(size_t)row * M + c0 + 2];
-                        if (c0 + 3 < M) v.w = U[(size_t)row * M + c0 + 3];
-                    }
-                }
-                uv[c] = v;
-            }
-            float scv[3] = {1.f, 1.f, 1.f};
-            if (!is_g) {
-#pragma unroll
-                for (int b = 0; b < 3; ++b) scv[b] = (valid && b < nd) ? vbar[(size_t)row * D + d0 + b] : 0.f;
-            }
-            RSTAMP();     // loads issued / landed
-            // ---- A operand
-            if (it > 0) mbar_wait(bar_afree, (it - 1) & 1);
-            RSTAMP();     // A free
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int c0 = c_lo + 4 * c;
-                if (c0 < c_hi) {
-                    float4 v = uv[c];
-                    if (is_g) {
-                        v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid) {
-                            if (c0 + 4 <= M && (M & 3) == 0) v = *reinterpret_cast<const float4*>(Asrc + (size_t)row * M + c0);
-                            else {
-                                if (c0 < M) v.x = Asrc[(size_t)row * M + c0];
-                                if (c0 + 1 < M) v.y = Asrc[(size_t)row * M + c0 + 1];
-                                if (c0 + 2 < M) v.z = Asrc[(size_t)row * M + c0 + 2];
-                                if (c0 + 3 < M) v.w = Asrc[(size_t)row * M + c0 + 3];
-                            }
+                    for (int j = 0; j < 8; ++j) {
+                        if (nrow0 + j < R) {
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(U + (size_t)(nrow0 + j) * M + f0)));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(W + (size_t)(nrow0 + j) * M + f0)));
                         }
                     }
-                    float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-                    if (sub == 1) hi = make_float4(tf32_lo_trunc(v.x, hi.x), tf32_lo_trunc(v.y, hi.y), tf32_lo_trunc(v.z, hi.z), tf32_lo_trunc(v.w, hi.w));
-                    store4(A_t, c0, hi);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) uv[j] = fact ? load_row4(U, row0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) nx[j] = fact ? load_row4(W, row0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) uv[j] = nx[j];
+                // this warp's rows of vbar / mubar -> its private slice of shared memory (read back as broadcasts below)
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int idx = lane + 32 * k;
+                    if (idx < 8 * D) { vs_w[idx] = vnx[k]; if (has_q) ms_w[idx] = mnx[k]; }
+                }
+                __syncwarp();
+                if (tit + 1 < my_tiles) {
+                    const int nrow0 = row0 + 128 * gsz;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) nx[j] = fact ? load_row4(U, nrow0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    load_slice(nrow0);
                 }
             }
-            if (qt == 3 && it == 0) {   // zero the feature padding [NPAD, 128) of A and of both B buffers once
-                for (int c0 = NPAD; c0 < 128; c0 += 4) {
-                    store4(A_t, c0, make_float4(0.f, 0.f, 0.f, 0.f));
-                    store4(B_t, c0, make_float4(0.f, 0.f, 0.f, 0.f));
-                    store4(B_t + RR_TILE_BYTES, c0, make_float4(0.f, 0.f, 0.f, 0.f));
+            RSTAMP();     // loads issued
+            // ---- A operand: U (P groups) or W hi / lo (G group)
+            if (it > 0) mbar_wait(bar_afree, (it - 1) & 1);
+            RSTAMP();     // A free
+            if (fact) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = G ? nx[j] : uv[j];
+                    float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+                    if (sub == 1) hi = make_float4(tf32_lo_trunc(v.x, hi.x), tf32_lo_trunc(v.y, hi.y), tf32_lo_trunc(v.z, hi.z), tf32_lo_trunc(v.w, hi.w));
+                    store4(A_t, 8 * warp + j, hi);
+                }
+            } else if (it == 0) {       // zero the feature padding [NPAD, 128) of A and of both B buffers once
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    store4(A_t, 8 * warp + j, make_float4(0.f, 0.f, 0.f, 0.f));
+                    store4(B_t, 8 * warp + j, make_float4(0.f, 0.f, 0.f, 0.f));
+                    store4(B_t + RR_TILE_BYTES, 8 * warp + j, make_float4(0.f, 0.f, 0.f, 0.f));
                 }
             }
             fence_proxy_async();
@@ -220,69 +245,83 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
             // ---- B operands
             for (int b = 0; b < nbi; ++b, ++bcount) {
                 const int buf = bcount & 1;
-                if (bcount >= 2) mbar_wait(bar_bfree + 8 * buf, ((bcount >> 1) - 1) & 1);
                 const uint32_t Bb = B_t + buf * RR_TILE_BYTES;
                 const bool isq = has_q && b == nd;
+                if (bcount >= 2) mbar_wait(bar_bfree + 8 * buf, ((bcount >> 1) - 1) & 1);
                 if (isq) {
-                    // B[r][d] = mubar[r][d] (16 columns, zero padded)
-                    if (qt == 0) {
+                    // B[r][d] = mubar[r][d] (16 columns, zero padded): lanes 0..3
+                    if (lane < 4) {
 #pragma unroll
-                        for (int c0 = 0; c0 < 16; c0 += 4) {
+                        for (int j = 0; j < 8; ++j) {
                             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (valid) {
-                                if (c0 < D) v.x = mubar[(size_t)row * D + c0];
-                                if (c0 + 1 < D) v.y = mubar[(size_t)row * D + c0 + 1];
-                                if (c0 + 2 < D) v.z = mubar[(size_t)row * D + c0 + 2];
-                                if (c0 + 3 < D) v.w = mubar[(size_t)row * D + c0 + 3];
-                            }
-                            store4(Bb, c0, make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w)));
+                            if (f0 < D) v.x = ms_w[j * D + f0];
+                            if (f0 + 1 < D) v.y = ms_w[j * D + f0 + 1];
+                            if (f0 + 2 < D) v.z = ms_w[j * D + f0 + 2];
+                            if (f0 + 3 < D) v.w = ms_w[j * D + f0 + 3];
+                            store4(Bb, 8 * warp + j, make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w)));
                         }
                     }
-                } else {
-                    const float sc = b == 0 ? scv[0] : b == 1 ? scv[1] : scv[2];
+                } else if (fact) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int c0 = c_lo + 4 * c;
-                        if (c0 < c_hi) {
-                            float4 v = uv[c];
-                            float4 hi = make_float4(tf32_rna(v.x * sc), tf32_rna(v.y * sc), tf32_rna(v.z * sc), tf32_rna(v.w * sc));
-                            if (is_g && b == 1) hi = make_float4(tf32_lo_trunc(v.x, hi.x), tf32_lo_trunc(v.y, hi.y), tf32_lo_trunc(v.z, hi.z), tf32_lo_trunc(v.w, hi.w));   // U_lo
-                            store4(Bb, c0, hi);
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        // P groups: the row comes back from the A image (tf32(u), exactly what the tensor core multiplies on the
+                        // A side), which frees the registers that hold the prefetched next tile; G group: full-precision u
+                        const float4 v = G ? uv[j] : load4s(A_t, 8 * warp + j);
+                        const float sc = G ? 1.f : vs_w[j * D + d0 + b];
+                        float4 hi = make_float4(tf32_rna(v.x * sc), tf32_rna(v.y * sc), tf32_rna(v.z * sc), tf32_rna(v.w * sc));
+                        if (G && b == 1) hi = make_float4(tf32_lo_trunc(v.x, hi.x), tf32_lo_trunc(v.y, hi.y), tf32_lo_trunc(v.z, hi.z), tf32_lo_trunc(v.w, hi.w));   // U_lo
+                        store4(Bb, 8 * warp + j, hi);
                     }
                 }
                 fence_proxy_async();
                 mbar_arrive(bar_bready + 8 * buf);
             }
         }
+        };
+        if (is_g) tiles_loop(std::true_type{}); else tiles_loop(std::false_type{});
         RSTAMP();         // all operands stored
-        // ---- flush: TMEM lane i = output row i; this quarter's columns
+        // ---- flush.  TMEM lane i = output row i.  The accumulator is staged in shared memory (the operand buffers are dead)
+        // so that the reductions go out row by row: a warp's vector reduction then covers one contiguous row segment instead
+        // of 32 different rows.
         mbar_wait(bar_done, 0);
         tc_fence_after();
         RSTAMP();         // MMAs done
-        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const int i = t;
-        for (int b = 0; b < nb; ++b) {
-            const bool isq = has_q && b == nd;
-            float* out; int ldo, ncols;
-            if (is_g) { out = P.G; ldo = M; ncols = M; }
-            else if (isq) { out = P.qmubar; ldo = D; ncols = D; }
-            else { out = P.Pd + (size_t)(d0 + b) * M * M; ldo = M; ncols = M; }
-            const uint32_t dcol = isq ? 384u : 128u * (uint32_t)b;
-            const int lo = isq ? (qt ? 16 : 0) : f_lo, hi = isq ? 16 : f_hi;
-            for (int c0 = lo; c0 < hi; c0 += 8) {
-                float v[8];
-                __syncwarp();
-                tmem_ld8(lane_addr + dcol + c0, v);
-                if (i < M) {
-                    float* dst = &out[(size_t)i * ldo + c0];
-                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && c0 + 8 <= ncols) {       // 16-byte aligned: two vector reductions instead of eight scalar
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (c0 + u < ncols) atomicAdd(dst + u, v[u]);
+        {
+            const int t = threadIdx.x & 127, qt = threadIdx.x >> 7;
+            const int n8 = NPAD >> 3, q8 = n8 >> 2, r8 = n8 & 3;
+            const int f_lo = 8 * (qt * q8 + min(qt, r8)), f_hi = f_lo + 8 * (q8 + (qt < r8 ? 1 : 0));
+            const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            const int SST = NPAD + 4;                  // staging row stride (floats): SST/4 odd -> conflict-free 16-byte accesses
+            float* stage = reinterpret_cast<float*>(sgen);      // [128][SST] over A_t / B_t (<= 67.6 KB of the 192 KB)
+            for (int b = 0; b < nb; ++b) {
+                const bool isq = has_q && b == nd;
+                float* out; int ldo, ncols;
+                if (is_g) { out = P.G; ldo = M; ncols = M; }
+                else if (isq) { out = P.qmubar; ldo = D; ncols = D; }
+                else { out = P.Pd + (size_t)(d0 + b) * M * M; ldo = M; ncols = M; }
+                const uint32_t dcol = isq ? 384u : 128u * (uint32_t)b;
+                const int lo = isq ? (qt ? 16 : 0) : f_lo, hi = isq ? 16 : f_hi;
+                if (b > 0) named_bar_sync(2, RR_ROWTHREADS);      // the previous accumulator's staging has been read
+                for (int c0 = lo; c0 < hi; c0 += 8) {
+                    float v[8];
+                    __syncwarp();
+                    tmem_ld8(lane_addr + dcol + c0, v);
+                    *reinterpret_cast<float4*>(stage + t * SST + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(stage + t * SST + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+                named_bar_sync(2, RR_ROWTHREADS);
+                if (f0 < ncols) {
+                    for (int i = warp; i < M; i += RR_ROWTHREADS / 32) {
+                        const float4 v = *reinterpret_cast<const float4*>(stage + i * SST + f0);
+                        float* dst = &out[(size_t)i * ldo + f0];
+                        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && f0 + 4 <= ncols) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                        } else {
+                            atomicAdd(dst, v.x);
+                            if (f0 + 1 < ncols) atomicAdd(dst + 1, v.y);
+                            if (f0 + 2 < ncols) atomicAdd(dst + 2, v.z);
+                            if (f0 + 3 < ncols) atomicAdd(dst + 3, v.w);
+                        }
                     }
                 }
             }
@@ -297,7 +336,7 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
 bool tc_rowred_supported(const LayerDev& P) { return P.M <= 128 && P.M >= 8 && P.Dout <= 16; }
 
 cudaError_t rowred_tc_init() {
-    return cudaFuncSetAttribute(k_layer_rowred_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * RR_TILE_BYTES + 1024 + 256);
+    return cudaFuncSetAttribute(k_layer_rowred_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * RR_TILE_BYTES + 1024 + 256 + 16 * 1024);
 }
 
 void launch_bwd_rowred_tc(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nl) {
@@ -306,7 +345,7 @@ void launch_bwd_rowred_tc(const LayerDev& P, const BwdArgs& a, int num_sms, cuda
     // the G group's row tile costs ~1.5x a P group's (five operand tiles and two row sets instead of four and one)
     int nsplit_p = max(1, min(ntiles, (int)(num_sms / (ngroups_d + 1.5))));
     int nsplit_g = max(1, min(ntiles, num_sms - ngroups_d * nsplit_p));
-    k_layer_rowred_tc<<<ngroups_d * nsplit_p + nsplit_g, RR_THREADS, 3 * RR_TILE_BYTES + 1024 + 256, st>>>(
+    k_layer_rowred_tc<<<ngroups_d * nsplit_p + nsplit_g, RR_THREADS, 3 * RR_TILE_BYTES + 1024 + 256 + 16 * 1024, st>>>(
         P, a.U, a.W, a.mubar, a.vbar, a.R, ngroups_d, nsplit_p, nsplit_g, a.dbg_rr);
     *nl += 1;
 }
