@@ -130,13 +130,15 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
         const bool vec = (M & 3) == 0;
         const uint32_t foff = (uint32_t)(f0 >> 5) * 16384u + (uint32_t)((f0 & 7) << 2);
         const uint32_t gran = (uint32_t)((f0 & 31) >> 3);
-        auto store4 = [&](uint32_t base, int r, float4 v) {            // r: row inside the tile (k index of the GEMM)
-            const uint32_t off = foff + (uint32_t)r * 128u + ((gran ^ (uint32_t)(r & 3)) << 5);
-            *reinterpret_cast<float4*>(sgen + (base - sbase) + off) = v;
+        // element (row r = 8 warp + j, features f0..f0+3) of an operand image; r & 3 == j & 3, so the swizzle term is one of
+        // four per-lane constants and j * 128 an immediate
+        uint8_t* const wbase = sgen + foff + (uint32_t)warp * 1024u;
+        const uint32_t swz[4] = {(gran ^ 0u) << 5, (gran ^ 1u) << 5, (gran ^ 2u) << 5, (gran ^ 3u) << 5};
+        auto store4 = [&](uint32_t base, int j, float4 v) {
+            *reinterpret_cast<float4*>(wbase + (base - sbase) + j * 128 + swz[j & 3]) = v;
         };
-        auto load4s = [&](uint32_t base, int r) -> float4 {            // the same element of an operand image
-            const uint32_t off = foff + (uint32_t)r * 128u + ((gran ^ (uint32_t)(r & 3)) << 5);
-            return *reinterpret_cast<const float4*>(sgen + (base - sbase) + off);
+        auto load4s = [&](uint32_t base, int j) -> float4 {
+            return *reinterpret_cast<const float4*>(wbase + (base - sbase) + j * 128 + swz[j & 3]);
         };
         auto load_row4 = [&](const float* __restrict__ src, int grow) -> float4 {     // features f0..f0+3 of global row grow
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -152,10 +154,33 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
             }
             return v;
         };
+        // rows r0 .. r0+7 of src, this lane's four features.  Fast path (whole rows inside the matrix, M % 4 == 0): one base
+        // pointer, eight loads at a constant stride -- the generic path's per-row address arithmetic and branches were ~15 % of
+        // the kernel's instructions
+        auto load_rows8 = [&](const float* __restrict__ src, int r0, float4 (&dst)[8]) {
+            if (vec && r0 + 8 <= R) {                  // warp-uniform: lanes past the last feature are predicated off, not diverged
+                const float4* p = reinterpret_cast<const float4*>(src + (size_t)r0 * M + (f0 < M ? f0 : 0));
+                const int st = M >> 2;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = f0 < M ? p[j * st] : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = fact ? load_row4(src, r0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        // this lane's (up to four) elements of a warp's [8 rows][D] slice of vbar / mubar: element idx = lane + 32 k is row
+        // idx / D, output idx % D; stored transposed ([d][8]) so that the scale of row j for output d is slice[8 d + j]
+        int sl_row[4], sl_dst[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = lane + 32 * k;
+            sl_row[k] = idx < 8 * D ? idx / D : 1 << 20;
+            sl_dst[k] = idx < 8 * D ? (idx % D) * 8 + idx / D : 0;
+        }
         int bcount = 0;
         const bool dbg = dbgp && blockIdx.x == 0 && threadIdx.x == 0;
         int dbi = 0;
-#define RSTAMP() do { if (dbg && dbi < 38) dbgp[dbi++] = clock64(); } while (0)
+#define RSTAMP() do { if (dbg && dbi < 20) dbgp[dbi++] = clock64(); } while (0)
         RSTAMP();
         // the loop over row tiles, compiled twice (P groups / G group) so that neither variant carries the other's registers
         auto tiles_loop = [&](auto GC) {
@@ -168,16 +193,15 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
         auto load_slice = [&](int r0) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int idx = lane + 32 * k;
-                const bool ok = idx < 8 * D && r0 + idx / D < R;
-                vnx[k] = ok ? vbar[(size_t)r0 * D + idx] : 0.f;
-                mnx[k] = (ok && has_q) ? mubar[(size_t)r0 * D + idx] : 0.f;
+                const bool ok = r0 + sl_row[k] < R;
+                vnx[k] = ok ? vbar[(size_t)r0 * D + lane + 32 * k] : 0.f;
+                mnx[k] = (ok && has_q) ? mubar[(size_t)r0 * D + lane + 32 * k] : 0.f;
             }
         };
         if (!G) {
             const int r0 = split * 128 + 8 * warp;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) nx[j] = fact ? load_row4(U, r0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            load_rows8(U, r0, nx);
             load_slice(r0);
         }
         for (int it = 0; it < n_it; ++it) {
@@ -197,10 +221,8 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                         }
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) uv[j] = fact ? load_row4(U, row0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) nx[j] = fact ? load_row4(W, row0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                load_rows8(U, row0, uv);
+                load_rows8(W, row0, nx);
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) uv[j] = nx[j];
@@ -208,14 +230,12 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int idx = lane + 32 * k;
-                    if (idx < 8 * D) { vs_w[idx] = vnx[k]; if (has_q) ms_w[idx] = mnx[k]; }
+                    if (sl_row[k] < 8) { vs_w[sl_dst[k]] = vnx[k]; if (has_q) ms_w[sl_dst[k]] = mnx[k]; }
                 }
                 __syncwarp();
                 if (tit + 1 < my_tiles) {
                     const int nrow0 = row0 + 128 * gsz;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) nx[j] = fact ? load_row4(U, nrow0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    load_rows8(U, nrow0, nx);
                     load_slice(nrow0);
                 }
             }
@@ -229,14 +249,14 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                     const float4 v = G ? nx[j] : uv[j];
                     float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
                     if (sub == 1) hi = make_float4(tf32_lo_trunc(v.x, hi.x), tf32_lo_trunc(v.y, hi.y), tf32_lo_trunc(v.z, hi.z), tf32_lo_trunc(v.w, hi.w));
-                    store4(A_t, 8 * warp + j, hi);
+                    store4(A_t, j, hi);
                 }
             } else if (it == 0) {       // zero the feature padding [NPAD, 128) of A and of both B buffers once
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    store4(A_t, 8 * warp + j, make_float4(0.f, 0.f, 0.f, 0.f));
-                    store4(B_t, 8 * warp + j, make_float4(0.f, 0.f, 0.f, 0.f));
-                    store4(B_t + RR_TILE_BYTES, 8 * warp + j, make_float4(0.f, 0.f, 0.f, 0.f));
+                    store4(A_t, j, make_float4(0.f, 0.f, 0.f, 0.f));
+                    store4(B_t, j, make_float4(0.f, 0.f, 0.f, 0.f));
+                    store4(B_t + RR_TILE_BYTES, j, make_float4(0.f, 0.f, 0.f, 0.f));
                 }
             }
             fence_proxy_async();
@@ -247,34 +267,39 @@ __global__ void __launch_bounds__(RR_THREADS, 1) k_layer_rowred_tc(LayerDev P, c
                 const int buf = bcount & 1;
                 const uint32_t Bb = B_t + buf * RR_TILE_BYTES;
                 const bool isq = has_q && b == nd;
+                if (dbg && it == 1) dbgp[20 + 4 * b] = clock64();
                 if (bcount >= 2) mbar_wait(bar_bfree + 8 * buf, ((bcount >> 1) - 1) & 1);
+                if (dbg && it == 1) dbgp[21 + 4 * b] = clock64();
                 if (isq) {
                     // B[r][d] = mubar[r][d] (16 columns, zero padded): lanes 0..3
                     if (lane < 4) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (f0 < D) v.x = ms_w[j * D + f0];
-                            if (f0 + 1 < D) v.y = ms_w[j * D + f0 + 1];
-                            if (f0 + 2 < D) v.z = ms_w[j * D + f0 + 2];
-                            if (f0 + 3 < D) v.w = ms_w[j * D + f0 + 3];
-                            store4(Bb, 8 * warp + j, make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w)));
+                            if (f0 < D) v.x = ms_w[8 * f0 + j];
+                            if (f0 + 1 < D) v.y = ms_w[8 * (f0 + 1) + j];
+                            if (f0 + 2 < D) v.z = ms_w[8 * (f0 + 2) + j];
+                            if (f0 + 3 < D) v.w = ms_w[8 * (f0 + 3) + j];
+                            store4(Bb, j, make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w)));
                         }
                     }
                 } else if (fact) {
+                    const float* scp = vs_w + 8 * (d0 + b);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         // P groups: the row comes back from the A image (tf32(u), exactly what the tensor core multiplies on the
                         // A side), which frees the registers that hold the prefetched next tile; G group: full-precision u
-                        const float4 v = G ? uv[j] : load4s(A_t, 8 * warp + j);
-                        const float sc = G ? 1.f : vs_w[j * D + d0 + b];
+                        const float4 v = G ? uv[j] : load4s(A_t, j);
+                        const float sc = G ? 1.f : scp[j];
                         float4 hi = make_float4(tf32_rna(v.x * sc), tf32_rna(v.y * sc), tf32_rna(v.z * sc), tf32_rna(v.w * sc));
                         if (G && b == 1) hi = make_float4(tf32_lo_trunc(v.x, hi.x), tf32_lo_trunc(v.y, hi.y), tf32_lo_trunc(v.z, hi.z), tf32_lo_trunc(v.w, hi.w));   // U_lo
-                        store4(Bb, 8 * warp + j, hi);
+                        store4(Bb, j, hi);
                     }
                 }
+                if (dbg && it == 1) dbgp[22 + 4 * b] = clock64();
                 fence_proxy_async();
                 mbar_arrive(bar_bready + 8 * buf);
+                if (dbg && it == 1) dbgp[23 + 4 * b] = clock64();
             }
         }
         };
