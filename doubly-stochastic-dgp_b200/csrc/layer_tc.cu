@@ -12,8 +12,7 @@
 #include "tc_pack.cuh"
 
 #define TC_ROWS 128
-#define TC_NSTAGE 3          // weight ring slots (barriers): slots 0,1 in the ring area, slot 2 = the A_lo operand buffer
-                             // once the 3xTF32 projections are done (G2 streams 1.5x more bytes in flight)
+#define TC_NS_MAX 10         // weight ring sub-slots (barriers)
 #define TC_CHUNK_BYTES 16384 // one [128 rows] x [32 k] activation k-block
 #define TC_THREADS 576
 
@@ -103,10 +102,16 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
     const uint32_t A_hi = sbase, A_lo = sbase + 65536, Bring = sbase + 131072;
     const uint32_t slotb = tcp::slot_bytes(P.M);
     const uint32_t misc = Bring + 2 * slotb;
-    const bool three = P.Dout <= 8 && slotb <= 40960;            // third slot + scratch fit into the 64 KB of A_lo
-    auto slot_addr = [&](int sl) { return sl == 2 ? A_lo : Bring + (uint32_t)sl * slotb; };
-    const uint32_t bar_full = misc, bar_empty = misc + 8 * TC_NSTAGE;
-    const uint32_t bar_a = bar_empty + 8 * TC_NSTAGE;        // a_ready[3]
+    // Weights stream as 32-wide k-block bands (<= 128 NPAD bytes, one TMA bulk copy each) through a ring of sub-slots: the
+    // ring area holds `nr` of them; once the 3xTF32 projections are done A_lo is dead and adds `nalo` more for the G2 stream
+    // (its last bytes keep the |c_d|^2 scratch), so up to nr + nalo bands are in flight instead of two or three whole blocks.
+    const uint32_t band_full = 128u * (uint32_t)tcp::npad_of(P.M);
+    const uint32_t csq_bytes = 2u * (uint32_t)P.Dout * 128u * 4u;
+    const int nr = (int)(2 * slotb / band_full);
+    const int nalo = csq_bytes >= 65536u ? 0 : min(TC_NS_MAX - nr, (int)((65536u - csq_bytes) / band_full));
+    auto slot_addr = [&](int sl) { return sl < nr ? Bring + (uint32_t)sl * band_full : A_lo + (uint32_t)(sl - nr) * band_full; };
+    const uint32_t bar_full = misc, bar_empty = misc + 8 * TC_NS_MAX;
+    const uint32_t bar_a = bar_empty + 8 * TC_NS_MAX;        // a_ready[3]
     const uint32_t bar_acc = bar_a + 24;                      // acc_full[2]
     const uint32_t bar_acc2f = bar_acc + 16;                  // acc2_full[2]
     const uint32_t bar_acc2e = bar_acc2f + 16;                // acc2_empty[2]
@@ -114,17 +119,27 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
     float* Zs = part_s + 512;                                                       // [M][Din], pre-scaled by 1/lengthscale
     float* qmu_s = Zs + ((P.M * P.Din + 3) & ~3);                                   // [M][D], 16-byte aligned
     // scratch aliased on A_lo once it is dead (G2 reads A_hi only): |c_d|^2 partials [2][D][128]
-    float* csq_p = reinterpret_cast<float*>(sgen + (A_lo - sbase) + (three ? 40960 : 0));
+    float* csq_p = reinterpret_cast<float*>(sgen + (A_lo - sbase) + (65536u - min(csq_bytes, 65536u)));
 
     const int M = P.M, Din = P.Din, D = P.Dout;
     const int nkb = (M + 31) / 32, NPAD = (M + 15) & ~15;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = tile * TC_ROWS, R = a.R;
 
+    // the tile's inputs are requested before anything else: the round trip (~2k cycles) overlaps the barrier set-up and the
+    // Z / q_mu staging below instead of heading the Gram phase
+    float xraw[DINP];
+#pragma unroll
+    for (int q = 0; q < DINP; ++q) xraw[q] = 0.f;
+    if (warp < TC_WARP_TMA && row0 + (int)(threadIdx.x & 127) < R) {
+#pragma unroll
+        for (int q = 0; q < DINP; ++q)
+            if (q < Din) xraw[q] = __ldcg(&a.Xin[(size_t)(row0 + (threadIdx.x & 127)) * Din + q]);
+    }
     if (threadIdx.x == 0) {
         if (reinit)
-            for (int i = 0; i < 2 * TC_NSTAGE + 9; ++i) mbar_inval(misc + 8 * i);
-        for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+            for (int i = 0; i < 2 * TC_NS_MAX + 9; ++i) mbar_inval(misc + 8 * i);
+        for (int s = 0; s < TC_NS_MAX; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int i = 0; i < 3; ++i) mbar_init(bar_a + 8 * i, TC_ROWTHREADS);
         for (int i = 0; i < 2; ++i) { mbar_init(bar_acc + 8 * i, 1); mbar_init(bar_acc2f + 8 * i, 1); mbar_init(bar_acc2e + 8 * i, TC_ROWTHREADS / 2); }
         fence_mbar_init();
@@ -137,84 +152,89 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
 
 
     if (warp == TC_WARP_TMA) {
-        // ===================== TMA producer (one lane): streams the packed weight chunks through the ring ==========
+        // ===================== TMA producer (one lane): one bulk copy per band, in the order the MMA warp consumes them =====
         if (lane == 0) {
             const char* wsrc = reinterpret_cast<const char*>(P.wpack_fwd);
-            int cnt[3] = {0, 0, 0};         // uses of each slot so far
-            auto load = [&](int blk, int pat, int sl) {            // one band block = one bulk copy
-                const uint32_t bytes = tcp::block_bytes(pat, M);
-                mbar_wait(bar_empty + 8 * sl, ((cnt[sl] & 1) ^ 1));
-                mbar_arrive_expect_tx(bar_full + 8 * sl, bytes);
-                tma_bulk_g2s(slot_addr(sl), wsrc + (size_t)blk * slotb, bytes, bar_full + 8 * sl);
-                ++cnt[sl];
+            uint32_t par = 0;          // bit s: parity of the next use of sub-slot s
+            int s = 0;
+            bool alo_ok = false;
+            auto load_block = [&](int blk, int pat, int nslots) {
+                for (int q = 0; q < nkb; ++q) {
+                    const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
+                    const uint32_t bytes = 128u * (uint32_t)tcp::band_rows(pat, M, kb);
+                    if (s >= nr && !alo_ok) {      // first band into A_lo: the projections must have finished reading it
+                        mbar_wait(P.white ? bar_acc : bar_acc + 8, 0);
+                        alo_ok = true;
+                    }
+                    mbar_wait(bar_empty + 8 * s, ((par >> s) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+                    tma_bulk_g2s(slot_addr(s), wsrc + (size_t)blk * slotb + tcp::band_offset(pat, M, kb), bytes, bar_full + 8 * s);
+                    par ^= 1u << s;
+                    if (++s == nslots) s = 0;
+                }
             };
-            load(tcp::blk_g1(0), tcp::PAT_LE, 0); load(tcp::blk_g1(1), tcp::PAT_LE, 1);
-            if (!P.white) { load(tcp::blk_g1p(0), tcp::PAT_GE, 0); load(tcp::blk_g1p(1), tcp::PAT_GE, 1); }
-            for (int d = 0; d < D; ++d) {
-                const int sl = three ? (2 + d) % 3 : d & 1;
-                if (three && d == 0) mbar_wait(P.white ? bar_acc : bar_acc + 8, 0);      // A_lo is dead: projections done
-                load(tcp::blk_g2(d), tcp::PAT_GE, sl);
-            }
+            load_block(tcp::blk_g1(0), tcp::PAT_LE, nr); load_block(tcp::blk_g1(1), tcp::PAT_LE, nr);
+            if (!P.white) { load_block(tcp::blk_g1p(0), tcp::PAT_GE, nr); load_block(tcp::blk_g1p(1), tcp::PAT_GE, nr); }
+            s = 0;
+            for (int d = 0; d < D; ++d) load_block(tcp::blk_g2(d), tcp::PAT_GE, nr + nalo);
         }
     } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer: whole warp runs the uniform control flow, one elected lane issues ==========
         {
-            int cnt[3] = {0, 0, 0};
+            uint32_t par = 0;
+            int s = 0;
             const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             auto mkdesc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
-            // one band block: D (+)= A * B^T over all k-blocks.  mode 0: A_hi and A_lo against this block (B_hi of a 3xTF32
-            // product), 1: A_hi only, accumulating (B_lo), 2: A_hi only (1xTF32 product, fresh accumulator)
-            auto do_block = [&](uint32_t dcol, int pat, int mode, int sl) {
-                mbar_wait(bar_full + 8 * sl, cnt[sl] & 1);
-                ++cnt[sl];
-                tc_fence_after();
-                const uint32_t bslot = slot_addr(sl);
-                bool first = mode != 1;
-                uint32_t boff = 0;
+            // one band block: D (+)= A * B^T, band by band.  mode 0: A_hi and A_lo against this block (B_hi of a 3xTF32
+            // product), 1: A_hi only, accumulating (B_lo), 2: A_hi only (1xTF32 product, fresh accumulator).  In both band
+            // orders the first band of a block spans all NPAD accumulator columns, so it is the one that clears them.
+            auto do_block = [&](uint32_t dcol, int pat, int mode, int nslots) {
 #pragma unroll 1
                 for (int q = 0; q < nkb; ++q) {
                     const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
+                    mbar_wait(bar_full + 8 * s, (par >> s) & 1u);
+                    tc_fence_after();
                     const int nks = min(4, (M - 32 * kb + 7) / 8);
                     const int nrows = tcp::band_rows(pat, M, kb);
-                    const uint32_t bbase = bslot + boff, abase = kb * TC_CHUNK_BYTES;
-                    boff += 128u * (uint32_t)nrows;
+                    const uint32_t bbase = slot_addr(s), abase = kb * TC_CHUNK_BYTES;
                     const uint32_t id = make_idesc_tf32(128, nrows);
                     const uint32_t dc = tmem + dcol + (uint32_t)tcp::band_row0(pat, kb);
                     if (elect_one()) {
 #pragma unroll 1
                         for (int ks = 0; ks < nks; ++ks) {
                             const uint64_t bd = mkdesc(bbase + ks * 32), ah = mkdesc(A_hi + abase + ks * 32);
-                            mma_tf32(dc, ah, bd, id, (first && ks == 0) ? 0u : 1u);
+                            mma_tf32(dc, ah, bd, id, (mode != 1 && q == 0 && ks == 0) ? 0u : 1u);
                             if (mode == 0) mma_tf32(dc, mkdesc(A_lo + abase + ks * 32), bd, id, 1u);
                         }
+                        mma_commit(bar_empty + 8 * s);
                     }
                     __syncwarp();
-                    first = false;
+                    par ^= 1u << s;
+                    if (++s == nslots) s = 0;
                 }
-                if (elect_one()) mma_commit(bar_empty + 8 * sl);
-                __syncwarp();
             };
             auto commit = [&](uint32_t bar) { if (elect_one()) mma_commit(bar); __syncwarp(); };
             // G1: b = Linv k   (3xTF32)
             mbar_wait(bar_a, 0);
             tc_fence_after();
-            do_block(0u, tcp::PAT_LE, 0, 0);
-            do_block(0u, tcp::PAT_LE, 1, 1);
+            do_block(0u, tcp::PAT_LE, 0, nr);
+            do_block(0u, tcp::PAT_LE, 1, nr);
             commit(bar_acc);
             if (!P.white) {
                 // G1': u = Linv^T b   (3xTF32)
                 mbar_wait(bar_a + 8, 0);
                 tc_fence_after();
-                do_block(128u, tcp::PAT_GE, 0, 0);
-                do_block(128u, tcp::PAT_GE, 1, 1);
+                do_block(128u, tcp::PAT_GE, 0, nr);
+                do_block(128u, tcp::PAT_GE, 1, nr);
                 commit(bar_acc + 8);
             }
             // G2: c_d = L_d^T u   (1xTF32), accumulators double-buffered (buffer d&1 is consumed by quarter pair d&1)
             mbar_wait(bar_a + 16, 0);
             tc_fence_after();
+            s = 0;
             for (int d = 0; d < D; ++d) {
                 if (d >= 2) { mbar_wait(bar_acc2e + 8 * (d & 1), ((d >> 1) - 1) & 1); tc_fence_after(); }
-                do_block(256u + 128u * (uint32_t)(d & 1), tcp::PAT_GE, 2, three ? (2 + d) % 3 : d & 1);
+                do_block(256u + 128u * (uint32_t)(d & 1), tcp::PAT_GE, 2, nr + nalo);
                 commit(bar_acc2f + 8 * (d & 1));
             }
         }
@@ -256,7 +276,7 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
         float xs[DINP];
 #pragma unroll
         for (int q = 0; q < DINP; ++q)
-            xs[q] = (valid && q < Din) ? __ldcg(&a.Xin[(size_t)row * Din + q]) * (1.0f / P.ls[P.ard ? q : 0]) : 0.f;
+            xs[q] = q < Din ? xraw[q] * (1.0f / P.ls[P.ard ? q : 0]) : 0.f;
         const float var0 = P.var[0];
         const bool rbf = P.kern == DSDGP_KERN_RBF;
         const float l2var = log2f(var0);
