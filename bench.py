@@ -4,10 +4,16 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one process per GPU under torchrun)
   python bench.py --impl reference --gpus N --steps K ...  # the reference restatement (torch-CPU float64) on host cores
 
-Workload = BASELINE.json configs[2] (the config the metric is quoted on): 5-layer RBF DGP, kin8nm shape,
-N=1000 minibatch rows, M=100 inducing points, S=20 samples, dims 8->8->8->8->8->1, synthetic data.
+Workload (default, --config 3) = BASELINE.json configs[2] (the config the metric is quoted on): 5-layer RBF DGP, kin8nm
+shape, N=1000 minibatch rows, M=100 inducing points, S=20 samples, dims 8->8->8->8->8->1, synthetic data.
 One step = minibatch in + ELBO forward + full backward + Adam update (= one session.run(minimize_op) of the
-reference, demos/run_regression.py:83,138).
+reference, demos/run_regression.py:83,138).  --config 2 / 4 / 5 run the other BASELINE configs (4: the step is one
+natural-gradient step on the final layer's q(U), as BASELINE.json words it).
+
+N > 1 (torchrun): --scaling strong (default) is the BASELINE metric itself -- S_total = 20 fixed, the S*N sample rows are
+sharded, `value` = steps/s of that one problem; --scaling weak keeps S=20 per GPU (S_total = 20 N) and reports it in
+`other_scaling`.  Every run prints a `parity` block (ELBO of the sharded evaluation vs a single-GPU evaluation of the same
+global minibatch with the same Philox seed, and vs the float64 oracle at N=1) and exits non-zero beyond 1e-4.
 
 Timing: W (>=3) warm-up steps; K timed steps bracketed by barrier + synchronize; every timed step is measured
 with CUDA events on the stream the kernels are launched on (the ctx stream), L2 is flushed (256 MiB write)
@@ -30,9 +36,36 @@ for p in (ROOT, PKG):
 
 import numpy as np  # noqa: E402
 
+# BASELINE.json configs (1-based ids as in SURVEY 8(d)); config 1 is the CPU-runnable parity case (tests only)
+CONFIGS = {
+    2: dict(dims=[8, 8, 1], N=1000, M=100, S=20, kern='rbf', n_classes=0, step='adam', num_data=8192, seed=2000,
+            name="BASELINE configs[1]: 2-layer RBF DGP N=1000 M=100 S=20 dims 8-8-1"),
+    3: dict(dims=[8, 8, 8, 8, 8, 1], N=1000, M=100, S=20, kern='rbf', n_classes=0, step='adam', num_data=8192, seed=3000,
+            name="BASELINE configs[2]: 5-layer RBF DGP N=1000 M=100 S=20 dims 8-8-8-8-8-1"),
+    4: dict(dims=[9, 9, 9, 1], N=4096, M=512, S=32, kern='matern52', n_classes=0, step='natgrad', num_data=45730, seed=4000,
+            name="BASELINE configs[3]: 3-layer Matern52 DGP N=4096 M=512 S=32 dims 9-9-9-1, natural-gradient step on the final q(U)"),
+    5: dict(dims=[784, 30, 10], N=1000, M=100, S=10, kern='rbf', n_classes=10, step='adam', num_data=60000, seed=5000,
+            name="BASELINE configs[4]: 2-layer MNIST-shape multiclass DGP N=1000 M=100 S=10 dims 784-30-10"),
+}
+CFG_ID = 3
 WORKLOAD = dict(dims=[8, 8, 8, 8, 8, 1], N=1000, M=100, S=20)
 NUM_DATA = 8192          # kin8nm size (demos/datasets.py:133)
 METRIC = "ELBO training steps/sec (N=1000,M=100,S=20,L=5; fwd+bwd+Adam)"
+
+
+def select_config(cid):
+    global CFG_ID, WORKLOAD, NUM_DATA, METRIC
+    c = CONFIGS[cid]
+    CFG_ID = cid
+    WORKLOAD = dict(dims=c['dims'], N=c['N'], M=c['M'], S=c['S'])
+    NUM_DATA = c['num_data']
+    if cid != 3:
+        METRIC = (f"ELBO training steps/sec (N={c['N']},M={c['M']},S={c['S']},L={len(c['dims']) - 1}; fwd+bwd+"
+                  f"{'NatGrad' if c['step'] == 'natgrad' else 'Adam'})")
+
+
+def config_dict():
+    return {"workload": CONFIGS[CFG_ID]['name'], **WORKLOAD}
 
 
 def algorithmic_flops(dims, N, M, S, white=False):
@@ -92,9 +125,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_workload(seed=3000):
-    from tests.synth import make_problem
-    return make_problem(seed=seed, num_data=NUM_DATA, **WORKLOAD)
+def make_workload():
+    from workloads import make_problem
+    c = CONFIGS[CFG_ID]
+    kw = dict(kern=c['kern'], n_classes=c['n_classes'])
+    if CFG_ID == 4:
+        kw['max_cond'] = None          # (a 512 x 512 condition-number search is not worth the start-up time; timing only)
+    return make_problem(seed=c['seed'], num_data=NUM_DATA, **WORKLOAD, **kw)
 
 
 def measured_peaks():
@@ -110,12 +147,20 @@ def measured_peaks():
 # autograd backward, Adam on unconstrained variables) on the host cores.
 # ----------------------------------------------------------------------------------------------------------------
 def run_cpu_reference(steps, warmup, max_seconds=None):
+    """Returns (steps/s of the FULL workload, steps done, seconds, threads).  Config 4 is timed on an S=1 sample of its S=32
+    (the per-row work is linear in S; the M^3 work is counted S times, which favours the GPU side slightly less than the
+    truth) and scaled; the others run whole steps."""
     import torch
-    from tests.synth import build_oracle
+    from oracle.problems import build_oracle
     from oracle import reference_dgp as R
     ncpu = os.cpu_count() or 1
     prob = make_workload()
+    scale = 1.0
+    if CFG_ID == 4:
+        scale = prob['S'] / 1.0
+        prob = dict(prob, S=1, zs=[z[:1] for z in prob['zs']])
     o = build_oracle(prob, faithful=True)
+    o.num_samples = prob['S']
     st = R.AdamState(o, lr=0.01)
     rng = np.random.default_rng(0)
 
@@ -149,8 +194,9 @@ def run_cpu_reference(steps, warmup, max_seconds=None):
         if max_seconds and time.perf_counter() - t0 > max_seconds:
             break
     dt = time.perf_counter() - t0
-    run_cpu_reference.last_stats = {"median_ms": 1e3 * float(np.median(per_step)), "min_ms": 1e3 * float(np.min(per_step))}
-    return done / dt, done, dt, cores
+    run_cpu_reference.last_stats = {"median_ms": 1e3 * scale * float(np.median(per_step)), "min_ms": 1e3 * scale * float(np.min(per_step))}
+    run_cpu_reference.sample_note = "" if scale == 1.0 else f" (timed on an S=1 sample of S={int(scale)}, time scaled by {int(scale)})"
+    return done / (dt * scale), done, dt, cores
 
 
 def main_reference(args):
@@ -160,12 +206,12 @@ def main_reference(args):
     sps, done, dt, cores = run_cpu_reference(args.steps, args.warmup)
     out = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": done,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / done, "higher_is_better": True, "scaling": args.scaling,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / sps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[2]: 5-layer RBF DGP N=1000 M=100 S=20 dims 8-8-8-8-8-1", **WORKLOAD},
+        "config": config_dict(),
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", **run_cpu_reference.last_stats,
-                         "sample": f"{done} full steps of the same workload; reference restatement (torch-CPU float64, "
-                                   "reference-faithful D_out tiling, autograd, Adam), not TF 1.8"},
+                         "sample": f"{done} steps of the same workload{run_cpu_reference.sample_note}; reference restatement (torch-CPU "
+                                   "float64, reference-faithful D_out tiling, autograd, Adam), not TF 1.8"},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -177,7 +223,7 @@ def main_b200(args):
     import torch
     import torch.distributed as dist
     from doubly_stochastic_dgp import _lib
-    from tests.gpu_common import build_model
+    from workloads import build_model
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -192,12 +238,14 @@ def main_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     K, W = args.steps, max(3, args.warmup)
+    cfg = CONFIGS[CFG_ID]
     prob = make_workload()
     N, S = prob['N'], prob['S']
+    natgrad = cfg['step'] == 'natgrad'
+    Dy = 1 if cfg['n_classes'] else cfg['dims'][-1]
     if N % world:
         raise SystemExit("N must divide by the number of GPUs")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
-    uid = [None]
 
     def max_over_ranks(v):
         if world == 1:
@@ -206,37 +254,56 @@ def main_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def run_mode(mode, want_profile, want_e2e):
-        """mode 'weak': every GPU evaluates S=20 samples of the SAME (N=1000) minibatch -- the S-shards of one ELBO with
-        S_total = 20*world are all-reduced (BASELINE: "the S Monte-Carlo samples shard across the GPUs"); per-GPU work fixed.
-        mode 'strong': S_total = 20 fixed; the S*N sample rows are sharded (N/world minibatch rows x all S per GPU)."""
-        strong = mode == "strong"
-        N_loc = N // world if strong else N
+    def new_model(with_comm):
         m = build_model(prob, device=local_rank)
-        if world > 1:
+        if with_comm and world > 1:
             ids = [_lib.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
             m.comm_init(ids[0], rank, world)
-        ctx = m._ensure_ctx(N_loc, S)
-        m.adam_init(0.01)
+        return m
+
+    def shard_options(ctx, strong, N_loc):
         if world > 1:
             if strong:
                 ctx.set_option("n_global", N); ctx.set_option("n_offset", rank * N_loc)
             else:
                 ctx.set_option("n_global", N); ctx.set_option("n_offset", 0)
                 ctx.set_option("s_world", world); ctx.set_option("s_offset", rank * S)
-        # a pool of different minibatches: pinned host copies (e2e leg) and device-resident copies (value leg)
-        POOL = 8
-        rng = np.random.default_rng(100)              # same pool on every rank; strong mode takes this rank's rows
+
+    def minibatch_pool(n, strong, N_loc):
+        """a pool of different minibatches: pinned host copies (e2e leg) and device-resident copies (value leg);
+        same pool on every rank, strong mode takes this rank's rows"""
+        rng = np.random.default_rng(100)
         hostX, hostY, devX, devY = [], [], [], []
-        for _ in range(POOL):
+        for _ in range(n):
             xf = rng.normal(size=(N, WORKLOAD['dims'][0])).astype(np.float32)
-            yf = (np.sin(xf.sum(1, keepdims=True)) + 0.1 * rng.normal(size=(N, 1))).astype(np.float32)
+            if cfg['n_classes']:
+                yf = rng.integers(0, cfg['n_classes'], size=(N, 1)).astype(np.float32)
+            else:
+                yf = (np.sin(xf.sum(1, keepdims=True)) + 0.1 * rng.normal(size=(N, 1))).astype(np.float32)
+                yf = np.tile(yf, (1, Dy))
             lo = rank * N_loc if strong else 0
             x = torch.from_numpy(np.ascontiguousarray(xf[lo:lo + N_loc])).pin_memory()
             y = torch.from_numpy(np.ascontiguousarray(yf[lo:lo + N_loc])).pin_memory()
             hostX.append(x); hostY.append(y)
             devX.append(x.cuda()); devY.append(y.cuda())
+        return hostX, hostY, devX, devY
+
+    def run_mode(mode, want_profile, want_e2e):
+        """mode 'strong': the BASELINE problem itself -- S_total fixed, the S*N sample rows sharded (N/world minibatch rows x all
+        S per GPU), one all-reduce of [grad || ELBO]; value = steps/s of that problem.
+        mode 'weak': every GPU evaluates S samples of the SAME minibatch -- the S-shards of one ELBO with S_total = S*world are
+        all-reduced; per-GPU work fixed; value counts (N, S) evaluations/s (= steps/s x world)."""
+        strong = mode == "strong"
+        N_loc = N // world if strong else N
+        m = new_model(True)
+        ctx = m._ensure_ctx(N_loc, S)
+        if not natgrad:
+            m.adam_init(0.01)
+        shard_options(ctx, strong, N_loc)
+        POOL = 8 if CFG_ID != 4 else 2
+        hostX, hostY, devX, devY = minibatch_pool(POOL, strong, N_loc)
+        last = len(cfg['dims']) - 2
 
         def barrier():
             torch.cuda.synchronize()
@@ -247,6 +314,9 @@ def main_b200(args):
 
         def dev_step(i, sync):
             j = i % POOL
+            if natgrad:     # one NatGradOptimizer(gamma).minimize(maxiter=1) on the final layer (always synchronous)
+                return ctx.natgrad_step(devX[j].data_ptr(), devY[j].data_ptr(), N_loc, S, NUM_DATA, 1000 + i, [last], 0.1,
+                                        flags=_lib.FLAG_DEVICE_PTRS)
             return ctx.train_step(devX[j].data_ptr(), devY[j].data_ptr(), N_loc, S, NUM_DATA, 1000 + i,
                                   flags=_lib.FLAG_DEVICE_PTRS | (0 if sync else _lib.FLAG_NO_SYNC), want_elbo=sync)
 
@@ -281,7 +351,7 @@ def main_b200(args):
                 ctx.sync()
         barrier()
         clk = clocks.stop()
-        units = 1 if strong else world        # weak: every rank does a full (N=1000, S=20) evaluation per step
+        units = 1 if strong else world        # weak: every rank does a full (N, S) evaluation per step
         res = {"value": units * K / (tot_ms / 1e3), "ms_per_step": tot_ms / K, "ms_per_step_back_to_back": b2b_ms / K,
                "gpu_launches": int(launches), "clocks": clk, "rows_per_gpu": N_loc * S, "N_loc": N_loc, "e2e": None,
                "stage_ms": None, "roofline": None}
@@ -289,17 +359,18 @@ def main_b200(args):
         if want_e2e:
             Xh = [x.numpy() for x in hostX]
             Yh = [y.numpy() for y in hostY]
+            api_step = (lambda x, y: m.natgrad_step(gamma=0.1, X=x, Y=y)) if natgrad else (lambda x, y: m.train_step(x, y))
             for i in range(3):
-                m.train_step(Xh[i % POOL], Yh[i % POOL])
+                api_step(Xh[i % POOL], Yh[i % POOL])
             barrier()
             t0 = time.perf_counter()
             for i in range(K):
-                m.train_step(Xh[i % POOL], Yh[i % POOL])
+                api_step(Xh[i % POOL], Yh[i % POOL])
             barrier()
             dt = max_over_ranks(time.perf_counter() - t0)
             res["e2e"] = {"value": units * K / dt, "unit": "steps/s",
                           "h2d_bytes_per_step": int(Xh[0].nbytes + Yh[0].nbytes), "d2h_bytes_per_step": 16,
-                          "timing": "host wall clock around K public-API calls (model.train_step), each returning the ELBO"}
+                          "timing": "host wall clock around K public-API calls (model.train_step / natgrad_step), each returning the ELBO"}
         if want_profile:
             try:
                 profile_leg(ctx, dev_step, res, N_loc, tot_ms)
@@ -310,10 +381,9 @@ def main_b200(args):
 
     def profile_leg(ctx, dev_step, res, N_loc, tot_ms):
         """Per-stage device times (eager launches bracketed by CUDA events) -> dominant kernel and its roofline entry."""
-        # ---- per-stage profile (eager launches bracketed by events) -> dominant kernel and its roofline
         ctx.set_option("profile", 1)
         acc = None
-        reps = 5
+        reps = 5 if CFG_ID != 4 else 2
         for i in range(reps + 1):
             dev_step(5000 + i, True)
             p = np.array(ctx.profile())
@@ -322,11 +392,11 @@ def main_b200(args):
         ctx.set_option("profile", 0)
         p = acc / reps
         L = len(WORKLOAD['dims']) - 1
-        names = ["prep(Kuu,chol,KL)", "likelihood", "grad-assembly", "allreduce", "adam"]
+        names = ["prep(Kuu,chol,KL)", "likelihood", "grad-assembly", "allreduce", "tail(result+adam)"]
         for l in range(L):
             names += [f"layer{l + 1}.fwd", f"layer{l + 1}.bwd_rows", f"layer{l + 1}.rowred"]
         fwd_fl, fixed, step_fl = algorithmic_flops(WORKLOAD['dims'], N_loc, WORKLOAD['M'], S)
-        chained = all(p[5 + 3 * l] == 0 for l in range(1, L))     # persistent kernel: all layers' forward in one launch
+        chained = L > 1 and all(p[5 + 3 * l] == 0 for l in range(1, L))     # persistent kernel: all layers' forward in one launch
         if chained:
             names[5] = "fwd_chain(all layers, one persistent launch)"
             fwd_fl = list(fwd_fl)
@@ -339,7 +409,7 @@ def main_b200(args):
         ach = fwd_fl[l] / (p[top] * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and CFG_ID == 3:
             with open(tpath) as f:
                 traffic = json.load(f).get("fwd_chain" if names[top].startswith("fwd_chain") else names[top].split(".")[1])
         res["roofline"] = {
@@ -347,45 +417,95 @@ def main_b200(args):
             "frac": ach / peak_tf32, "traffic": traffic,
             "note": f"algorithmic flops/launch = rows*f(l) = {fwd_fl[l]:.4g} (SURVEY 8(d): each of forward, row-backward "
                     f"and row-reduction kernels of a layer carries rows*f(l)); kernel time from CUDA events around the "
-                    f"launch in an eager (non-graph) pass; peak = {how} bf16_tflops/2 = TF32-dense equivalent (the kernel "
-                    "issues tcgen05 kind::tf32, ~1.3-1.4x the algorithmic MMA work because of the 3xTF32 stages); "
-                    "traffic = dram read+write bytes per launch from the ncu --set full capture summarised in profiles/",
+                    f"launch in an eager (non-graph) pass; peak = {how} bf16_tflops/2 = TF32-dense equivalent (the tcgen05 "
+                    "kernels issue kind::tf32, ~1.3-1.4x the algorithmic MMA work because of the 3xTF32 stages; shapes outside "
+                    "their range run the fp32 SIMT kernels, see DESIGN.md); traffic = dram read+write bytes per launch from the "
+                    "ncu --set full capture summarised in profiles/",
             "step_achieved": step_fl / (tot_ms / K * 1e-3) / 1e12, "step_algorithmic_gflop": step_fl / 1e9}
 
+    def parity_leg():
+        """ELBO of the sharded evaluation (all-reduced inside the step) vs ONE GPU evaluating the same global minibatch with the
+        same Philox seed (draws are keyed by global (s, n): shard-invariant), and -- at N=1 -- vs the float64 oracle on injected
+        draws.  BASELINE.md section 3: parity gates the speed number."""
+        out = {"tolerance_rel": 1e-4}
+        strong = args.scaling == "strong"
+        N_loc = N // world if strong else N
+        _, _, devX, devY = minibatch_pool(1, strong, N_loc)
+        if world > 1:
+            m = new_model(True)
+            ctx = m._ensure_ctx(N_loc, S)
+            shard_options(ctx, strong, N_loc)
+            e_sharded = _elbo_dev(ctx, devX[0], devY[0], N_loc, S, 777)
+            m._ctx.close()
+            if rank == 0:
+                m1 = build_model(prob, device=local_rank)
+                S1 = S if strong else S * world
+                ctx1 = m1._ensure_ctx(N, S1)
+                _, _, fX, fY = minibatch_pool(1, False, N)
+                e_single = _elbo_dev(ctx1, fX[0], fY[0], N, S1, 777)
+                m1._ctx.close()
+                out["sharded_vs_single_gpu"] = {"elbo_sharded": e_sharded, "elbo_single": e_single,
+                                                "rel_err": abs(e_sharded - e_single) / abs(e_single)}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from oracle.problems import build_oracle
+            from workloads import round_f32
+            p32 = round_f32(prob)
+            if CFG_ID == 4:      # one sample shard of the full-size problem (the float64 oracle at S=32 needs > 100 GB)
+                p32 = dict(p32, S=1, zs=[z[:1] for z in p32['zs']])
+            m = build_model(p32, device=local_rank)
+            e_dev = m.compute_log_likelihood(zs=p32['zs'])
+            m._ctx.close()
+            o = build_oracle(p32)
+            o.num_samples = p32['S']
+            e_ref = float(o.compute_log_likelihood(zs=p32['zs']))
+            out["vs_oracle"] = {"elbo_device": e_dev, "elbo_oracle_f64": e_ref, "rel_err": abs(e_dev - e_ref) / abs(e_ref),
+                                "sample": "full workload, injected draws" if CFG_ID != 4 else "S=1 shard of the full-size workload, injected draws"}
+        return out
+
+    def _elbo_dev(ctx, xd, yd, n, s, seed):
+        import ctypes as C
+        e = C.c_double()
+        _lib.check(ctx.lib.dsdgp_elbo(ctx.h, C.c_void_p(xd.data_ptr()), C.c_void_p(yd.data_ptr()), n, s, float(NUM_DATA), None,
+                                      seed, _lib.FLAG_DEVICE_PTRS, C.byref(e)))
+        return e.value
+
+    parity = parity_leg()
     primary = run_mode(args.scaling, want_profile=True, want_e2e=not args.no_e2e)
     other = None
-    if world > 1:
+    if world > 1 and not natgrad:
         other_mode = "strong" if args.scaling == "weak" else "weak"
         o = run_mode(other_mode, want_profile=False, want_e2e=False)
-        other = {"scaling": other_mode, "value": o["value"], "ms_per_step": o["ms_per_step"], "rows_per_gpu": o["rows_per_gpu"]}
+        other = {"scaling": other_mode, "value": o["value"], "ms_per_step": o["ms_per_step"], "rows_per_gpu": o["rows_per_gpu"],
+                 "note": "weak: S=20 per GPU, S_total = 20 x n_gpus; value counts (N, S) evaluations/s" if other_mode == "weak"
+                         else "strong: S_total fixed, rows sharded"}
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sps, done, dt, cores = run_cpu_reference(steps=args.cpu_steps, warmup=1, max_seconds=25)
         cpu = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", **run_cpu_reference.last_stats,
-               "sample": f"{done} full steps ({dt:.1f} s) of the same workload: reference restatement (torch-CPU float64, "
-                         "reference-faithful tiling, autograd backward, Adam), not TF 1.8"}
+               "sample": f"{done} steps ({dt:.1f} s) of the same workload{run_cpu_reference.sample_note}: reference restatement "
+                         "(torch-CPU float64, reference-faithful tiling, autograd backward, Adam), not TF 1.8"}
 
+    bad = [k for k, v in parity.items() if isinstance(v, dict) and not (v["rel_err"] <= parity["tolerance_rel"])]
     if rank == 0:
         weak = args.scaling == "weak"
         out = {
             "metric": METRIC, "value": primary["value"], "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": primary["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]: 5-layer RBF DGP N=1000 M=100 S=20 dims 8-8-8-8-8-1", **WORKLOAD,
-                       "rows_per_gpu": primary["rows_per_gpu"],
-                       "parallelism": (f"dp{world}: S sharded -- every GPU draws S=20 samples of the N=1000 minibatch, S_total={S * world}, "
-                                       "one NCCL all-reduce of [grad || ELBO]; value counts (N=1000,S=20) evaluations/s"
-                                       if weak else
-                                       f"dp{world}: S_total=20 fixed, the S*N sample rows sharded ({primary['N_loc']} minibatch rows x all S per GPU), "
-                                       "one NCCL all-reduce of [grad || ELBO]"),
-                       "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events on the launch stream",
-                       "precision": "tcgen05 kind::tf32 (3xTF32 for the whitened projections / solves, 1xTF32 elsewhere), "
-                                    "fp32 epilogues, fp64 MxM factorisation + KL"},
+            "dtype": "tf32", "data": "synthetic", "config": config_dict(),
+            "run": {"rows_per_gpu": primary["rows_per_gpu"],
+                    "parallelism": (f"dp{world}: S sharded -- every GPU draws S={S} samples of the N={N} minibatch, S_total={S * world}, "
+                                    f"one NCCL all-reduce of [grad || ELBO]; value counts (N={N},S={S}) evaluations/s"
+                                    if weak else
+                                    f"dp{world}: S_total={S} fixed, the S*N sample rows sharded ({primary['N_loc']} minibatch rows x all S per GPU), "
+                                    "one NCCL all-reduce of [grad || ELBO]"),
+                    "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events on the launch stream",
+                    "precision": "tcgen05 kind::tf32 (3xTF32 for the whitened projections / solves, 1xTF32 elsewhere), "
+                                 "fp32 epilogues, fp64 MxM factorisation + KL"},
             "ms_per_step_back_to_back": primary["ms_per_step_back_to_back"], "gpu_launches": primary["gpu_launches"],
             "clocks": primary["clocks"], "e2e": primary["e2e"], "roofline": primary["roofline"], "cpu_baseline": cpu,
-            "stage_ms": primary["stage_ms"], "other_scaling": other,
+            "stage_ms": primary["stage_ms"], "other_scaling": other, "parity": parity,
         }
         if primary.get("roofline_error"):
             out["roofline_error"] = primary["roofline_error"]
@@ -393,6 +513,8 @@ def main_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if bad:
+        raise SystemExit(f"parity gate failed: {bad} beyond {parity['tolerance_rel']}")
 
 
 if __name__ == "__main__":
@@ -401,11 +523,15 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=20)
     a = ap.parse_args()
+    select_config(a.config)
+    if a.config == 4:
+        a.steps = min(a.steps, 10); a.cpu_steps = min(a.cpu_steps, 3)      # (a step is ~100x the north-star's)
     if a.impl == "reference":
         if a.steps > 30:
             a.steps = 30          # each step is a bounded sample: one full CPU step (~0.5 s); keep the run to minutes

@@ -9,20 +9,7 @@ from doubly_stochastic_dgp.likelihoods import Gaussian, MultiClass
 from doubly_stochastic_dgp.mean_functions import Identity, Linear, Zero
 
 
-def build_model(prob, **kw):
-    settings.jitter = prob['jitter']
-    kcls = RBF if prob['kern'] == 'rbf' else Matern52
-    layers = []
-    for lay in prob['layers']:
-        kern = kcls(lay['din'], variance=lay['var'], lengthscales=lay['ls'])
-        mf = {'zero': Zero, 'identity': Identity}.get(lay['mean'], None)
-        mf = mf() if mf else Linear(lay['W'])
-        layer = SVGP_Layer(kern, lay['Z'], lay['dout'], mf, white=lay['white'])
-        layer.q_mu = lay['q_mu']
-        layer.q_sqrt = lay['q_sqrt']
-        layers.append(layer)
-    lik = MultiClass(prob['n_classes']) if prob['n_classes'] else Gaussian(prob['lik_var'])
-    return DGP_Base(prob['X'], prob['Y'], lik, layers, num_samples=prob['S'], num_data=prob['num_data'], **kw)
+from workloads import build_model  # noqa: F401,E402
 
 
 def rel_err(a, b):

@@ -1,8 +1,8 @@
 import sys
 sys.path[:0]=['/root/repo','/root/repo/doubly-stochastic-dgp_b200']
 import numpy as np
-from tests.synth import make_problem, round_f32
-from tests.gpu_common import build_model
+from workloads import make_problem, round_f32
+from workloads import build_model
 for kw in [dict(dims=[8,8,1],N=150,M=100,S=2), dict(dims=[3,3,2],N=70,M=37,S=2)]:
     prob=round_f32(make_problem(seed=5,inner_q_scale=0.3,num_data=500,**kw))
     res={}

@@ -5,8 +5,8 @@ sys.path[:0] = ['/root/repo', '/root/repo/doubly-stochastic-dgp_b200']
 import numpy as np
 import torch
 from doubly_stochastic_dgp import _lib
-from tests.gpu_common import build_model
-from tests.synth import make_problem
+from workloads import build_model
+from workloads import make_problem
 
 prob = make_problem(seed=3000, dims=[8, 8, 8, 8, 8, 1], N=1000, M=100, S=20, num_data=8192)
 X = torch.from_numpy(np.float32(prob['X'])).cuda()
