@@ -54,7 +54,7 @@ static int nccl_load() {
 // ---- context ------------------------------------------------------------------------------------------------------
 enum { MODE_PROPAGATE = 0, MODE_ELBO = 1, MODE_GRAD = 2, MODE_TRAIN = 3 };
 
-struct LayerOff { size_t Z, q_mu, q_sqrt, ls, var; int n_ls; };
+struct LayerOff { size_t Z, q_mu, q_sqrt, ls, var, wvar; int n_ls; };
 
 struct dsdgp_ctx {
     dsdgp_desc desc;
@@ -117,6 +117,7 @@ struct dsdgp_ctx {
     bool use_graph;
     int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
     int dbg_layer; long long* dbg_buf;
+    int g2_passes;                   // 0: automatic (per layer, from the size of q_sqrt), 1 / 3: forced
     unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain;
     float* wpack[DSDGP_MAX_LAYERS];
     std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
@@ -137,6 +138,7 @@ static size_t field_count(const dsdgp_ctx* c, int layer, int field) {
         case DSDGP_F_Q_SQRT: return (size_t)d.D_out * d.M * d.M;
         case DSDGP_F_LENGTHSCALES: return d.ard ? d.D_in : 1;
         case DSDGP_F_VARIANCE: return 1;
+        case DSDGP_F_WHITE_VARIANCE: return 1;
         case DSDGP_F_MEAN_W: return (size_t)d.D_in * d.D_out;
         case DSDGP_F_MEAN_B: return d.D_out;
     }
@@ -151,6 +153,7 @@ static long long field_offset(const dsdgp_ctx* c, int layer, int field) {
         case DSDGP_F_Q_SQRT: return o.q_sqrt;
         case DSDGP_F_LENGTHSCALES: return o.ls;
         case DSDGP_F_VARIANCE: return o.var;
+        case DSDGP_F_WHITE_VARIANCE: return o.wvar;
     }
     return -1;
 }
@@ -171,8 +174,13 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     for (int l = 0; l < desc->L; ++l) {
         const dsdgp_layer_desc& d = desc->layers[l];
         if (d.M < 1 || d.D_in < 1 || d.D_out < 1) return set_err(DSDGP_ERR_INVALID, "layer %d: bad sizes", l);
-        if (l > 0 && desc->layers[l - 1].D_out != d.D_in)
-            return set_err(DSDGP_ERR_INVALID, "layer %d: D_in=%d != previous D_out=%d", l, d.D_in, desc->layers[l - 1].D_out);
+        if (d.input_prop_dim < 0 || d.input_prop_dim > d.D_in)
+            return set_err(DSDGP_ERR_INVALID, "layer %d: input_prop_dim=%d outside [0, D_in=%d]", l, d.input_prop_dim, d.D_in);
+        if (l == desc->L - 1 && d.input_prop_dim)
+            return set_err(DSDGP_ERR_INVALID, "the final layer cannot propagate inputs (its output is the likelihood's F)");
+        if (l > 0 && desc->layers[l - 1].D_out + desc->layers[l - 1].input_prop_dim != d.D_in)
+            return set_err(DSDGP_ERR_INVALID, "layer %d: D_in=%d != previous D_out=%d + input_prop_dim=%d", l, d.D_in,
+                           desc->layers[l - 1].D_out, desc->layers[l - 1].input_prop_dim);
         if (d.mean == DSDGP_MEAN_IDENTITY && d.D_in != d.D_out)
             return set_err(DSDGP_ERR_INVALID, "layer %d: Identity mean needs D_in == D_out", l);
         if (d.kernel != DSDGP_KERN_RBF && d.kernel != DSDGP_KERN_MATERN52)
@@ -186,6 +194,8 @@ int dsdgp_create(dsdgp_ctx** out, const dsdgp_desc* desc) {
     } else if (desc->likelihood == DSDGP_LIK_MULTICLASS) {
         if (desc->num_classes != last.D_out || desc->num_classes < 2 || desc->num_classes > 32)
             return set_err(DSDGP_ERR_INVALID, "MultiClass: num_classes=%d must equal last D_out=%d (2..32)", desc->num_classes, last.D_out);
+    } else if (desc->likelihood == DSDGP_LIK_BERNOULLI) {
+        if (desc->D_y != last.D_out) return set_err(DSDGP_ERR_INVALID, "Bernoulli likelihood: D_y=%d != last D_out=%d", desc->D_y, last.D_out);
     } else return set_err(DSDGP_ERR_UNSUPPORTED, "likelihood %d", desc->likelihood);
 
     CK(cudaSetDevice(desc->device));
@@ -242,6 +252,7 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
         o.n_ls = d.ard ? d.D_in : 1;
         o.ls = n; n += o.n_ls;
         o.var = n; n += 1;
+        o.wvar = n; n += 1;
         n = (n + 3) & ~(size_t)3;
     }
     c->off_likvar = n; n += 1;
@@ -265,6 +276,7 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
                     }
             for (int i = 0; i < o.n_ls; ++i) { kinds[o.ls + i] = 1; init[o.ls + i] = 1.f; }
             kinds[o.var] = 1; init[o.var] = 1.f;
+            kinds[o.wvar] = d.kernel_white ? 1 : 4; init[o.wvar] = d.kernel_white ? 1.f : 0.f;      // White(variance=1) default
         }
         kinds[c->off_likvar] = desc->likelihood == DSDGP_LIK_GAUSSIAN ? 1 : 4;
         init[c->off_likvar] = 1.f;
@@ -305,7 +317,7 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
             size_t Rl = (l == 0) ? (size_t)desc->N_max : Rmax;
             CK(dmalloc(&c->U[l], Rl * d.M));
             CK(dmalloc(&c->Fmean[l], Rl * d.D_out)); CK(dmalloc(&c->Fvar[l], Rl * d.D_out));
-            CK(dmalloc(&c->F[l], Rmax * d.D_out)); CK(dmalloc(&c->zs[l], Rmax * d.D_out));
+            CK(dmalloc(&c->F[l], Rmax * (d.D_out + d.input_prop_dim))); CK(dmalloc(&c->zs[l], Rmax * d.D_out));
             CK(dmalloc(&c->xbar[l], Rl * d.D_in));
             CK(dmalloc(&c->mubar[l], Rl * d.D_out)); CK(dmalloc(&c->vbar[l], Rl * d.D_out)); CK(dmalloc(&c->Wbuf[l], Rl * d.M));
             CK(dmalloc(&c->meanW[l], (size_t)d.D_in * d.D_out)); CK(dmalloc(&c->meanB[l], (size_t)d.D_out));
@@ -314,11 +326,11 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
             if (d.M <= 128 && d.M >= 8 && d.D_in <= 16 && d.D_out <= 32) CK(dmalloc(&c->wpack[l], tc_fwd_pack_bytes(d.M, d.D_out, d.white) / sizeof(float)));
             P.wpack_fwd = c->wpack[l];
             P.M = d.M; P.Din = d.D_in; P.Dout = d.D_out; P.kern = d.kernel; P.ard = d.ard; P.white = d.white;
-            P.mean = d.mean; P.n_ls = o.n_ls; P.idx = l;
+            P.mean = d.mean; P.n_ls = o.n_ls; P.idx = l; P.kwhite = d.kernel_white ? 1 : 0; P.ipd = d.input_prop_dim;
             P.Z = c->params + o.Z; P.q_mu = c->params + o.q_mu; P.q_sqrt = c->params + o.q_sqrt;
-            P.ls = c->params + o.ls; P.var = c->params + o.var; P.meanW = c->meanW[l]; P.meanB = c->meanB[l];
+            P.ls = c->params + o.ls; P.var = c->params + o.var; P.wvar = c->params + o.wvar; P.meanW = c->meanW[l]; P.meanB = c->meanB[l];
             P.gZ = c->grads + o.Z; P.gq_mu = c->grads + o.q_mu; P.gq_sqrt = c->grads + o.q_sqrt;
-            P.gls = c->grads + o.ls; P.gvar = c->grads + o.var;
+            P.gls = c->grads + o.ls; P.gvar = c->grads + o.var; P.gwvar = c->grads + o.wvar;
             P.K64 = p64; P.Lu64 = p64 + mm; P.Linv64 = p64 + 2 * mm; P.Kinv64 = p64 + 3 * mm; P.Ssum64 = p64 + 4 * mm;
             P.T1 = p64 + 5 * mm; P.KbarKL = p64 + 6 * mm; P.Gsym = p64 + 7 * mm; P.scal = p64 + 8 * mm; p64 += 8 * mm + 8;
             P.Linv32 = p32; P.LinvT32 = p32 + mm; P.q_sqrtT = p32 + 2 * mm; p32 += 2 * mm + (size_t)d.D_out * mm;
@@ -337,6 +349,7 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
     c->s_offset_opt = 0; c->s_world_opt = 1;
     c->use_graph = true; c->nlaunch = 0; c->last_ms = 0.f; c->path = 1;
     c->dbg_layer = -1; CK(dmalloc(&c->dbg_buf, 64));
+    c->g2_passes = 0;
     c->chain_max_tiles = (int)((Rmax + 127) / 128);
     CK(dmalloc(&c->chain_flags, (size_t)2 * DSDGP_MAX_LAYERS * c->chain_max_tiles));
     c->epoch = 0; c->chain = true;
@@ -376,7 +389,9 @@ static int check_field(dsdgp_ctx* c, int layer, int field, size_t n) {
         return 0;
     }
     if (layer < 0 || layer >= c->desc.L) return set_err(DSDGP_ERR_INVALID, "layer %d out of range", layer);
-    if (field < 0 || field > DSDGP_F_MEAN_B) return set_err(DSDGP_ERR_INVALID, "field %d unknown", field);
+    if (field < 0 || (field > DSDGP_F_MEAN_B && field != DSDGP_F_WHITE_VARIANCE)) return set_err(DSDGP_ERR_INVALID, "field %d unknown", field);
+    if (field == DSDGP_F_WHITE_VARIANCE && !c->desc.layers[layer].kernel_white)
+        return set_err(DSDGP_ERR_INVALID, "layer %d has no White kernel term", layer);
     size_t want = field_count(c, layer, field);
     if (n != want) return set_err(DSDGP_ERR_INVALID, "layer %d field %d: n=%zu, expected %zu", layer, field, n, want);
     return 0;
@@ -398,7 +413,7 @@ int dsdgp_set_param(dsdgp_ctx* c, int layer, int field, const double* host, size
             int M = c->desc.layers[layer].M;
             for (size_t k = 0; k < n; ++k) { int i = (k / M) % M, j = k % M; if (j > i) tmp[k] = 0.f; }
         }
-        if (field == DSDGP_F_LENGTHSCALES || field == DSDGP_F_VARIANCE || field == DSDGP_F_LIK_VARIANCE)
+        if (field == DSDGP_F_LENGTHSCALES || field == DSDGP_F_VARIANCE || field == DSDGP_F_LIK_VARIANCE || field == DSDGP_F_WHITE_VARIANCE)
             for (size_t k = 0; k < n; ++k)
                 if (!(tmp[k] > 0.f)) return set_err(DSDGP_ERR_INVALID, "positive parameter got %g", (double)tmp[k]);
     }
@@ -455,14 +470,14 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     if (split_pack) {       // the q_sqrt weight tiles depend on parameters only: pack them beside the factorisation
         CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 2], st));
         CK(cudaStreamWaitEvent(c->stream2, c->ev_dag[2 * DSDGP_MAX_LAYERS + 2], 0));
-        launch_pack_fwd(c->ls, 2, c->stream2, nl);
+        launch_pack_fwd(c->ls, 2, c->acc, c->stream2, nl);
         CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 4], c->stream2));
     }
     launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, st, side ? c->stream2 : st, c->ev_dag[0], nl);
     if (split_pack) {
-        launch_pack_fwd(c->ls, 1, st, nl);
+        launch_pack_fwd(c->ls, 1, c->acc, st, nl);
         CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 4], 0));
-    } else if (any_tc) launch_pack_fwd(c->ls, 0, st, nl);
+    } else if (any_tc) launch_pack_fwd(c->ls, 0, c->acc, st, nl);
     PROF_END(0);
     // forward
     const bool chain = c->chain && c->path == 1 && mode != MODE_PROPAGATE && tc_chain_fwd_supported(c->ls);
@@ -480,6 +495,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         a.z = (zmask >> l) & 1u ? c->zs[l] : nullptr;
         a.z_out = (a.z == nullptr && a.F != nullptr && mode >= MODE_GRAD) ? c->zs[l] : nullptr;
         a.dbg = (c->dbg_layer == l) ? c->dbg_buf : nullptr;
+        a.acc = c->acc; a.g2_passes = c->g2_passes;
         if (chain) {
             fc.a[l] = a; fc.tiles[l] = (a.R + 127) / 128; fc.base[l + 1] = fc.base[l] + fc.tiles[l];
             continue;
@@ -502,6 +518,9 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     if (c->desc.likelihood == DSDGP_LIK_GAUSSIAN)
         launch_lik_gaussian(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.D_y, c->params + c->off_likvar,
                             c->mubar[L - 1], c->vbar[L - 1], c->acc, c->sa_dev, grad, sw, st, nl);
+    else if (c->desc.likelihood == DSDGP_LIK_BERNOULLI)
+        launch_lik_bernoulli(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.D_y, c->mubar[L - 1], c->vbar[L - 1],
+                             c->acc, c->sa_dev, grad, sw, st, nl);
     else
         launch_lik_multiclass(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.num_classes, c->mubar[L - 1],
                               c->vbar[L - 1], c->acc, c->sa_dev, grad, sw, st, nl);
@@ -673,7 +692,8 @@ int dsdgp_propagate(dsdgp_ctx* c, const float* X, int N, int S, const float* con
     cudaMemcpyKind kind = (flags & DSDGP_FLAG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     for (int l = 0; l < L; ++l) {
         const size_t D = c->desc.layers[l].D_out, per = (size_t)N * D;
-        if (Fs && Fs[l]) CK(cudaMemcpyAsync(Fs[l], c->F[l], (size_t)S * per * sizeof(float), kind, c->stream));
+        // Fs: (S, N, input_prop_dim + D_out) -- the propagated inputs sit in front of the samples (layers.py:105-117)
+        if (Fs && Fs[l]) CK(cudaMemcpyAsync(Fs[l], c->F[l], (size_t)S * N * (D + c->desc.layers[l].input_prop_dim) * sizeof(float), kind, c->stream));
         const bool dedup = (l == 0);        // layer 1 holds N rows: the reference returns S identical copies (dgp.py:63)
         for (int which = 0; which < 2; ++which) {
             float* const* outp = which ? Fvars : Fmeans;
@@ -701,6 +721,7 @@ int dsdgp_propagate_full_cov(dsdgp_ctx* c, const float* X, int N, int S, const f
     for (int l = 0; l < L; ++l) {
         const dsdgp_layer_desc& d = c->desc.layers[l];
         if ((long long)S * d.D_out > 65535) return set_err(DSDGP_ERR_UNSUPPORTED, "full_cov: S*D_out=%lld > 65535", (long long)S * d.D_out);
+        if (d.input_prop_dim) return set_err(DSDGP_ERR_UNSUPPORTED, "full_cov with input_prop_dim (layers.py:112-115) is not on the device path");
         need = max(need, full_cov_ws_doubles(d.M, d.D_out, Dio, N, S));
         need_out = max(need_out, (size_t)S * N * N * d.D_out + 2 * (size_t)S * N * d.D_out);
     }
@@ -785,7 +806,7 @@ static int predict_common(dsdgp_ctx* c, const float* X, const float* Y, int N, i
             else CK(cudaMemcpyAsync(dst, src, (size_t)S * per * sizeof(float), kind, c->stream));
         }
     } else {
-        const int Do = c->desc.likelihood == DSDGP_LIK_GAUSSIAN ? D : 1;
+        const int Do = c->desc.likelihood == DSDGP_LIK_MULTICLASS ? 1 : D;
         launch_predict_density(c->desc.likelihood, c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, S, N, D, dedup ? 1 : 0, likvar,
                                c->mubar[L - 1], c->stream, &c->nlaunch);
         CK(cudaMemcpyAsync(out0, c->mubar[L - 1], (size_t)N * Do * sizeof(float), kind, c->stream));
@@ -801,6 +822,49 @@ int dsdgp_predict_y(dsdgp_ctx* c, const float* X, int N, int S, const float* con
 int dsdgp_predict_density(dsdgp_ctx* c, const float* X, const float* Y, int N, int S, const float* const* zs, uint64_t seed,
                           float* out, unsigned flags) {
     return predict_common(c, X, Y, N, S, zs, seed, flags, out, nullptr, true);
+}
+
+// BroadcastingLikelihood methods on caller-supplied marginals (utils.py:88-121).  The last layer's activation buffers are
+// the staging area: Fmean/Fvar <- inputs, F <- Y tiled over S, mubar/vbar <- outputs.
+int dsdgp_likelihood_apply(dsdgp_ctx* c, int what, const float* Fmu, const float* Fvar, const float* Y, int S, int N,
+                           float* out0, float* out1, unsigned flags) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    if (what < DSDGP_LIK_VE || what > DSDGP_LIK_PREDICT_DENSITY) return set_err(DSDGP_ERR_INVALID, "what=%d", what);
+    if (!Fmu || !Fvar || !out0 || (what == DSDGP_LIK_PREDICT_MEAN_AND_VAR && !out1) || (what != DSDGP_LIK_PREDICT_MEAN_AND_VAR && !Y))
+        return set_err(DSDGP_ERR_INVALID, "null argument");
+    const dsdgp_desc& d = c->desc;
+    const int L = d.L, D = d.layers[L - 1].D_out, lik = d.likelihood;
+    const size_t R = (size_t)S * N, Rmax = (size_t)d.N_max * d.S_max;
+    if (S < 1 || N < 1 || R > Rmax) return set_err(DSDGP_ERR_INVALID, "S*N=%zu outside [1, N_max*S_max=%zu]", R, Rmax);
+    if (L == 1 && R > (size_t)d.N_max) return set_err(DSDGP_ERR_INVALID, "single-layer context: S*N=%zu > N_max=%d", R, d.N_max);
+    CK(cudaSetDevice(d.device));
+    cudaStream_t st = c->stream;
+    const cudaMemcpyKind in = (flags & DSDGP_FLAG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind outk = (flags & DSDGP_FLAG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CK(cudaMemcpyAsync(c->Fmean[L - 1], Fmu, R * D * sizeof(float), in, st));
+    CK(cudaMemcpyAsync(c->Fvar[L - 1], Fvar, R * D * sizeof(float), in, st));
+    const float* likvar = c->params + c->off_likvar;
+    const int Do = lik == DSDGP_LIK_MULTICLASS ? 1 : D;
+    if (what == DSDGP_LIK_PREDICT_MEAN_AND_VAR) {
+        launch_predict_y(lik, c->Fmean[L - 1], c->Fvar[L - 1], (int)R, D, likvar, c->mubar[L - 1], c->vbar[L - 1], st, &c->nlaunch);
+        CK(cudaMemcpyAsync(out0, c->mubar[L - 1], R * D * sizeof(float), outk, st));
+        CK(cudaMemcpyAsync(out1, c->vbar[L - 1], R * D * sizeof(float), outk, st));
+    } else {
+        float* Yt = c->F[L - 1];          // (S, N, D_y): the first block is Y itself
+        CK(cudaMemcpyAsync(Yt, Y, (size_t)N * d.D_y * sizeof(float), in, st));
+        if (what == DSDGP_LIK_VE) {
+            launch_ve_elem(lik, c->Fmean[L - 1], c->Fvar[L - 1], Yt, (int)R, N, D, likvar, c->mubar[L - 1], st, &c->nlaunch);
+        } else {
+            // per-sample densities: the streaming log-mean-exp kernel with one "sample" per row; Y tiled over S (utils.py:77)
+            for (int s = 1; s < S; ++s)
+                CK(cudaMemcpyAsync(Yt + (size_t)s * N * d.D_y, Yt, (size_t)N * d.D_y * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            launch_predict_density(lik, c->Fmean[L - 1], c->Fvar[L - 1], Yt, 1, (int)R, D, 0, likvar, c->mubar[L - 1], st, &c->nlaunch);
+        }
+        CK(cudaMemcpyAsync(out0, c->mubar[L - 1], R * Do * sizeof(float), outk, st));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return DSDGP_OK;
 }
 
 static int elbo_common(dsdgp_ctx* c, int mode, const float* X, const float* Y, int N, int S, double num_data,
@@ -873,7 +937,8 @@ int dsdgp_set_trainable(dsdgp_ctx* c, int layer, int field, int trainable) {
         return DSDGP_OK;
     }
     if (field != DSDGP_F_LIK_VARIANCE && (layer < 0 || layer >= c->desc.L)) return set_err(DSDGP_ERR_INVALID, "layer %d out of range", layer);
-    if (field < 0 || field > DSDGP_F_LIK_VARIANCE) return set_err(DSDGP_ERR_INVALID, "field %d unknown", field);
+    if (field < 0 || field > DSDGP_F_WHITE_VARIANCE) return set_err(DSDGP_ERR_INVALID, "field %d unknown", field);
+    if (field == DSDGP_F_WHITE_VARIANCE && !c->desc.layers[layer].kernel_white) return DSDGP_OK;
     if (field == DSDGP_F_LIK_VARIANCE && c->desc.likelihood != DSDGP_LIK_GAUSSIAN) return DSDGP_OK;
     CK(cudaSetDevice(c->desc.device));
     const size_t o = (size_t)field_offset(c, layer, field), n = field_count(c, layer, field);
@@ -1090,6 +1155,13 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
         const int v = (int)value;
         if (n == "prep_algo") { if (v < 0 || v > 2) return set_err(DSDGP_ERR_INVALID, "prep_algo must be 0, 1 or 2"); c->ls.prep_algo = v; }
         else { if (v != 256 && v != 512 && v != 1024) return set_err(DSDGP_ERR_INVALID, "prep_threads must be 256, 512 or 1024"); c->ls.prep_threads = v; }
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    }
+    else if (n == "g2_passes") {      // TF32 passes of the forward variance product c_d = L_d^T u: 0 automatic, 1, 3
+        const int v = (int)value;
+        if (v < 0 || v > 3) return set_err(DSDGP_ERR_INVALID, "g2_passes must be 0 (automatic), 1, 2 or 3");
+        c->g2_passes = v;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     }

@@ -13,10 +13,13 @@
 // Per-layer view handed to kernels by value.
 struct LayerDev {
     int M, Din, Dout, kern, ard, white, mean, n_ls, idx;
-    // parameters (fp32, device)
-    const float *Z, *q_mu, *q_sqrt, *ls, *var, *meanW, *meanB;
+    int kwhite;     // 1: the layer kernel is Sum(kernel, White) -- wvar is a trainable parameter
+    int ipd;        // input_prop_dim (layers.py:105-117): this layer's F rows are [X[:ipd] | samples], row stride ipd + Dout
+    // parameters (fp32, device).  wvar: variance of the White term of Sum(kernel, White) (0 and fixed when there is none):
+    // Kuu += wvar I, Kdiag += wvar, K(Z, X) unchanged (gpflow White.K(X, X2) = 0)
+    const float *Z, *q_mu, *q_sqrt, *ls, *var, *wvar, *meanW, *meanB;
     // gradient destinations (fp32, same layout as the parameters)
-    float *gZ, *gq_mu, *gq_sqrt, *gls, *gvar;
+    float *gZ, *gq_mu, *gq_sqrt, *gls, *gvar, *gwvar;
     // per-step small-matrix results
     double *K64, *Lu64, *Linv64, *Kinv64, *Ssum64, *T1, *KbarKL, *Gsym;   // M x M each
     float *Linv32, *LinvT32, *q_sqrtT;                                    // M x M, M x M, D x M x M
@@ -55,6 +58,9 @@ struct Accum {             // fp64 scalar accumulators (zeroed every step)
     double elbo;           // lik - kl_weight*kl   (after all-reduce: the ELBO)
     int status;            // nonzero: Cholesky failed (layer index + 1)
     int pad;
+    // per layer: 1 when some |q_sqrt| entry exceeds 1e-3 sqrt(kernel variance) -- then |L_d^T u|^2 is not negligible in the
+    // conditional variance and the forward kernel runs that product as 3xTF32 instead of 1xTF32 (set by k_pack_fwd)
+    int g2flag[DSDGP_MAX_LAYERS];
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -180,6 +186,8 @@ struct FwdArgs {
     float jitter;
     const StepArgs* sa;
     long long* dbg;       // optional clock64() stamps of CTA 0 (diagnostics), else NULL
+    const Accum* acc;     // g2flag (see Accum)
+    int g2_passes;        // 0: per layer from acc->g2flag; 1 / 3: forced (option "g2_passes")
 };
 
 // all layers' forward tiles as one persistent launch (layer_tc.cu k_chain_fwd_tc)
@@ -221,13 +229,18 @@ void launch_lik_gaussian(const float* Fmean, const float* Fvar, const float* Y, 
 void launch_lik_multiclass(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int K,
                            float* mubar, float* vbar, Accum* acc, const StepArgs* sa, int want_grad,
                            const float* sample_w, cudaStream_t st, long long* nlaunch);
+void launch_lik_bernoulli(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy, float* mubar,
+                          float* vbar, Accum* acc, const StepArgs* sa, int want_grad, const float* sample_w,
+                          cudaStream_t st, long long* nlaunch);
+void launch_ve_elem(int lik, const float* Fmean, const float* Fvar, const float* Y, int R, int N, int D, const float* lik_var,
+                    float* out, cudaStream_t st, long long* nlaunch);
 void launch_elbo_finish(Accum* acc, const StepArgs* sa, float* glikvar, float* elbo_hi_lo, cudaStream_t st, long long* nlaunch);
 void launch_result(const Accum* acc, const float* elbo_hi_lo, int use_hi_lo, double* result, cudaStream_t st, long long* nlaunch);
 cudaError_t layer_kernels_init();
 cudaError_t layer_tc_init();
 bool tc_fwd_supported(const LayerDev& P);
 size_t tc_fwd_pack_bytes(int M, int D, int white);
-void launch_pack_fwd(const LayerSet& ls, int part, cudaStream_t st, long long* nlaunch);
+void launch_pack_fwd(const LayerSet& ls, int part, Accum* acc, cudaStream_t st, long long* nlaunch);
 void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nlaunch);
 bool tc_chain_fwd_supported(const LayerSet& ls);
 void launch_chain_fwd_tc(const LayerSet& ls, const FwdChain& fc, int num_sms, cudaStream_t st, long long* nlaunch);

@@ -35,7 +35,11 @@ __global__ void k_fc_gram(LayerDev P, const double* __restrict__ Xin, size_t xs,
         double k, kp;
         kern_eval_d(P.kern, r2, var, k, kp);
         if (idx < nuf) Kuf[(size_t)s * nuf + idx] = k;
-        else Kff[(size_t)s * nff + (idx - nuf)] = k;
+        else {
+            const size_t e = idx - nuf;
+            if (e / N == e % N) k += (double)P.wvar[0];        // White.K(X) = variance_w I
+            Kff[(size_t)s * nff + e] = k;
+        }
     }
 }
 

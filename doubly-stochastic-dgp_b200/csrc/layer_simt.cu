@@ -65,7 +65,7 @@ size_t fwd_smem_bytes(int M, int Dout, int TR) {
 }
 size_t bwd_smem_bytes(int M, int Dout, int TR) {
     size_t Mp = pad16(M), TRS = TR + 4;
-    return sizeof(float) * (5 * Mp * TRS + KB * NCH + QC * TRS + 2 * QC + 2 * (size_t)TR * Dout + TR + 8);
+    return sizeof(float) * (5 * Mp * TRS + KB * NCH + QC * TRS + 2 * QC + 2 * (size_t)TR * Dout + TR + 16);
 }
 
 // Gram stage: kT[i][r] = k(z_i, x_r) (and optionally kpT = dk/dr2), x rows row0.. from Xin.
@@ -201,9 +201,19 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_fwd(LayerDev P, FwdArgs a) {
     }
     __syncthreads();
     // mean function, variance, draw
-    const float var0 = P.var[0], jit = a.jitter;
+    const float var0 = P.var[0] + P.wvar[0], jit = a.jitter;      // Kdiag of Sum(kernel, White)
     const unsigned long long seed = a.sa->seed;
     const int noff = a.sa->n_offset, soff = a.sa->s_offset;
+    const int ipd = P.ipd, FS = ipd + D;                          // F rows: [X[:ipd] | samples] (layers.py:105-117)
+    if (a.F && ipd > 0) {
+        for (int e = tid; e < TR * ipd; e += DSDGP_NT) {
+            const int q = e % ipd, r = e / ipd, row = row0 + r;
+            if (row >= R) continue;
+            const float xv = a.Xin[(size_t)row * Din + q];
+            if (a.S_rep == 1) a.F[(size_t)row * FS + q] = xv;
+            else for (int s = 0; s < a.S_rep; ++s) a.F[((size_t)s * a.N + row) * FS + q] = xv;
+        }
+    }
     for (int e = tid; e < TR * D; e += DSDGP_NT) {
         int d = e % D, r = e / D, row = row0 + r;
         if (row >= R) continue;
@@ -223,13 +233,13 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_fwd(LayerDev P, FwdArgs a) {
                 int s = row / a.N, n = row % a.N;
                 float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, s + soff, n + noff, d);
                 if (a.z_out) a.z_out[(size_t)row * D + d] = z;
-                a.F[(size_t)row * D + d] = fmaf(z, sd, mean);
+                a.F[(size_t)row * FS + ipd + d] = fmaf(z, sd, mean);
             } else {
                 for (int s = 0; s < a.S_rep; ++s) {
                     size_t o = ((size_t)s * a.N + row) * D + d;
                     float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, s + soff, row + noff, d);
                     if (a.z_out) a.z_out[o] = z;
-                    a.F[o] = fmaf(z, sd, mean);
+                    a.F[((size_t)s * a.N + row) * FS + ipd + d] = fmaf(z, sd, mean);
                 }
             }
         }
@@ -258,7 +268,8 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_bwd(LayerDev P, BwdArgs a) {
     float* mub = lsacc + QC;           // [TR][D]
     float* vb = mub + TR * D;          // [TR][D]
     float* vs = vb + TR * D;           // [TR]
-    float* red = vs + TR;              // [8]
+    float* red = vs + TR;              // [16]
+    const int ipd = P.ipd, FS = ipd + D;       // upstream gradient rows: [d/dX[:ipd] | d/dF] (layers.py:105-117)
 
     const float jit = a.jitter;
     const unsigned long long seed = a.sa->seed;
@@ -273,14 +284,14 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_bwd(LayerDev P, BwdArgs a) {
                 float sd = sqrtf(fmaxf(a.Fvar[(size_t)row * D + d] + jit, 1e-30f));
                 if (a.S_rep == 1) {
                     int s = row / a.N, n = row % a.N;
-                    float fb = a.fbar[(size_t)row * D + d];
+                    float fb = a.fbar[(size_t)row * FS + ipd + d];
                     float z = a.z ? a.z[(size_t)row * D + d] : dsdgp_normal(seed, P.idx, s + soff, n + noff, d);
                     m = fb; v = fb * z / (2.f * sd);
                 } else {
                     float sz = 0.f;
                     for (int s = 0; s < a.S_rep; ++s) {
                         size_t o = ((size_t)s * a.N + row) * D + d;
-                        float fb = a.fbar[o];
+                        float fb = a.fbar[((size_t)s * a.N + row) * FS + ipd + d];
                         float z = a.z ? a.z[o] : dsdgp_normal(seed, P.idx, s + soff, row + noff, d);
                         m += fb; sz = fmaf(fb, z, sz);
                     }
@@ -409,14 +420,17 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_bwd(LayerDev P, BwdArgs a) {
         s2 = fmaf(kb * kT[i * TRS + r], inv_var, s2);
         kpT[i * TRS + r] = 2.f * kb * kpT[i * TRS + r];
     }
-    for (int e = tid; e < TR * D; e += DSDGP_NT) s2 += vb[e];
-    s2 = warp_sum(s2);
-    if ((tid & 31) == 0) red[tid >> 5] = s2;
+    float sw = 0.f;                                   // sum of vbar: d Kdiag / d variance = d Kdiag / d white-variance = 1
+    for (int e = tid; e < TR * D; e += DSDGP_NT) sw += vb[e];
+    s2 += sw;
+    s2 = warp_sum(s2); sw = warp_sum(sw);
+    if ((tid & 31) == 0) { red[tid >> 5] = s2; red[8 + (tid >> 5)] = sw; }
     __syncthreads();
     if (tid == 0) {
-        float t = 0.f;
-        for (int w = 0; w < DSDGP_NT / 32; ++w) t += red[w];
+        float t = 0.f, tw = 0.f;
+        for (int w = 0; w < DSDGP_NT / 32; ++w) { t += red[w]; tw += red[8 + w]; }
         atomicAdd(P.gvar, t);
+        if (P.kwhite) atomicAdd(P.gwvar, tw);
     }
     // B8: xbar, Zbar, lsbar (chunked over the input dimension)
     const float* gT = kpT;
@@ -440,6 +454,8 @@ __global__ void __launch_bounds__(DSDGP_NT) k_layer_bwd(LayerDev P, BwdArgs a) {
                 else if (P.mean == DSDGP_MEAN_LINEAR) {
                     for (int d = 0; d < D; ++d) s = fmaf(mub[r * D + d], __ldg(&P.meanW[q * D + d]), s);
                 }
+                // input propagation: the first ipd columns of this layer's output ARE its first ipd inputs
+                if (row < R && a.fbar && q < ipd) s += a.fbar[(size_t)row * FS + q];
                 if (row < R) a.xbar[(size_t)row * Din + q] = s;
             }
         }

@@ -21,21 +21,22 @@
 // ----------------------------------------------------------------------------------------------
 // part 0: every block; 1: the four Linv blocks (need this step's factorisation); 2: the q_sqrt blocks (parameters only --
 // packed on the side branch of the step DAG while the factorisation runs): G2 (L_d^T, forward) and S_d = L_d L_d^T (backward)
-__global__ void k_pack_fwd(LayerSet ls, int part) {
+__global__ void k_pack_fwd(LayerSet ls, int part, Accum* acc) {
     const LayerDev& P = ls.l[blockIdx.y];
     if (!P.wpack_fwd) return;
     const int M = P.M, D = P.Dout, nkb = tcp::nkb_of(M), NPAD = tcp::npad_of(M);
     const uint32_t slot = tcp::slot_bytes(M);
     const int nblk = tcp::num_blocks(D) + D;            // triangular blocks, then the D square S_d operands
+    const float g2thr = 1e-3f * sqrtf(P.var[0]);
     const int per_blk = nkb * 128 * 32;                 // (kb, n, kk) index space; rows outside a band are skipped
     const int blk0 = part == 2 ? 4 : 0, blk1 = part == 1 ? 4 : nblk;
     const size_t total = (size_t)(blk1 - blk0) * per_blk;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int blk = blk0 + (int)(e / per_blk), w = (int)(e % per_blk), kb = w >> 12, n = (w >> 5) & 127, kk = w & 31, k = kb * 32 + kk;
-        if (blk >= 4 + D) {
+        if (blk >= 4 + 2 * D) {
             // S_d[n][k] = sum_{j <= min(n,k)} L_d[n][j] L_d[k][j]  (symmetric: B[n][k] = S_d[k][n] = S_d[n][k])
             if (n >= NPAD) continue;
-            const int d = blk - 4 - D;
+            const int d = blk - 4 - 2 * D;
             float out = 0.f;
             if (n < M && k < M) {
                 const float* Ln = P.q_sqrt + ((size_t)d * M + n) * M;
@@ -63,8 +64,13 @@ __global__ void k_pack_fwd(LayerSet ls, int part) {
                 const float hi = tc::tf32_rna((float)v);
                 out = part ? tc::tf32_rna((float)(v - (double)hi)) : hi;
             } else {
-                const int d = blk - 4;
-                if (n <= k) out = tc::tf32_rna(P.q_sqrt[((size_t)d * M + k) * M + n]);                     // G2: L_d[k][n]
+                const int lo = blk >= 4 + D, d = blk - 4 - (lo ? D : 0);
+                if (n <= k) {                                                                               // G2: L_d[k][n]
+                    const float v = P.q_sqrt[((size_t)d * M + k) * M + n];
+                    const float hi = tc::tf32_rna(v);
+                    out = lo ? tc::tf32_rna(v - hi) : hi;
+                    if (!lo && fabsf(v) > g2thr && acc) atomicOr(&acc->g2flag[P.idx], 1);
+                }
             }
         }
         char* dst = reinterpret_cast<char*>(P.wpack_fwd) + (size_t)blk * slot + tcp::band_offset(pat, M, kb) +
@@ -73,9 +79,15 @@ __global__ void k_pack_fwd(LayerSet ls, int part) {
     }
 }
 
-void launch_pack_fwd(const LayerSet& ls, int part, cudaStream_t st, long long* nl) {
-    k_pack_fwd<<<dim3(part == 1 ? 24 : 96, ls.L), 256, 0, st>>>(ls, part);
+void launch_pack_fwd(const LayerSet& ls, int part, Accum* acc, cudaStream_t st, long long* nl) {
+    k_pack_fwd<<<dim3(part == 1 ? 24 : 96, ls.L), 256, 0, st>>>(ls, part, acc);
     *nl += 1;
+}
+
+// |c_d|^2 scratch in its own [D][128] region (then G2 may run as 3xTF32) iff everything still fits into 227 KB
+__host__ __device__ inline bool tc_fwd_csq_dedicated(int M, int Din, int D) {
+    const size_t base = 1024 + 131072 + 2 * (size_t)tcp::slot_bytes(M) + 256 + 2048 + sizeof(float) * ((size_t)M * Din + (size_t)M * D + 8);
+    return base + sizeof(float) * 128 * (size_t)D <= 226 * 1024;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -105,10 +117,22 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
     // Weights stream as 32-wide k-block bands (<= 128 NPAD bytes, one TMA bulk copy each) through a ring of sub-slots: the
     // ring area holds `nr` of them; once the 3xTF32 projections are done A_lo is dead and adds `nalo` more for the G2 stream
     // (its last bytes keep the |c_d|^2 scratch), so up to nr + nalo bands are in flight instead of two or three whole blocks.
+    // The |c_d|^2 partial sums live in a dedicated [D][128] region (the two halves of a pair add with shared-memory atomics)
+    // when it fits next to everything else, else as [2][D][128] partials at the end of A_lo.  Only with the dedicated region
+    // can A_lo keep u's low part, i.e. can G2 run as 3xTF32 (g2x3): the flag comes from k_pack_fwd (q_sqrt not negligible).
     const uint32_t band_full = 128u * (uint32_t)tcp::npad_of(P.M);
-    const uint32_t csq_bytes = 2u * (uint32_t)P.Dout * 128u * 4u;
+    const bool csq_ded = tc_fwd_csq_dedicated(P.M, P.Din, P.Dout);
+    const uint32_t csq_bytes = csq_ded ? 0u : 2u * (uint32_t)P.Dout * 128u * 4u;
+    // G2 precision (option "g2_passes"; 0 = automatic: 2 when k_pack_fwd flagged the layer's q_sqrt as non-negligible, else 1):
+    //   1: u_hi L_hi                      2: u_hi (L_hi + L_lo)                     3: (u_hi + u_lo) L_hi + u_hi L_lo
+    // Measured (tools/g2_passes_experiment.py): the ELBO error of (1) comes from rounding the WEIGHTS -- the same perturbation for
+    // every row, so it does not average out over the minibatch -- while u's rounding is independent per row and does; (2) is
+    // within 2x of (3) at the cost of the doubled weight stream only (no second operand image, A_lo stays a ring area).
+    const int g2p = a.g2_passes ? a.g2_passes : ((a.acc && a.acc->g2flag[P.idx] != 0) ? 2 : 1);
+    const bool g2x3 = csq_ded && g2p == 3;            // u's low part in A_lo
+    const bool g2lo = g2p == 2 || g2x3;               // stream the low parts of L_d too
     const int nr = (int)(2 * slotb / band_full);
-    const int nalo = csq_bytes >= 65536u ? 0 : min(TC_NS_MAX - nr, (int)((65536u - csq_bytes) / band_full));
+    const int nalo = (g2x3 || csq_bytes >= 65536u) ? 0 : min(TC_NS_MAX - nr, (int)((65536u - csq_bytes) / band_full));
     auto slot_addr = [&](int sl) { return sl < nr ? Bring + (uint32_t)sl * band_full : A_lo + (uint32_t)(sl - nr) * band_full; };
     const uint32_t bar_full = misc, bar_empty = misc + 8 * TC_NS_MAX;
     const uint32_t bar_a = bar_empty + 8 * TC_NS_MAX;        // a_ready[3]
@@ -119,7 +143,8 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
     float* Zs = part_s + 512;                                                       // [M][Din], pre-scaled by 1/lengthscale
     float* qmu_s = Zs + ((P.M * P.Din + 3) & ~3);                                   // [M][D], 16-byte aligned
     // scratch aliased on A_lo once it is dead (G2 reads A_hi only): |c_d|^2 partials [2][D][128]
-    float* csq_p = reinterpret_cast<float*>(sgen + (A_lo - sbase) + (65536u - min(csq_bytes, 65536u)));
+    float* csq_p = csq_ded ? qmu_s + ((P.M * P.Dout + 3) & ~3)
+                           : reinterpret_cast<float*>(sgen + (A_lo - sbase) + (65536u - min(csq_bytes, 65536u)));
 
     const int M = P.M, Din = P.Din, D = P.Dout;
     const int nkb = (M + 31) / 32, NPAD = (M + 15) & ~15;
@@ -146,6 +171,8 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
     }
     for (int e = threadIdx.x; e < M * Din; e += TC_THREADS) Zs[e] = P.Z[e] * (1.0f / P.ls[P.ard ? e % Din : 0]);
     for (int e = threadIdx.x; e < M * D; e += TC_THREADS) qmu_s[e] = P.q_mu[e];
+    if (csq_ded)
+        for (int e = threadIdx.x; e < D * 128; e += TC_THREADS) csq_p[e] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -176,7 +203,10 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
             load_block(tcp::blk_g1(0), tcp::PAT_LE, nr); load_block(tcp::blk_g1(1), tcp::PAT_LE, nr);
             if (!P.white) { load_block(tcp::blk_g1p(0), tcp::PAT_GE, nr); load_block(tcp::blk_g1p(1), tcp::PAT_GE, nr); }
             s = 0;
-            for (int d = 0; d < D; ++d) load_block(tcp::blk_g2(d), tcp::PAT_GE, nr + nalo);
+            for (int d = 0; d < D; ++d) {
+                load_block(tcp::blk_g2(d), tcp::PAT_GE, nr + nalo);
+                if (g2lo) load_block(tcp::blk_g2lo(D, d), tcp::PAT_GE, nr + nalo);
+            }
         }
     } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer: whole warp runs the uniform control flow, one elected lane issues ==========
@@ -234,7 +264,10 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
             s = 0;
             for (int d = 0; d < D; ++d) {
                 if (d >= 2) { mbar_wait(bar_acc2e + 8 * (d & 1), ((d >> 1) - 1) & 1); tc_fence_after(); }
-                do_block(256u + 128u * (uint32_t)(d & 1), tcp::PAT_GE, 2, nr + nalo);
+                // hi block: u_hi (and u_lo when g2x3) against L_hi; lo block (g2lo): u_hi against L_lo.  The band sequence must
+                // be exactly the producer's (every band it loads is consumed here)
+                do_block(256u + 128u * (uint32_t)(d & 1), tcp::PAT_GE, g2x3 ? 0 : 2, nr + nalo);
+                if (g2lo) do_block(256u + 128u * (uint32_t)(d & 1), tcp::PAT_GE, 1, nr + nalo);
                 commit(bar_acc2f + 8 * (d & 1));
             }
         }
@@ -353,7 +386,7 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
         tc_fence_after();
         STAMP();      // 2: G1 accumulators ready
         if (P.white) {
-            consume(0u, true, false);
+            consume(0u, true, g2x3);
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_a + 16);
@@ -366,7 +399,7 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
             mbar_wait(bar_acc + 8, 0);
             tc_fence_after();
             STAMP();  // 4: G1' ready
-            consume(128u, false, false);       // critical path: u -> A_hi only
+            consume(128u, false, g2x3);        // critical path: u -> A_hi (and A_lo when G2 runs as 3xTF32)
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(bar_a + 16);
@@ -432,7 +465,8 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
             }
             tc_fence_before();
             mbar_arrive(bar_acc2e + 8 * pair);
-            csq_p[(half * D + d) * 128 + t] = s;
+            if (csq_ded) atomicAdd(&csq_p[d * 128 + t], s);
+            else csq_p[(half * D + d) * 128 + t] = s;
             STAMP();  // E2[d] done
         }
         if (nmine == 0)
@@ -460,7 +494,8 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
                         for (int q = 0; q < Din; ++q) ms = fmaf(__ldcg(&a.Xin[(size_t)row * Din + q]), __ldg(&P.meanW[q * D + d]), ms);
                         mean += ms;
                     }
-                    const float v = var0 - bnt + csq_p[d * 128 + t] + csq_p[(D + d) * 128 + t];
+                    const float csq = csq_ded ? csq_p[d * 128 + t] : csq_p[d * 128 + t] + csq_p[(D + d) * 128 + t];
+                    const float v = (var0 + P.wvar[0]) - bnt + csq;      // Kdiag incl. a White term
                     a.Fmean[(size_t)row * D + d] = mean;
                     a.Fvar[(size_t)row * D + d] = v;
                     mean2[e] = mean;
@@ -553,10 +588,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_chain_fwd_tc(const __grid_con
     if (warp == TC_WARP_TMA) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-static size_t tc_fwd_smem(int M, int Din, int D) { return 1024 + 131072 + 2 * (size_t)tcp::slot_bytes(M) + 256 + 2048 + sizeof(float) * ((size_t)M * Din + (size_t)M * D + 8); }
+static size_t tc_fwd_smem_base(int M, int Din, int D) { return 1024 + 131072 + 2 * (size_t)tcp::slot_bytes(M) + 256 + 2048 + sizeof(float) * ((size_t)M * Din + (size_t)M * D + 8); }
+static size_t tc_fwd_smem(int M, int Din, int D) {
+    return tc_fwd_smem_base(M, Din, D) + (tc_fwd_csq_dedicated(M, Din, D) ? sizeof(float) * 128 * (size_t)D : 0);
+}
 
 bool tc_fwd_supported(const LayerDev& P) {
-    return P.M <= 128 && P.M >= 8 && P.Din <= 16 && P.Dout <= 32 && P.wpack_fwd != nullptr &&
+    return P.M <= 128 && P.M >= 8 && P.Din <= 16 && P.Dout <= 32 && P.wpack_fwd != nullptr && P.ipd == 0 &&
            tc_fwd_smem(P.M, P.Din, P.Dout) <= 226 * 1024;
 }
 

@@ -497,12 +497,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             }
         }
         BSTAMP();   // R6 done
-        if (qt == 0)
-#pragma unroll
-            for (int d = 0; d < DOUTP; ++d) s2 += vb[d];
+        if (qt == 0) s2 += vs;                    // d Kdiag / d variance = 1
         s2 = warp_sum(s2);
         lsum = warp_sum(lsum);
         if (lane == 0) { red_s[warp] = s2; red_s[16 + warp] = lsum; }
+        if (qt == 0 && P.kwhite) {                // the same sum is the gradient of a White term's variance (Kdiag += wvar)
+            const float sw = warp_sum(vs);
+            if (lane == 0) atomicAdd(P.gwvar, sw);
+        }
         if (threadIdx.x < 32) red_s[32 + threadIdx.x] = 0.f;     // ARD lengthscale accumulators
         named_bar_sync(1, TC_ROWTHREADS);                        // g_s, red_s complete; A_u is dead (G7 has completed)
         if (threadIdx.x == 0) {
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     X(8, 8, 0, false) X(8, 8, 0, true) X(8, 8, 1, false) X(8, 8, 1, true)
 
 bool tc_bwd_supported(const LayerDev& P) {
-    if (!(P.M <= 128 && P.M >= 8 && (P.M & 3) == 0 && P.wpack_fwd != nullptr)) return false;
+    if (!(P.M <= 128 && P.M >= 8 && (P.M & 3) == 0 && P.wpack_fwd != nullptr && P.ipd == 0)) return false;
     if (P.Din != 8 || !(P.Dout == 1 || P.Dout == 8)) return false;      // compile-time shapes (see the kernel comment)
     return bwd_smem_plan(P.M, P.Din, P.Dout).total + 1024 <= 227 * 1024;
 }

@@ -54,6 +54,54 @@ void launch_lik_gaussian(const float* Fmean, const float* Fvar, const float* Y, 
     *nl += 1;
 }
 
+// Bernoulli, probit link (gpflow.likelihoods.Bernoulli default; tests/test_dgp.py:48-54): VE = 20-point Gauss-Hermite of
+// log p(y | f), p(y=1 | f) = Phi(f) (1 - 2e-3) + 1e-3 (gpflow probit), f = mu + sqrt(2 v) x_h.  One thread per element.
+__device__ __forceinline__ double bern_ve(double mu, double v, bool y1, double* gm, double* gv) {
+    const bool clipped = v < 1e-10;
+    if (clipped) v = 1e-10;
+    const double sd2 = sqrt(2.0 * v);
+    double ve = 0.0, dm = 0.0, dv = 0.0;
+    for (int h = 0; h < 20; ++h) {
+        const double x = mu + sd2 * c_gh_x[h];
+        const double w = c_gh_w[h] * 0.56418958354775628;       // / sqrt(pi)
+        const double p = 0.5 * (1.0 + erf(x * 0.70710678118654752)) * (1.0 - 2e-3) + 1e-3;
+        const double dp = 0.3989422804014327 * exp(-0.5 * x * x) * (1.0 - 2e-3);
+        ve += w * log(y1 ? p : 1.0 - p);
+        const double dl = y1 ? dp / p : -dp / (1.0 - p);         // d log p(y|f) / df
+        dm += w * dl;
+        dv += w * dl * c_gh_x[h] / sd2;                          // df/dv = x_h / sqrt(2 v)
+    }
+    if (gm) { *gm = dm; *gv = clipped ? 0.0 : dv; }
+    return ve;
+}
+__device__ __forceinline__ double bern_predict_p(double mu, double v) {
+    return 0.5 * (1.0 + erf(mu / sqrt(1.0 + v) * 0.70710678118654752)) * (1.0 - 2e-3) + 1e-3;
+}
+__global__ void k_lik_bernoulli(const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
+                                int R, int N, int Dy, float* __restrict__ mubar, float* __restrict__ vbar, Accum* acc,
+                                const StepArgs* sa, int want_grad, const float* __restrict__ sw) {
+    const double c0 = sa->lik_scale;
+    double ve = 0.0;
+    const size_t total = (size_t)R * Dy;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int r = idx / Dy, d = idx % Dy, n = r % N;
+        const double c = sw ? c0 * (double)sw[r / N] : c0;
+        double gm, gv;
+        ve += c * bern_ve(Fmean[idx], Fvar[idx], Y[(size_t)n * Dy + d] > 0.5f, want_grad ? &gm : nullptr, &gv);
+        if (want_grad) { mubar[idx] = (float)(c * gm); vbar[idx] = (float)(c * gv); }
+    }
+    ve = warp_sum_d(ve);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&acc->lik, ve);
+}
+void launch_lik_bernoulli(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy, float* mubar,
+                          float* vbar, Accum* acc, const StepArgs* sa, int want_grad, const float* sw, cudaStream_t st,
+                          long long* nl) {
+    const size_t total = (size_t)R * Dy;
+    k_lik_bernoulli<<<(int)min((size_t)1024, (total + 127) / 128), 128, 0, st>>>(Fmean, Fvar, Y, R, N, Dy, mubar, vbar, acc, sa,
+                                                                                  want_grad, sw);
+    *nl += 1;
+}
+
 // MultiClass / RobustMax(eps = 1e-3): one thread per row; 20-point Gauss-Hermite over the labelled latent.
 #define MC_MAXK 32
 __global__ void k_lik_multiclass(const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
@@ -206,12 +254,40 @@ __global__ void k_density_multiclass(const float* __restrict__ Fmean, const floa
     out[n] = (float)(mx + log(acc));
 }
 
+// Bernoulli: p = Phi(mu / sqrt(1 + v)) (squashed), var = p - p^2 ; density = log(y ? p : 1 - p), log-mean-exp over S
+__global__ void k_predict_y_bernoulli(const float* __restrict__ Fmean, const float* __restrict__ Fvar, size_t total,
+                                      float* __restrict__ mean, float* __restrict__ var) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const double p = bern_predict_p(Fmean[i], Fvar[i]);
+        mean[i] = (float)p;
+        var[i] = (float)(p - p * p);
+    }
+}
+__global__ void k_density_bernoulli(const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
+                                    int S, int N, int Dy, int dedup, float* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * Dy) return;
+    const bool y1 = Y[i] > 0.5f;
+    const double lS = log((double)S);
+    double mx = -INFINITY, acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const size_t j = dedup ? i : (size_t)s * N * Dy + i;
+        const double p = bern_predict_p(Fmean[j], Fvar[j]);
+        const double l = log(y1 ? p : 1.0 - p) - lS;
+        if (l > mx) { acc = acc * exp(mx - l) + 1.0; mx = l; }
+        else acc += exp(l - mx);
+    }
+    out[i] = (float)(mx + log(acc));
+}
+
 void launch_predict_y(int lik, const float* Fmean, const float* Fvar, int R, int D, const float* lik_var, float* mean,
                       float* var, cudaStream_t st, long long* nl) {
     const size_t total = (size_t)R * D;
     if (lik == DSDGP_LIK_GAUSSIAN) {
         int nb = (int)min((size_t)1184, (total + 255) / 256);
         k_predict_y_gaussian<<<nb, 256, 0, st>>>(Fmean, Fvar, total, lik_var, mean, var);
+    } else if (lik == DSDGP_LIK_BERNOULLI) {
+        k_predict_y_bernoulli<<<(int)min((size_t)1184, (total + 255) / 256), 256, 0, st>>>(Fmean, Fvar, total, mean, var);
     } else {
         k_predict_y_multiclass<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(Fmean, Fvar, R, D, mean, var);
     }
@@ -221,8 +297,37 @@ void launch_predict_density(int lik, const float* Fmean, const float* Fvar, cons
                             const float* lik_var, float* out, cudaStream_t st, long long* nl) {
     if (lik == DSDGP_LIK_GAUSSIAN)
         k_density_gaussian<<<(unsigned)(((size_t)N * D + 127) / 128), 128, 0, st>>>(Fmean, Fvar, Y, S, N, D, dedup, lik_var, out);
+    else if (lik == DSDGP_LIK_BERNOULLI)
+        k_density_bernoulli<<<(unsigned)(((size_t)N * D + 127) / 128), 128, 0, st>>>(Fmean, Fvar, Y, S, N, D, dedup, out);
     else
         k_density_multiclass<<<(N + 127) / 128, 128, 0, st>>>(Fmean, Fvar, Y, S, N, D, dedup, out);
+    *nl += 1;
+}
+
+// BroadcastingLikelihood.variational_expectations (utils.py:88-93) on caller-supplied marginals: out (S*N, Do), one value per
+// element (Gaussian, Bernoulli) or per row (MultiClass), unscaled -- the host-callable form of what k_lik_* sum up.
+__global__ void k_ve_elem(int lik, const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
+                          int R, int N, int D, const float* __restrict__ lik_var, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lik == DSDGP_LIK_MULTICLASS) {
+        if (i >= (size_t)R) return;
+        const int y = (int)(Y[i % N] + 0.5f);
+        const double p = mc_prob_is_largest(Fmean + i * D, Fvar + i * D, D, y);
+        out[i] = (float)(p * log(1.0 - 1e-3) + (1.0 - p) * log(1e-3 / (D - 1.0)));
+        return;
+    }
+    if (i >= (size_t)R * D) return;
+    const int r = (int)(i / D), d = (int)(i % D), n = r % N;
+    const double y = Y[(size_t)n * D + d], mu = Fmean[i], v = Fvar[i];
+    if (lik == DSDGP_LIK_GAUSSIAN) {
+        const double s2 = (double)lik_var[0];
+        out[i] = (float)(-0.5 * 1.8378770664093453 - 0.5 * log(s2) - 0.5 * ((y - mu) * (y - mu) + v) / s2);
+    } else out[i] = (float)bern_ve(mu, v, y > 0.5, nullptr, nullptr);
+}
+void launch_ve_elem(int lik, const float* Fmean, const float* Fvar, const float* Y, int R, int N, int D, const float* lik_var,
+                    float* out, cudaStream_t st, long long* nl) {
+    const size_t total = lik == DSDGP_LIK_MULTICLASS ? (size_t)R : (size_t)R * D;
+    k_ve_elem<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(lik, Fmean, Fvar, Y, R, N, D, lik_var, out);
     *nl += 1;
 }
 

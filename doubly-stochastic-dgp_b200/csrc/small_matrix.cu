@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(1024) k_prepA(LayerSet ls, double jitter, Accu
         }
         double k, kp;
         kern_eval_d(P.kern, r2, var, k, kp);
-        if (i == j) k += jitter;
+        if (i == j) k += jitter + (double)P.wvar[0];
         P.K64[idx] = k;
         A[idx] = k;
         X[idx] = (i == j) ? 1.0 : 0.0;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(NT) k_prepA_ldl(LayerSet ls, double jitter, Ac
             }
             double k, kp;
             kern_eval_d(P.kern, r2, var, k, kp);
-            if (i == j) k += jitter;
+            if (i == j) k += jitter + (double)P.wvar[0];
             P.K64[i * M + j] = k;
             P.K64[j * M + i] = k;
             B[j * MS + i] = k;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(NT) k_prepA_c4(LayerSet ls, double jitter, Acc
             }
             double k, kp;
             kern_eval_d(P.kern, r2, var, k, kp);
-            if (i == j) k += jitter;
+            if (i == j) k += jitter + (double)P.wvar[0];
             P.K64[i * M + j] = k;
             P.K64[j * M + i] = k;
             C[j * MS + i] = k;
@@ -634,7 +634,7 @@ __global__ void k_fin_kbar(LayerSet ls, const StepArgs* sa, int lbase) {
     const LayerDev& P = ls.l[lbase + blockIdx.y];
     const int M = P.M, Din = P.Din;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    double s2 = 0.0;
+    double s2 = 0.0, sw = 0.0;
     if (idx < M * M) {
         int i = idx / M, j = idx % M;
         double kb;
@@ -650,9 +650,10 @@ __global__ void k_fin_kbar(LayerSet ls, const StepArgs* sa, int lbase) {
         kern_eval_d(P.kern, r2, (double)P.var[0], k, kp);
         P.Gsym[idx] = kb * kp;
         s2 = kb * k / (double)P.var[0];
+        if (i == j) sw = kb;               // d Kuu / d white-variance = I
     }
-    s2 = warp_sum_d(s2);
-    if ((threadIdx.x & 31) == 0) atomicAdd(P.gvar, (float)s2);
+    s2 = warp_sum_d(s2); sw = warp_sum_d(sw);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(P.gvar, (float)s2); if (P.kwhite && sw != 0.0) atomicAdd(P.gwvar, (float)sw); }
 }
 
 // Zbar_iq += 4/l_q^2 sum_j g_ij (z_iq - z_jq) ; lsbar_q += -2/l_q^3 sum_ij g_ij (z_iq - z_jq)^2

@@ -4,7 +4,8 @@
 // (128 B per row, 8-row atoms of 1024 B).  One block = one contiguous TMA bulk copy.
 //   pattern GE (k >= n : G1', G2, G7): k-blocks nkb-1 .. 0, rows [0, min(NPAD, 32 kb + 32))
 //   pattern LE (k <= n : G1,  G5, G6): k-blocks 0 .. nkb-1, rows [32 kb, NPAD)
-// Block order in wpack: [G1 hi][G1 lo][G1' hi][G1' lo][G2 d=0..D-1], each at a stride of slot_bytes; then the square operands
+// Block order in wpack: [G1 hi][G1 lo][G1' hi][G1' lo][G2 hi d=0..D-1][G2 lo d=0..D-1], each at a stride of slot_bytes (the
+// lo parts are only streamed when the layer's q_sqrt is large enough for 1xTF32 to matter); then the square operands
 // S_d = L_d L_d^T (backward: y_d = S_d u), d = 0..D-1, each nkb full bands of NPAD rows (sfull_bytes), k-blocks 0..nkb-1.
 #pragma once
 #include <stdint.h>
@@ -41,7 +42,8 @@ __host__ __device__ inline uint32_t slot_bytes(int M) {
 __host__ __device__ inline int blk_g1(int part) { return part; }                 // part: 0 hi, 1 lo
 __host__ __device__ inline int blk_g1p(int part) { return 2 + part; }
 __host__ __device__ inline int blk_g2(int d) { return 4 + d; }
-__host__ __device__ inline int num_blocks(int D) { return 4 + D; }
+__host__ __device__ inline int blk_g2lo(int D, int d) { return 4 + D + d; }
+__host__ __device__ inline int num_blocks(int D) { return 4 + 2 * D; }
 // square (non-triangular) operands: one band = all NPAD rows of one k-block
 __host__ __device__ inline uint32_t sfull_band_bytes(int M) { return 128u * (uint32_t)npad_of(M); }
 __host__ __device__ inline uint32_t sfull_bytes(int M) { return (uint32_t)nkb_of(M) * sfull_band_bytes(M); }

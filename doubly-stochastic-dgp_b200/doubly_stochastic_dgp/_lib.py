@@ -6,14 +6,15 @@ import os
 import numpy as np
 
 MAX_LAYERS = 16
-F_Z, F_Q_MU, F_Q_SQRT, F_LENGTHSCALES, F_VARIANCE, F_MEAN_W, F_MEAN_B, F_LIK_VARIANCE = range(8)
+F_Z, F_Q_MU, F_Q_SQRT, F_LENGTHSCALES, F_VARIANCE, F_MEAN_W, F_MEAN_B, F_LIK_VARIANCE, F_WHITE_VARIANCE = range(9)
 FLAG_DEVICE_PTRS, FLAG_NO_SYNC = 1, 2
 ERR_NOT_PD = -3
 
 
 class LayerDesc(C.Structure):
     _fields_ = [("M", C.c_int), ("D_in", C.c_int), ("D_out", C.c_int), ("kernel", C.c_int),
-                ("ard", C.c_int), ("white", C.c_int), ("mean", C.c_int)]
+                ("ard", C.c_int), ("white", C.c_int), ("mean", C.c_int), ("kernel_white", C.c_int),
+                ("input_prop_dim", C.c_int)]
 
 
 class Desc(C.Structure):
@@ -38,7 +39,7 @@ SYMBOLS = ["dsdgp_last_error", "dsdgp_version", "dsdgp_create", "dsdgp_destroy",
            "dsdgp_adam_init", "dsdgp_train_step", "dsdgp_kl", "dsdgp_comm_unique_id", "dsdgp_comm_init", "dsdgp_sync",
            "dsdgp_launch_count", "dsdgp_last_step_ms", "dsdgp_set_option", "dsdgp_timer_start",
            "dsdgp_timer_stop", "dsdgp_profile", "dsdgp_set_trainable", "dsdgp_natgrad_step", "dsdgp_predict_y",
-           "dsdgp_predict_density", "dsdgp_propagate_full_cov", "dsdgp_set_sample_weights"]
+           "dsdgp_predict_density", "dsdgp_propagate_full_cov", "dsdgp_set_sample_weights", "dsdgp_likelihood_apply"]
 
 
 def lib_path():
@@ -74,6 +75,8 @@ def load():
     lib.dsdgp_predict_density.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
                                           C.c_void_p, C.c_uint]
     lib.dsdgp_set_sample_weights.argtypes = [C.c_void_p, DP, C.c_int]
+    lib.dsdgp_likelihood_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_uint]
     lib.dsdgp_set_trainable.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.dsdgp_natgrad_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                        C.c_uint64, C.c_uint, C.POINTER(C.c_int), C.c_int, C.c_double, DP]
@@ -168,12 +171,13 @@ class Context:
         N = X.shape[0]
         L = self.L
         douts = [self.desc.layers[l].D_out for l in range(L)]
+        ipds = [self.desc.layers[l].input_prop_dim for l in range(L)]
         zarr, keep = self._zs(zs, S, N)
         outs = []
         arrs = []
-        for w in want:
-            if w:
-                o = [np.empty((S, N, douts[l]), dtype=np.float32) for l in range(L)]
+        for k, w in enumerate(want):
+            if w:     # Fs carry the propagated inputs in front of the samples (layers.py:105-117)
+                o = [np.empty((S, N, douts[l] + (ipds[l] if k == 0 else 0)), dtype=np.float32) for l in range(L)]
                 a, _ = _ptr_array(o, L)
             else:
                 o, a = None, None
@@ -246,10 +250,32 @@ class Context:
         """logsumexp_S(likelihood.predict_density - log S): (N,D_y) Gaussian, (N,1) MultiClass."""
         X, Y = self._xy(X, Y)
         N = X.shape[0]
-        Do = self.desc.D_y if self.desc.likelihood == 0 else 1
+        Do = 1 if self.desc.likelihood == 1 else self.desc.D_y      # MultiClass: one density per row
         zarr, keep = self._zs(zs, S, N)
         out = np.empty((N, Do), dtype=np.float32)
         check(self.lib.dsdgp_predict_density(self.h, _ptr(X), _ptr(Y), N, S, zarr, seed, _ptr(out), 0))
+        return out
+
+    def likelihood_apply(self, what, Fmu, Fvar, Y=None):
+        """BroadcastingLikelihood.{variational_expectations (0), predict_mean_and_var (1), predict_density (2)} on (S,N,D)
+        marginals (utils.py:88-121), evaluated by the device epilogues.  Returns float32 arrays of shape (S,N,-1)."""
+        Fmu, Fvar = f32(Fmu), f32(Fvar)
+        D = self.desc.layers[self.L - 1].D_out
+        if Fmu.ndim != 3 or Fmu.shape[2] != D or Fvar.shape != Fmu.shape:
+            raise ValueError(f"Fmu / Fvar must be (S, N, {D}) arrays of the same shape, got {Fmu.shape} and {Fvar.shape}")
+        S, N = Fmu.shape[:2]
+        Do = 1 if self.desc.likelihood == 1 else D
+        if what == 1:
+            mean, var = np.empty((S, N, D), dtype=np.float32), np.empty((S, N, D), dtype=np.float32)
+            check(self.lib.dsdgp_likelihood_apply(self.h, what, _ptr(Fmu), _ptr(Fvar), None, S, N, _ptr(mean), _ptr(var), 0))
+            return mean, var
+        Y = f32(Y)
+        if Y.ndim == 1:
+            Y = Y.reshape(-1, 1)
+        if Y.shape != (N, self.desc.D_y):
+            raise ValueError(f"Y has shape {Y.shape}, expected ({N}, {self.desc.D_y})")
+        out = np.empty((S, N, Do), dtype=np.float32)
+        check(self.lib.dsdgp_likelihood_apply(self.h, what, _ptr(Fmu), _ptr(Fvar), _ptr(Y), S, N, _ptr(out), None, 0))
         return out
 
     def _elbo(self, fn, X, Y, S, num_data, zs, seed, flags):

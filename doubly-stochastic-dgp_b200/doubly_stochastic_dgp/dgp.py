@@ -51,6 +51,7 @@ class DGP_Base(Parameterized):
             self._Ymb = _Minibatch(Y, minibatch_size, seed=0)
         self.X, self.Y = X, Y
         self.likelihood = BroadcastingLikelihood(likelihood)        # dgp.py:57
+        object.__setattr__(self.likelihood, "_model", self)
         self.layers = list(layers)                                   # dgp.py:59
         self._device = device
         self._ctx = None
@@ -70,6 +71,8 @@ class DGP_Base(Parameterized):
         out = []
         for l in self.layers:
             out += [l.feature.Z, l.q_mu, l.q_sqrt, l.kern.lengthscales, l.kern.variance]
+            if getattr(l.kern, "white_variance", None) is not None:
+                out.append(l.kern.white_variance)
             if isinstance(l.mean_function, Linear):
                 out += [l.mean_function.A, l.mean_function.b]
         lik = self.likelihood.likelihood
@@ -89,6 +92,8 @@ class DGP_Base(Parameterized):
         for i, l in enumerate(self.layers):
             out += [(i, _lib.F_Z, l.feature.Z), (i, _lib.F_Q_MU, l.q_mu), (i, _lib.F_Q_SQRT, l.q_sqrt),
                     (i, _lib.F_LENGTHSCALES, l.kern.lengthscales), (i, _lib.F_VARIANCE, l.kern.variance)]
+            if getattr(l.kern, "white_variance", None) is not None:
+                out.append((i, _lib.F_WHITE_VARIANCE, l.kern.white_variance))
         lik = self.likelihood.likelihood
         if isinstance(lik, Gaussian):
             out.append((-1, _lib.F_LIK_VARIANCE, lik.variance))
@@ -105,6 +110,8 @@ class DGP_Base(Parameterized):
             l.q_sqrt._value = c.get_param(i, _lib.F_Q_SQRT, l.q_sqrt.shape)
             l.kern.lengthscales._value = c.get_param(i, _lib.F_LENGTHSCALES, l.kern.lengthscales.shape)
             l.kern.variance._value = c.get_param(i, _lib.F_VARIANCE, ())
+            if getattr(l.kern, "white_variance", None) is not None:
+                l.kern.white_variance._value = c.get_param(i, _lib.F_WHITE_VARIANCE, ())
         lik = self.likelihood.likelihood
         if isinstance(lik, Gaussian):
             lik.variance._value = c.get_param(-1, _lib.F_LIK_VARIANCE, ())
@@ -114,7 +121,10 @@ class DGP_Base(Parameterized):
         for l in self.layers:
             Z = l.feature.Z._value
             descs.append((Z.shape[0], Z.shape[1], l.num_outputs, l.kern.code, int(l.kern.ARD), int(bool(l.white)),
-                          l.mean_function.code))
+                          l.mean_function.code, int(getattr(l.kern, "white_variance", None) is not None),
+                          # (a final layer never feeds another one: a stand-alone layer's propagation is the host-side concat
+                          # of layers.sample_from_conditional)
+                          0 if l is self.layers[-1] else int(l.input_prop_dim or 0)))
             if l.kern.input_dim != Z.shape[1]:
                 raise ValueError(f"kernel input_dim {l.kern.input_dim} != Z columns {Z.shape[1]}")
         return descs
@@ -149,6 +159,8 @@ class DGP_Base(Parameterized):
                 c.set_param(i, _lib.F_Q_SQRT, l.q_sqrt._value)
                 c.set_param(i, _lib.F_LENGTHSCALES, l.kern.lengthscales._value)
                 c.set_param(i, _lib.F_VARIANCE, l.kern.variance._value)
+                if getattr(l.kern, "white_variance", None) is not None:
+                    c.set_param(i, _lib.F_WHITE_VARIANCE, l.kern.white_variance._value)
                 if isinstance(l.mean_function, Linear):
                     c.set_param(i, _lib.F_MEAN_W, l.mean_function.A._value)
                     c.set_param(i, _lib.F_MEAN_B, l.mean_function.b._value)
@@ -224,6 +236,14 @@ class DGP_Base(Parameterized):
         for which in range(3):
             out.append([np.concatenate([np.concatenate([cell[which][l] for cell in line], axis=1) for line in parts], axis=0)
                         .astype(np.float64) for l in range(L)])
+        for l, layer in enumerate(self.layers):
+            ipd = 0 if l == L - 1 else (layer.input_prop_dim or 0)
+            if ipd and not full_cov:
+                # layers.py:105-117: mean = concat([X_prop, mean]), var = concat([0, var]); the samples left the device
+                # already concatenated.  X_prop is the layer's own input, i.e. the first ipd columns of its Fs
+                Xp = out[0][l][:, :, :ipd]
+                out[1][l] = np.concatenate([Xp, out[1][l]], axis=2)
+                out[2][l] = np.concatenate([np.zeros_like(Xp), out[2][l]], axis=2)
         return out[0], out[1], out[2]
 
     def _build_predict(self, X, full_cov=False, S=1, zs=None):
@@ -254,6 +274,8 @@ class DGP_Base(Parameterized):
                               q_sqrt=ctx.get_grad(i, _lib.F_Q_SQRT, l.q_sqrt.shape),
                               lengthscales=ctx.get_grad(i, _lib.F_LENGTHSCALES, l.kern.lengthscales.shape),
                               variance=ctx.get_grad(i, _lib.F_VARIANCE, ())))
+            if getattr(l.kern, "white_variance", None) is not None:
+                grads[-1]["white_variance"] = ctx.get_grad(i, _lib.F_WHITE_VARIANCE, ())
         lik_grad = None
         if isinstance(self.likelihood.likelihood, Gaussian):
             lik_grad = ctx.get_grad(-1, _lib.F_LIK_VARIANCE, ())
@@ -374,11 +396,31 @@ class DGP_Base(Parameterized):
             self._ctx.comm_init(id_bytes, rank, world)
 
     # ------------------------------------------------------------------ per-layer services for layers.py
+    def _layer_snapshot(self, layer):
+        """A private one-layer model holding a copy of `layer`'s current parameters: layers.py:46-119 work on any layer, also
+        one that belongs to a model (its own context is sized and wired for the whole chain)."""
+        import copy
+        self._refresh_from_device()
+        kern = copy.copy(layer.kern)
+        kern.variance = Parameter(layer.kern.variance._value)
+        kern.lengthscales = Parameter(layer.kern.lengthscales._value)
+        if getattr(layer.kern, "white_variance", None) is not None:
+            kern.white_variance = Parameter(layer.kern.white_variance._value)
+        mf = layer.mean_function
+        if isinstance(mf, Linear):
+            mf = Linear(mf.A._value, mf.b._value)
+        from .layers import SVGP_Layer
+        clone = SVGP_Layer(kern, layer.feature.Z._value, layer.num_outputs, mf, white=layer.white,
+                           input_prop_dim=layer.input_prop_dim)
+        clone.q_mu = layer.q_mu._value
+        clone.q_sqrt = layer.q_sqrt._value
+        return _single_layer_model(clone)
+
     def _layer_conditional(self, layer, X, full_cov=False):
-        raise NotImplementedError("layer.conditional_ND on a layer inside a model: use model.propagate")
+        return self._layer_snapshot(layer)._layer_conditional(layer, X, full_cov=full_cov)
 
     def _layer_propagate(self, layer, X, **kw):
-        raise NotImplementedError("layer.sample_from_conditional on a layer inside a model: use model.propagate")
+        return self._layer_snapshot(layer)._layer_propagate(layer, X, **kw)
 
     def _layer_KL(self, layer):
         ctx = self._ensure_ctx(1, 1)
@@ -447,6 +489,18 @@ class _SingleLayer(DGP_Base):
 
     def _layer_propagate(self, layer, X, **kw):
         return self.propagate(X, **kw)
+
+
+def _likelihood_model(likelihood, D):
+    """Private one-layer model of output width D whose context evaluates `likelihood`'s epilogues (utils.py:88-121) for a
+    BroadcastingLikelihood used outside a model."""
+    from .kernels import RBF
+    from .layers import SVGP_Layer
+    layer = SVGP_Layer(RBF(1), np.zeros((1, 1)), D, Zero())
+    K = likelihood.num_classes if isinstance(likelihood, MultiClass) else 0
+    m = _SingleLayer.__new__(_SingleLayer)
+    DGP_Base.__init__(m, np.zeros((1, 1)), np.zeros((1, 1 if K else D)), likelihood, [layer])
+    return m
 
 
 def _single_layer_model(layer):

@@ -20,8 +20,8 @@ class InducingPoints(Parameterized):
 
 class Layer(Parameterized):
     def __init__(self, input_prop_dim=None, **kwargs):
-        if input_prop_dim:
-            raise NotImplementedError("input_prop_dim is not on the accelerated path yet (SURVEY.md 8(f) rank 4)")
+        # layers.py:39-44: the first input_prop_dim input columns are concatenated in front of the layer's samples / mean
+        # (zeros in front of the variance), layers.py:105-117 -- done by the forward kernel's epilogue on the device
         self.input_prop_dim = input_prop_dim
 
 
@@ -76,10 +76,18 @@ class SVGP_Layer(Layer):
         model = self._ctx_model()
         if full_cov:
             outs = [model._layer_propagate(self, X[s], S=1, full_cov=True, zs=[z[s][None]]) for s in range(S)]
-            return (np.concatenate([o[0][0] for o in outs]), np.concatenate([o[1][0] for o in outs]),
-                    np.concatenate([o[2][0] for o in outs]))
-        Fs, Fm, Fv = model._layer_propagate(self, X.reshape(S * N, D), S=1, zs=[z.reshape(1, S * N, Do)])
-        return Fs[0].reshape(S, N, Do), Fm[0].reshape(S, N, Do), Fv[0].reshape(S, N, Do)
+            samples, mean, var = (np.concatenate([o[0][0] for o in outs]), np.concatenate([o[1][0] for o in outs]),
+                                  np.concatenate([o[2][0] for o in outs]))
+        else:
+            Fs, Fm, Fv = model._layer_propagate(self, X.reshape(S * N, D), S=1, zs=[z.reshape(1, S * N, Do)])
+            samples, mean, var = Fs[0].reshape(S, N, Do), Fm[0].reshape(S, N, Do), Fv[0].reshape(S, N, Do)
+        if self.input_prop_dim:          # layers.py:105-117 (inside a DGP the forward kernel's epilogue does this)
+            Xp = np.asarray(X, dtype=np.float64)[:, :, :self.input_prop_dim]
+            samples = np.concatenate([Xp, samples], 2)
+            mean = np.concatenate([Xp, mean], 2)
+            zeros = np.zeros((S, N, N, self.input_prop_dim)) if full_cov else np.zeros_like(Xp)
+            var = np.concatenate([zeros, var], 3 if full_cov else 2)
+        return samples, mean, var
 
     def KL(self):
         """layers.py:221-246."""
@@ -87,7 +95,14 @@ class SVGP_Layer(Layer):
 
 
 def _host_K(kern, Z):
-    """K(Z,Z) for the construction-time q_sqrt initialisation only (M x M, once)."""
+    """K(Z,Z) for the construction-time q_sqrt initialisation only (M x M, once); a White term adds to the diagonal."""
+    K = _host_K_stationary(kern, Z)
+    if getattr(kern, "white_variance", None) is not None:
+        K = K + float(kern.white_variance.value) * np.eye(Z.shape[0])
+    return K
+
+
+def _host_K_stationary(kern, Z):
     ls = np.asarray(kern.lengthscales.value, dtype=np.float64)
     d = (Z[:, None, :] - Z[None, :, :]) / ls
     r2 = np.sum(d * d, -1)

@@ -1,4 +1,4 @@
-"""gpflow.likelihoods stand-ins (reference call sites utils.py:88-121): descriptors only.  variational_expectations
+"""gpflow.likelihoods stand-ins (reference call sites utils.py:88-121; Gaussian, MultiClass, Bernoulli): descriptors only.  variational_expectations
 (the training path) and the prediction epilogues predict_mean_and_var / predict_density all run on the device
 (csrc/lik_adam.cu: k_lik_*, k_predict_y_*, k_density_*) and are reached through the model: compute_log_likelihood,
 predict_y, predict_density (dgp.py:92-126)."""
@@ -25,3 +25,9 @@ class MultiClass(Likelihood):
         if epsilon != 1e-3:
             raise NotImplementedError("RobustMax epsilon is fixed at 1e-3 in the device kernel")
         self.epsilon = float(epsilon)
+
+
+class Bernoulli(Likelihood):
+    """gpflow.likelihoods.Bernoulli() with its default probit link (tests/test_dgp.py:48-54): 20-point Gauss-Hermite
+    variational expectations, closed-form predict_mean_and_var (csrc/lik_adam.cu k_lik_bernoulli, k_predict_y_bernoulli)."""
+    code = 2

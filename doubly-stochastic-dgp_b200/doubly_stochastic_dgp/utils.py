@@ -40,9 +40,28 @@ class BroadcastingLikelihood(Parameterized):
     def parameters(self):
         return self.likelihood.parameters()
 
+    # ---- utils.py:88-121: the wrapped likelihood applied to (S,N,D) marginals, Y of shape (N,D_y).  The arithmetic is the
+    # device epilogue of csrc/lik_adam.cu (dsdgp_likelihood_apply), reached through the owning model's context; a wrapper
+    # used stand-alone builds a private one-layer context of the right width.
+    def _ctx(self, Fmu):
+        Fmu = np.asarray(Fmu)
+        if Fmu.ndim != 3:
+            raise ValueError(f"expected (S, N, D) marginals, got shape {Fmu.shape}")
+        S, N, D = Fmu.shape
+        model = self.__dict__.get("_model")
+        if model is None or model.layers[-1].num_outputs != D:
+            from .dgp import _likelihood_model
+            model = _likelihood_model(self.likelihood, D)
+            if self.__dict__.get("_model") is None:
+                object.__setattr__(self, "_private_model", model)
+        return model._ensure_ctx(N, S) if len(model.layers) > 1 else model._ensure_ctx(S * N, 1)
+
+    def variational_expectations(self, Fmu, Fvar, Y):
+        return self._ctx(Fmu).likelihood_apply(0, Fmu, Fvar, Y).astype(np.float64)
+
     def predict_mean_and_var(self, Fmu, Fvar):
-        raise NotImplementedError("the likelihood epilogues run on the device: use model.predict_y(Xnew, num_samples)")
+        m, v = self._ctx(Fmu).likelihood_apply(1, Fmu, Fvar)
+        return m.astype(np.float64), v.astype(np.float64)
 
     def predict_density(self, Fmu, Fvar, Y):
-        raise NotImplementedError("the likelihood epilogues run on the device: use "
-                                  "model.predict_density(Xnew, Ynew, num_samples)")
+        return self._ctx(Fmu).likelihood_apply(2, Fmu, Fvar, Y).astype(np.float64)

@@ -51,9 +51,11 @@ extern "C" {
 #define DSDGP_MEAN_ZERO 0
 #define DSDGP_MEAN_IDENTITY 1
 #define DSDGP_MEAN_LINEAR 2
-/* likelihoods: gpflow.likelihoods.Gaussian / MultiClass(RobustMax) (utils.py:88-93) */
+/* likelihoods: gpflow.likelihoods.Gaussian / MultiClass(RobustMax) / Bernoulli(probit) (utils.py:88-93;
+ * tests/test_dgp.py:40-60) */
 #define DSDGP_LIK_GAUSSIAN 0
 #define DSDGP_LIK_MULTICLASS 1
+#define DSDGP_LIK_BERNOULLI 2
 
 /* parameter fields for set/get_param, get_grad */
 #define DSDGP_F_Z 0
@@ -64,6 +66,7 @@ extern "C" {
 #define DSDGP_F_MEAN_W 5            /* Linear mean: (D_in,D_out), fixed (layer_initializations.py:41-42) */
 #define DSDGP_F_MEAN_B 6
 #define DSDGP_F_LIK_VARIANCE 7      /* layer = -1 */
+#define DSDGP_F_WHITE_VARIANCE 8    /* variance of the White term of a Sum(kernel, White) layer kernel (kernel_white = 1) */
 
 /* flags */
 #define DSDGP_FLAG_DEVICE_PTRS 1u   /* X, Y, zs, outputs are device pointers (default: host) */
@@ -80,6 +83,10 @@ typedef struct {
     int ard;      /* 0: one lengthscale, 1: D_in lengthscales */
     int white;    /* layers.py:124 `white` */
     int mean;     /* DSDGP_MEAN_* */
+    int kernel_white;    /* 1: the layer kernel is Sum(kernel, White): + variance_w I on Kuu and + variance_w on Kdiag
+                          * (demos/demo_step_function.ipynb:111, demos/run_regression.py:65-66) */
+    int input_prop_dim;  /* layers.py:105-117: the first input_prop_dim input columns are concatenated in front of the layer's
+                          * samples; the next layer's D_in = input_prop_dim + D_out.  0: none */
 } dsdgp_layer_desc;
 
 /* The model (dgp.py:42-59 DGP_Base.__init__). */
@@ -132,6 +139,16 @@ DSDGP_API int dsdgp_predict_y(dsdgp_ctx* ctx, const float* X, int N, int S, cons
  * Y: (N,D_y) (class ids (N,1) for MultiClass); out: (N,D_y) Gaussian, (N,1) MultiClass. */
 DSDGP_API int dsdgp_predict_density(dsdgp_ctx* ctx, const float* X, const float* Y, int N, int S, const float* const* zs,
                           uint64_t seed, float* out, unsigned flags);
+
+/* BroadcastingLikelihood.{variational_expectations, predict_mean_and_var, predict_density} (utils.py:88-121) on
+ * caller-supplied marginals of the last layer: Fmu, Fvar (S,N,D_last) float32, Y (N,D_y) (ignored by what = 1).
+ * what = 0: variational_expectations -> out0 (S,N,Do);  1: predict_mean_and_var -> out0 mean, out1 var (S,N,D_last);
+ * 2: predict_density -> out0 (S,N,Do).  Do = D_last (Gaussian, Bernoulli) or 1 (MultiClass).  S*N <= N_max*S_max. */
+#define DSDGP_LIK_VE 0
+#define DSDGP_LIK_PREDICT_MEAN_AND_VAR 1
+#define DSDGP_LIK_PREDICT_DENSITY 2
+DSDGP_API int dsdgp_likelihood_apply(dsdgp_ctx* ctx, int what, const float* Fmu, const float* Fvar, const float* Y, int S, int N,
+                           float* out0, float* out1, unsigned flags);
 
 /* DGP_Base._build_likelihood (dgp.py:92-98) == compute_log_likelihood(): ELBO scalar. */
 DSDGP_API int dsdgp_elbo(dsdgp_ctx* ctx, const float* X, const float* Y, int N, int S, double num_data,

@@ -13,9 +13,15 @@ def build_oracle(prob, faithful=False):
     layers = []
     for lay in prob['layers']:
         kern = kcls(lay['din'], variance=lay['var'], lengthscales=lay['ls'])
-        layer = R.SVGP_Layer(kern, lay['Z'], lay['dout'], mfs[lay['mean']](lay), white=lay['white'])
+        if lay.get('wvar') is not None:
+            kern = R.Sum([kern, R.White(lay['din'], variance=lay['wvar'])])
+        layer = R.SVGP_Layer(kern, lay['Z'], lay['dout'], mfs[lay['mean']](lay), white=lay['white'],
+                             input_prop_dim=lay.get('ipd'))
         layer.q_mu = torch.as_tensor(lay['q_mu']).clone()
         layer.q_sqrt = torch.as_tensor(lay['q_sqrt']).clone()
         layers.append(layer)
-    lik = R.MultiClass(prob['n_classes']) if prob['n_classes'] else R.Gaussian(prob['lik_var'])
+    if prob.get('lik') == 'bernoulli':
+        lik = R.Bernoulli()
+    else:
+        lik = R.MultiClass(prob['n_classes']) if prob['n_classes'] else R.Gaussian(prob['lik_var'])
     return R.DGP_Base(prob['X'], prob['Y'], lik, layers, num_samples=prob['S'], num_data=prob['num_data'])

@@ -101,6 +101,44 @@ class Matern52(Stationary):
         return self.variance * (1.0 + s5 * r + 5.0 / 3.0 * r * r) * torch.exp(-s5 * r)
 
 
+class White:
+    """gpflow.kernels.White: K(X) = variance I, K(X, X2) = 0, Kdiag = variance."""
+    def __init__(self, input_dim, variance=1.0):
+        self.input_dim = int(input_dim)
+        self.variance = _t(variance).clone()
+
+    def parameters(self):
+        return [self.variance]
+
+    def K(self, X, X2=None):
+        if X2 is None:
+            return self.variance * torch.eye(X.shape[0], dtype=DT)
+        return torch.zeros(X.shape[0], X2.shape[0], dtype=DT)
+
+    def Kdiag(self, X):
+        return self.variance * torch.ones(X.shape[0], dtype=DT)
+
+
+class Sum:
+    """gpflow.kernels.Sum (`k1 + k2`, demos/run_regression.py:65-66): K and Kdiag add."""
+    def __init__(self, kern_list):
+        self.kern_list = list(kern_list)
+        self.input_dim = self.kern_list[0].input_dim
+
+    @property
+    def variance(self):
+        return self.kern_list[0].variance
+
+    def parameters(self):
+        return [p for k in self.kern_list for p in k.parameters()]
+
+    def K(self, X, X2=None):
+        return sum(k.K(X, X2) for k in self.kern_list)
+
+    def Kdiag(self, X):
+        return sum(k.Kdiag(X) for k in self.kern_list)
+
+
 # ----------------------------------------------------------------------------
 # GPflow mean functions (call site layers.py:219)
 # ----------------------------------------------------------------------------

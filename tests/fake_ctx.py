@@ -20,7 +20,8 @@ class FakeContext:
         self.lik_code, self.K, self.D_y, self.jitter = likelihood, num_classes, D_y, jitter
         self.N_max, self.S_max = N_max, S_max
         self.p = {}
-        for l, (M, Din, Dout, kern, ard, white, mean) in enumerate(self.descs):
+        for l, (M, Din, Dout, kern, ard, white, mean, kwhite, ipd) in enumerate(self.descs):
+            self.p[(l, _lib.F_WHITE_VARIANCE)] = np.ones(()) if kwhite else None
             self.p[(l, _lib.F_Z)] = np.zeros((M, Din))
             self.p[(l, _lib.F_Q_MU)] = np.zeros((M, Dout))
             self.p[(l, _lib.F_Q_SQRT)] = np.tile(np.eye(M)[None], (Dout, 1, 1))
@@ -64,11 +65,13 @@ class FakeContext:
     def _model(self, S, num_data=1.0, X=None, Y=None):
         R.settings.jitter = self.jitter
         layers = []
-        for l, (M, Din, Dout, kern, ard, white, mean) in enumerate(self.descs):
+        for l, (M, Din, Dout, kern, ard, white, mean, kwhite, ipd) in enumerate(self.descs):
             kcls = R.RBF if kern == 0 else R.Matern52
             k = kcls(Din, variance=float(self.p[(l, _lib.F_VARIANCE)]), lengthscales=self.p[(l, _lib.F_LENGTHSCALES)])
+            if kwhite:
+                k = R.Sum([k, R.White(Din, variance=float(self.p[(l, _lib.F_WHITE_VARIANCE)]))])
             mf = [R.Zero(), R.Identity(), None][mean] or R.Linear(self.p[(l, _lib.F_MEAN_W)], self.p[(l, _lib.F_MEAN_B)])
-            lay = R.SVGP_Layer(k, self.p[(l, _lib.F_Z)], Dout, mf, white=bool(white))
+            lay = R.SVGP_Layer(k, self.p[(l, _lib.F_Z)], Dout, mf, white=bool(white), input_prop_dim=ipd or None)
             lay.q_mu = torch.as_tensor(self.p[(l, _lib.F_Q_MU)]).clone()
             lay.q_sqrt = torch.as_tensor(self.p[(l, _lib.F_Q_SQRT)]).clone()
             layers.append(lay)

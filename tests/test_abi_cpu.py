@@ -31,11 +31,11 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_struct_matches_header_layout():
     from doubly_stochastic_dgp import _lib
-    assert ctypes.sizeof(_lib.LayerDesc) == 7 * 4
+    assert ctypes.sizeof(_lib.LayerDesc) == 9 * 4
     # int L; LayerDesc[16]; int lik, K, D_y; (pad) double jitter; int N_max, S_max, device; (pad)
     assert _lib.Desc.jitter.offset % 8 == 0
     assert _lib.Desc.layers.offset == 4
-    assert ctypes.sizeof(_lib.Desc) == 4 + 16 * 28 + 12 + 8 + 12 + 4
+    assert ctypes.sizeof(_lib.Desc) == 4 + 16 * 36 + 12 + 8 + 12 + 4
 
 
 def test_create_without_gpu_fails_loudly():

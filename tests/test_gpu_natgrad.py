@@ -36,9 +36,9 @@ def _check_against_oracle(prob, ids, gamma, path, tol_elbo=None, tol_par=None):
     e0 = m.natgrad_step(var_list=var_list, gamma=gamma, zs=prob['zs'], X=prob['X'], Y=prob['Y'])
     o = build_oracle(prob)
     e0_ref = R.natgrad_step(o, ids, gamma, zs=prob['zs'])
-    # value before the update.  TF32 path: with the synthetic q_sqrt = 0.3 I on top of an ill-conditioned Kuu the variance is
-    # dominated by |L_d^T u|^2, the one GEMM that is single-pass TF32 (DESIGN.md "TF32 passes"): 1.6e-4 measured there
-    assert abs(e0 - e0_ref) <= (1e-4 if path == 0 else 5e-4) * abs(e0_ref), (e0, e0_ref)
+    # value before the update: 1e-4 on BOTH paths (round 1 waived 5e-4 on the TF32 path: with q_sqrt = 0.3 I the variance is
+    # dominated by |L_d^T u|^2, which is now a 3xTF32 product whenever q_sqrt is not negligible -- csrc/layer_tc.cu g2x3)
+    assert abs(e0 - e0_ref) <= 1e-4 * abs(e0_ref), (e0, e0_ref)
     e1 = m.compute_log_likelihood(zs=prob['zs'], X=prob['X'], Y=prob['Y'])
     e1_ref = o.compute_log_likelihood(zs=prob['zs'])
     assert abs(e1 - e1_ref) <= tol_elbo * abs(e1_ref), (e1, e1_ref)

@@ -109,17 +109,24 @@ def build_model(prob, **kw):
     from doubly_stochastic_dgp.likelihoods import Gaussian, MultiClass
     from doubly_stochastic_dgp.mean_functions import Identity, Linear, Zero
     settings.jitter = prob['jitter']
+    from doubly_stochastic_dgp.kernels import White
+    from doubly_stochastic_dgp.likelihoods import Bernoulli
     kcls = RBF if prob['kern'] == 'rbf' else Matern52
     layers = []
     for lay in prob['layers']:
         kern = kcls(lay['din'], variance=lay['var'], lengthscales=lay['ls'])
+        if lay.get('wvar') is not None:           # Sum(kernel, White)  (demos/run_regression.py:65-66)
+            kern = kern + White(lay['din'], variance=lay['wvar'])
         mf = {'zero': Zero, 'identity': Identity}.get(lay['mean'], None)
         mf = mf() if mf else Linear(lay['W'])
-        layer = SVGP_Layer(kern, lay['Z'], lay['dout'], mf, white=lay['white'])
+        layer = SVGP_Layer(kern, lay['Z'], lay['dout'], mf, white=lay['white'], input_prop_dim=lay.get('ipd'))
         layer.q_mu = lay['q_mu']
         layer.q_sqrt = lay['q_sqrt']
         layers.append(layer)
-    lik = MultiClass(prob['n_classes']) if prob['n_classes'] else Gaussian(prob['lik_var'])
+    if prob.get('lik') == 'bernoulli':
+        lik = Bernoulli()
+    else:
+        lik = MultiClass(prob['n_classes']) if prob['n_classes'] else Gaussian(prob['lik_var'])
     return DGP_Base(prob['X'], prob['Y'], lik, layers, num_samples=prob['S'], num_data=prob['num_data'], **kw)
 
 
