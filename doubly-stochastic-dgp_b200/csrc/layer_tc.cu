@@ -48,8 +48,10 @@ __global__ void k_pack_fwd(LayerSet ls, int part, Accum* acc) {
                 if (j <= jm) s0 = fmaf(Ln[j], Lk[j], s0);
                 out = tc::tf32_rna(s0 + s1);
             }
+            const bool t32 = tcp::is_tail32(M, kb);
+            if (t32 && kk >= 8) continue;
             char* dst = reinterpret_cast<char*>(P.wpack_fwd) + tcp::s_region_offset(M, D) + (size_t)d * tcp::sfull_bytes(M) +
-                        (size_t)kb * tcp::sfull_band_bytes(M) + tc::sw128_offset(n, kk);
+                        (size_t)kb * tcp::sfull_band_bytes(M) + (t32 ? tcp::sw32_offset(n, kk) : tc::sw128_offset(n, kk));
             *reinterpret_cast<float*>(dst) = out;
             continue;
         }
@@ -73,8 +75,10 @@ __global__ void k_pack_fwd(LayerSet ls, int part, Accum* acc) {
                 }
             }
         }
+        const bool t32 = tcp::is_tail32(M, kb);
+        if (t32 && kk >= 8) continue;
         char* dst = reinterpret_cast<char*>(P.wpack_fwd) + (size_t)blk * slot + tcp::band_offset(pat, M, kb) +
-                    tc::sw128_offset(n - r0, kk);
+                    (t32 ? tcp::sw32_offset(n - r0, kk) : tc::sw128_offset(n - r0, kk));
         *reinterpret_cast<float*>(dst) = out;
     }
 }
@@ -188,7 +192,7 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
             auto load_block = [&](int blk, int pat, int nslots) {
                 for (int q = 0; q < nkb; ++q) {
                     const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
-                    const uint32_t bytes = 128u * (uint32_t)tcp::band_rows(pat, M, kb);
+                    const uint32_t bytes = tcp::band_tx_bytes(pat, M, kb);
                     if (s >= nr && !alo_ok) {      // first band into A_lo: the projections must have finished reading it
                         mbar_wait(P.white ? bar_acc : bar_acc + 8, 0);
                         alo_ok = true;
@@ -215,6 +219,9 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
             int s = 0;
             const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             auto mkdesc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
+            // tail band (tc_pack.cuh tail32): SWIZZLE_32B K-major, 8-row atoms 256 B apart
+            const uint64_t desc32_hi = ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+            auto mkdesc32 = [&](uint32_t addr) { return desc32_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
             // one band block: D (+)= A * B^T, band by band.  mode 0: A_hi and A_lo against this block (B_hi of a 3xTF32
             // product), 1: A_hi only, accumulating (B_lo), 2: A_hi only (1xTF32 product, fresh accumulator).  In both band
             // orders the first band of a block spans all NPAD accumulator columns, so it is the one that clears them.
@@ -229,10 +236,11 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
                     const uint32_t bbase = slot_addr(s), abase = kb * TC_CHUNK_BYTES;
                     const uint32_t id = make_idesc_tf32(128, nrows);
                     const uint32_t dc = tmem + dcol + (uint32_t)tcp::band_row0(pat, kb);
+                    const bool t32 = tcp::is_tail32(M, kb);          // (then nks == 1)
                     if (elect_one()) {
 #pragma unroll 1
                         for (int ks = 0; ks < nks; ++ks) {
-                            const uint64_t bd = mkdesc(bbase + ks * 32), ah = mkdesc(A_hi + abase + ks * 32);
+                            const uint64_t bd = t32 ? mkdesc32(bbase) : mkdesc(bbase + ks * 32), ah = mkdesc(A_hi + abase + ks * 32);
                             mma_tf32(dc, ah, bd, id, (mode != 1 && q == 0 && ks == 0) ? 0u : 1u);
                             if (mode == 0) mma_tf32(dc, mkdesc(A_lo + abase + ks * 32), bd, id, 1u);
                         }

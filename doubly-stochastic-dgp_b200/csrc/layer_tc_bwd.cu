@@ -141,14 +141,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             for (int d = 0; d < D; ++d)
                 for (int kb = 0; kb < nkb; ++kb) {
                     if (nband++ == 2) mbar_wait(bar_au, 0);
-                    load(ssrc + (size_t)d * tcp::sfull_bytes(M) + (size_t)kb * band_full, band_full, BW_NSA);
+                    load(ssrc + (size_t)d * tcp::sfull_bytes(M) + (size_t)kb * band_full, tcp::sfull_band_tx_bytes(M, kb), BW_NSA);
                 }
             s = 0;
             const uint32_t slotb = tcp::slot_bytes(M);
             auto load_block = [&](int blk, int pat) {
                 for (int q = 0; q < nkb; ++q) {
                     const int kb = pat == tcp::PAT_GE ? nkb - 1 - q : q;
-                    load(wsrc + (size_t)blk * slotb + tcp::band_offset(pat, M, kb), 128u * (uint32_t)tcp::band_rows(pat, M, kb), BW_NR);
+                    load(wsrc + (size_t)blk * slotb + tcp::band_offset(pat, M, kb), tcp::band_tx_bytes(pat, M, kb), BW_NR);
                 }
             };
             if (!WHITE) { load_block(tcp::blk_g1(0), tcp::PAT_LE); load_block(tcp::blk_g1(1), tcp::PAT_LE); }
@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         int s = 0;
         const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         auto mkdesc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
+        // tail band (tc_pack.cuh tail32): SWIZZLE_32B K-major, 8-row atoms 256 B apart
+        const uint64_t desc32_hi = ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+        auto mkdesc32 = [&](uint32_t addr) { return desc32_hi | (uint64_t)(((addr >> 4) & 0x3FFF) | (1u << 16)); };
         // one band: D[:, n0 .. n0+nrows) (+)= A[:, 32 kb .. ) * band^T.  with_lo: also A_lo against the same band
         auto do_band = [&](uint32_t dcol, uint32_t Ahi, uint32_t Alo, int kb, int n0, int nrows, bool with_lo, bool fresh, int nslots) {
             mbar_wait(bar_full + 8 * s, (par >> s) & 1u);
@@ -168,10 +171,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             const int nks = min(4, (M - 32 * kb + 7) / 8);
             const uint32_t id = make_idesc_tf32(128, nrows);
             const uint32_t dc = tmem + dcol + (uint32_t)n0;
+            const bool t32 = tcp::is_tail32(M, kb);          // (then nks == 1)
             if (tc::elect_one()) {
 #pragma unroll 1
                 for (int ks = 0; ks < nks; ++ks) {
-                    const uint64_t bd = mkdesc(bbase + ks * 32);
+                    const uint64_t bd = t32 ? mkdesc32(bbase) : mkdesc(bbase + ks * 32);
                     mma_tf32(dc, mkdesc(Ahi + abase + ks * 32), bd, id, (fresh && ks == 0) ? 0u : 1u);
                     if (with_lo) mma_tf32(dc, mkdesc(Alo + abase + ks * 32), bd, id, 1u);
                 }

@@ -21,6 +21,20 @@ __host__ __device__ inline int band_rows(int pat, int M, int kb) {
     return pat == PAT_GE ? (NPAD < 32 * kb + 32 ? NPAD : 32 * kb + 32) : NPAD - 32 * kb;
 }
 __host__ __device__ inline int band_row0(int pat, int kb) { return pat == PAT_GE ? 0 : 32 * kb; }
+// Tail band: when the last k-block holds at most 8 real k's (M = 100: k = 96..99) it is ONE UMMA k-step.  Its image is then
+// stored with 32-byte rows (SWIZZLE_32B K-major: 8-row atoms of 256 B) instead of 128-byte rows: a quarter of the bytes for
+// the band that is mostly padding (M = 100: G2 38 -> 27.5 KB per output, S_d 56 -> 45.5 KB).  The band keeps its place in
+// the packed buffer (offsets are still computed with 128-byte rows); only the transferred size and the descriptor change.
+__host__ __device__ inline bool tail32(int M) { return M - 32 * (nkb_of(M) - 1) <= 8; }
+__host__ __device__ inline bool is_tail32(int M, int kb) { return kb == nkb_of(M) - 1 && tail32(M); }
+__host__ __device__ inline uint32_t band_tx_bytes(int pat, int M, int kb) {
+    return (is_tail32(M, kb) ? 32u : 128u) * (uint32_t)band_rows(pat, M, kb);
+}
+__host__ __device__ inline uint32_t sfull_band_tx_bytes(int M, int kb) { return (is_tail32(M, kb) ? 32u : 128u) * (uint32_t)npad_of(M); }
+// byte offset of element (row, k < 8) in a SWIZZLE_32B K-major band (256-byte aligned base): Swizzle<1,4,3>
+__host__ __device__ inline uint32_t sw32_offset(int row, int k) {
+    return (uint32_t)((row >> 3) * 256 + (row & 7) * 32 + ((((k >> 2) & 1) ^ ((row >> 2) & 1)) << 4) + ((k & 3) << 2));
+}
 // byte offset of k-block kb's band inside its block (bands are stored in MMA order)
 __host__ __device__ inline uint32_t band_offset(int pat, int M, int kb) {
     const int nkb = nkb_of(M);
