@@ -464,12 +464,29 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
             tc_fence_after();
             STAMP();  // G2[d] ready
             float s = 0.f;
-            for (int c0 = h_lo; c0 < h_hi; c0 += 8) {
-                float v[8];
-                __syncwarp();
-                tmem_ld8(lane_addr + 256 + 128 * pair + c0, v);
+            {
+                // this half's columns (<= 64) in two batches of up to four loads, one wait per batch
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) s = fmaf(v[u], v[u], s);
+                for (int b4 = 0; b4 < 2; ++b4) {
+                    uint32_t r[4][8];
+                    __syncwarp();
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8)
+                        if (h_lo + 8 * (4 * b4 + c8) < h_hi) tmem_ld8_nw(lane_addr + 256 + 128 * pair + h_lo + 8 * (4 * b4 + c8), r[c8]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        if (h_lo + 8 * (4 * b4 + c8) < h_hi) {
+#pragma unroll
+                            for (int u = 0; u < 8; u += 2) {
+                                const float a0 = __uint_as_float(r[c8][u]), a1 = __uint_as_float(r[c8][u + 1]);
+                                s0 = fmaf(a0, a0, s0); s1 = fmaf(a1, a1, s1);
+                            }
+                        }
+                    }
+                }
+                s = s0 + s1;
             }
             tc_fence_before();
             mbar_arrive(bar_acc2e + 8 * pair);

@@ -364,14 +364,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             tc_fence_after();
             BSTAMP();   // 2+d: y_d ready
             const float sc = 2.f * vb[d];
+            {
+                // this quarter's columns of y_d in two batches of two loads, one wait per batch
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-                if (c8 < nch) {
-                    float v[8];
+                for (int b2 = 0; b2 < 2; ++b2) {
+                    uint32_t r[2][8];
                     __syncwarp();
-                    tmem_ld8(lane_addr + 128 * (d & 1) + c_lo + 8 * c8, v);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) ub[8 * c8 + u] = fmaf(sc, v[u], ub[8 * c8 + u]);
+                    for (int c8 = 0; c8 < 2; ++c8)
+                        if (2 * b2 + c8 < nch) tmem_ld8_nw(lane_addr + 128 * (d & 1) + c_lo + 8 * (2 * b2 + c8), r[c8]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c8 = 0; c8 < 2; ++c8) {
+                        if (2 * b2 + c8 < nch) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                ub[8 * (2 * b2 + c8) + u] = fmaf(sc, __uint_as_float(r[c8][u]), ub[8 * (2 * b2 + c8) + u]);
+                        }
+                    }
                 }
             }
             tc_fence_before();

@@ -116,6 +116,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// non-blocking TMEM loads: issue several, then ONE tmem_ld_wait() -- a (load, wait) pair is a ~150-cycle round trip per warp,
+// so seven of them in a row made the |c_d|^2 epilogue latency-bound (0.85k cycles per output for 56 columns)
+__device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // one lane of a converged warp (deterministically the same lane every time for a full mask)
 __device__ __forceinline__ bool elect_one() {
     uint32_t p;
