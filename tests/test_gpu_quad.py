@@ -59,3 +59,39 @@ def test_quad_elbo_grad_and_natgrad_match_oracle(dims, H):
     e3, e3_ref = m.compute_log_likelihood(), o.compute_log_likelihood()
     assert e3_ref > e_ref
     assert abs(e3 - e3_ref) <= 1e-3 * abs(e3_ref), (e3, e3_ref)
+
+
+def test_I3_quadrature_equals_mean_of_sampled_elbos_on_the_device():
+    """Identity I3 of the reference (tests/test_dgp.py:120-174), on the device for BOTH models: the Gauss-Hermite ELBO of DGP_Quad
+    lies within 3 standard errors of the mean of the Monte-Carlo ELBOs of DGP_Base (in-kernel Philox draws, a fresh seed per
+    evaluation) with the same parameters, and the quadrature value is deterministic.  Fixture as in the reference: N = 2 points,
+    two RBF(1, lengthscales=0.1) layers, Gaussian(0.01), H = 300 nodes, 100 samples per evaluation; the reference first fits
+    (q_mu, q_sqrt) with L-BFGS, which the identity does not need -- random well-conditioned q here."""
+    from doubly_stochastic_dgp.dgp import DGP_Base, DGP_Quad
+    from doubly_stochastic_dgp.kernels import RBF
+    from doubly_stochastic_dgp.layer_initializations import init_layers_linear
+    from doubly_stochastic_dgp.likelihoods import Gaussian
+    from doubly_stochastic_dgp import settings
+    settings.jitter = 1e-6
+    np.random.seed(0)
+    N = 2
+    X = np.random.uniform(size=(N, 1))
+    Y = np.sin(20 * X) + np.random.randn(*X.shape) * 0.001
+    rng = np.random.default_rng(4)
+    q_mu = [0.5 * rng.normal(size=(N, 1)) for _ in range(2)]
+    q_sqrt = [np.tril(0.2 * rng.normal(size=(1, N, N))) + 0.4 * np.eye(N)[None] for _ in range(2)]
+
+    def layers():
+        ls = init_layers_linear(X, Y, X, [RBF(1, lengthscales=0.1), RBF(1, lengthscales=0.1)])
+        for l, mu, sq in zip(ls, q_mu, q_sqrt):
+            l.q_mu = mu
+            l.q_sqrt = sq
+        return ls
+
+    m_quad = DGP_Quad(X, Y, Gaussian(0.01), layers(), H=300)
+    m_mc = DGP_Base(X, Y, Gaussian(0.01), layers(), num_samples=100)
+    Lq = [m_quad.compute_log_likelihood() for _ in range(2)]
+    assert Lq[0] == Lq[1]                                              # quadrature is deterministic
+    Ls = np.array([m_mc.compute_log_likelihood() for _ in range(1000)])
+    mean, se = Ls.mean(), Ls.std() / np.sqrt(len(Ls))
+    assert abs(Lq[0] - mean) < 3 * se + 1e-4 * abs(mean), (Lq[0], mean, se)   # 99.73 % CI (+ the fp32 path's own 1e-4)
