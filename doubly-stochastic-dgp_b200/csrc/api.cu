@@ -59,7 +59,8 @@ struct LayerOff { size_t Z, q_mu, q_sqrt, ls, var, wvar; int n_ls; };
 struct dsdgp_ctx {
     dsdgp_desc desc;
     int num_sms;
-    cudaStream_t stream;
+    cudaStream_t stream;             // where steps are enqueued: own_stream, or the caller's (dsdgp_set_stream)
+    cudaStream_t own_stream;
     cudaEvent_t ev0, ev1, tm0, tm1;
     bool ev_valid;
     bool profile;
@@ -218,7 +219,8 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, desc->device));
     c->num_sms = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     CK(cudaEventCreate(&c->tm0)); CK(cudaEventCreate(&c->tm1));
     c->ev_valid = false; c->profile = false;
@@ -377,7 +379,7 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     for (int i = 0; i < 16; ++i) cudaEventDestroy(c->sa_ev[i]);
     cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3);
     for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 8; ++i) cudaEventDestroy(c->ev_dag[i]);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
     return DSDGP_OK;
 }
@@ -507,7 +509,10 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     }
     if (chain) {          // profile mode: the whole chain is reported in the first layer's forward slot
         PROF_BEGIN(5);
-        launch_chain_fwd_tc(c->ls, fc, c->num_sms, st, nl);
+        if (!launch_chain_fwd_tc(c->ls, fc, c->num_sms, st, nl)) {
+            // the cooperative launch was refused (not every CTA can be resident: MPS limits, green contexts): one launch per layer
+            for (int l = 0; l < L; ++l) launch_fwd_tc(c->ls.l[l], fc.a[l], st, nl);
+        }
         PROF_END(5);
     }
     if (mode == MODE_PROPAGATE) return DSDGP_OK;
@@ -1091,6 +1096,33 @@ int dsdgp_kl(dsdgp_ctx* c, double* kl) {
     for (int l = 0; l < c->desc.L; ++l)
         CK(cudaMemcpy(&kl[l], c->ls.l[l].scal + 3, sizeof(double), cudaMemcpyDeviceToHost));
     return DSDGP_OK;
+}
+
+// work is enqueued on a caller-supplied stream.  The side branches of the step DAG stay on the ctx's own streams
+// (joined with events), so the caller's stream sees one ordered sequence of steps.  NULL: back to the ctx's private stream.
+int dsdgp_set_stream(dsdgp_ctx* c, void* stream) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    CK(cudaSetDevice(c->desc.device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);      // graphs were captured on the old stream
+    c->graphs.clear(); c->graph_launches.clear();
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    c->ev_valid = false;
+    return DSDGP_OK;
+}
+// Device views of the flat fp32 parameter and gradient buffers (caller may read them on the ctx stream, e.g. wrap them as
+// torch tensors through __cuda_array_interface__): *n = element count; dsdgp_param_offset gives a field's position.
+int dsdgp_device_buffers(dsdgp_ctx* c, float** params, float** grads, size_t* n) {
+    if (!c) return set_err(DSDGP_ERR_INVALID, "null ctx");
+    if (params) *params = c->params;
+    if (grads) *grads = c->grads;
+    if (n) *n = c->n_params;
+    return DSDGP_OK;
+}
+long long dsdgp_param_offset(dsdgp_ctx* c, int layer, int field) {
+    if (!c) return -1;
+    if (field != DSDGP_F_LIK_VARIANCE && (layer < 0 || layer >= c->desc.L)) return -1;
+    return field_offset(c, layer, field);
 }
 
 int dsdgp_sync(dsdgp_ctx* c) {

@@ -243,7 +243,7 @@ size_t tc_fwd_pack_bytes(int M, int D, int white);
 void launch_pack_fwd(const LayerSet& ls, int part, Accum* acc, cudaStream_t st, long long* nlaunch);
 void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nlaunch);
 bool tc_chain_fwd_supported(const LayerSet& ls);
-void launch_chain_fwd_tc(const LayerSet& ls, const FwdChain& fc, int num_sms, cudaStream_t st, long long* nlaunch);
+bool launch_chain_fwd_tc(const LayerSet& ls, const FwdChain& fc, int num_sms, cudaStream_t st, long long* nlaunch);
 cudaError_t layer_tc_bwd_init();
 bool tc_bwd_supported(const LayerDev& P);
 void launch_bwd_rows_tc(const LayerDev& P, const BwdArgs& a, cudaStream_t st, long long* nlaunch);

@@ -645,12 +645,31 @@ bool tc_chain_fwd_supported(const LayerSet& ls) {
     return ls.L >= 2;      // (same M everywhere: the shared-memory carve-up, hence the mbarrier addresses, must not move)
 }
 
-void launch_chain_fwd_tc(const LayerSet& ls, const FwdChain& fc, int num_sms, cudaStream_t st, long long* nl) {
+// The chain kernel's CTAs wait on flags published by other CTAs of the same launch: every CTA must be resident at once.  The
+// launch is therefore COOPERATIVE (the driver refuses it instead of letting it hang when the grid cannot be co-resident: MPS
+// with a thread-percentage limit, green contexts, another long-lived kernel holding SMs) and the grid is sized from the
+// occupancy query, not from the SM count alone.  Returns false if the launch was refused -- the caller falls back to one
+// launch per layer.
+bool launch_chain_fwd_tc(const LayerSet& ls, const FwdChain& fc, int num_sms, cudaStream_t st, long long* nl) {
     size_t sm = 0;
     for (int l = 0; l < ls.L; ++l) sm = max(sm, tc_fwd_smem(ls.l[l].M, ls.l[l].Din, ls.l[l].Dout));
-    int grid = min(num_sms, fc.base[fc.L]);
-    k_chain_fwd_tc<8, 8><<<grid, TC_THREADS, sm, st>>>(ls, fc);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_fwd_tc<8, 8>, TC_THREADS, sm) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return false;
+    }
+    const int grid = min(num_sms * per_sm, fc.base[fc.L]);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, k_chain_fwd_tc<8, 8>, ls, fc) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
     *nl += 1;
+    return true;
 }
 
 void launch_fwd_tc(const LayerDev& P, const FwdArgs& a, cudaStream_t st, long long* nl) {

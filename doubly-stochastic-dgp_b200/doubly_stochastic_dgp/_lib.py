@@ -39,7 +39,8 @@ SYMBOLS = ["dsdgp_last_error", "dsdgp_version", "dsdgp_create", "dsdgp_destroy",
            "dsdgp_adam_init", "dsdgp_train_step", "dsdgp_kl", "dsdgp_comm_unique_id", "dsdgp_comm_init", "dsdgp_sync",
            "dsdgp_launch_count", "dsdgp_last_step_ms", "dsdgp_set_option", "dsdgp_timer_start",
            "dsdgp_timer_stop", "dsdgp_profile", "dsdgp_set_trainable", "dsdgp_natgrad_step", "dsdgp_predict_y",
-           "dsdgp_predict_density", "dsdgp_propagate_full_cov", "dsdgp_set_sample_weights", "dsdgp_likelihood_apply"]
+           "dsdgp_predict_density", "dsdgp_propagate_full_cov", "dsdgp_set_sample_weights", "dsdgp_likelihood_apply",
+           "dsdgp_set_stream", "dsdgp_device_buffers", "dsdgp_param_offset"]
 
 
 def lib_path():
@@ -91,6 +92,10 @@ def load():
     lib.dsdgp_launch_count.restype = C.c_longlong
     lib.dsdgp_last_step_ms.argtypes = [C.c_void_p, FP]
     lib.dsdgp_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    lib.dsdgp_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.dsdgp_device_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.dsdgp_param_offset.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.dsdgp_param_offset.restype = C.c_longlong
     _lib = lib
     return lib
 
@@ -367,6 +372,20 @@ class Context:
         ms = C.c_float()
         check(self.lib.dsdgp_last_step_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def set_stream(self, stream):
+        """Enqueue all following work on a caller-owned CUDA stream (int handle, e.g. torch.cuda.Stream().cuda_stream); None:
+        back to the context's own stream."""
+        check(self.lib.dsdgp_set_stream(self.h, C.c_void_p(int(stream)) if stream else None))
+
+    def device_buffers(self):
+        """(params_ptr, grads_ptr, n): device addresses of the flat fp32 parameter / gradient buffers."""
+        p, g, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        check(self.lib.dsdgp_device_buffers(self.h, C.byref(p), C.byref(g), C.byref(n)))
+        return p.value, g.value, n.value
+
+    def param_offset(self, layer, field):
+        return int(self.lib.dsdgp_param_offset(self.h, layer, field))
 
     def set_option(self, name, value):
         check(self.lib.dsdgp_set_option(self.h, name.encode(), float(value)))

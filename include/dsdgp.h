@@ -193,6 +193,16 @@ DSDGP_API int dsdgp_comm_init(dsdgp_ctx* ctx, const void* id128, int rank, int w
 /* SVGP_Layer.KL() for every layer (layers.py:221-246): kl[L], evaluated from the current parameters. */
 DSDGP_API int dsdgp_kl(dsdgp_ctx* ctx, double* kl);
 
+/* Enqueue all following work of this ctx on the caller's CUDA stream (a cudaStream_t passed as void*; NULL: the ctx's own
+ * stream).  The caller keeps ownership of the stream.  Replaces nothing upstream (the reference runs inside a TF session);
+ * SURVEY 8(b) asks for it so that a PyTorch caller can order the step against its own work. */
+DSDGP_API int dsdgp_set_stream(dsdgp_ctx* ctx, void* stream);
+/* Device pointers of the flat fp32 parameter and gradient buffers (n elements each; the gradient buffer carries two more
+ * floats, the ELBO as hi/lo) and the element offset of a field inside them (-1: no such field), for callers that keep
+ * parameters on the device (SURVEY 8(b) "caller owns ... device pointers").  The layout is documented in DESIGN.md section 3. */
+DSDGP_API int dsdgp_device_buffers(dsdgp_ctx* ctx, float** params, float** grads, size_t* n);
+DSDGP_API long long dsdgp_param_offset(dsdgp_ctx* ctx, int layer, int field);
+
 DSDGP_API int dsdgp_sync(dsdgp_ctx* ctx);
 /* Number of kernels of this library launched (or replayed inside CUDA graphs) by this ctx so far. */
 DSDGP_API long long dsdgp_launch_count(dsdgp_ctx* ctx);

@@ -296,3 +296,39 @@ def test_failed_factorisation_updates_nothing():
         assert np.isfinite(m.train_step(zs=prob['zs']))
     finally:
         settings.jitter = old
+
+
+# ------------------------------------------------------------------------------------------------ boundary
+def test_caller_stream_and_device_views_of_the_parameter_store():
+    """dsdgp_set_stream: steps enqueued on a caller-owned stream give the same result; dsdgp_device_buffers / dsdgp_param_offset:
+    the flat fp32 parameter and gradient buffers can be read on the device without a host round trip."""
+    from doubly_stochastic_dgp import _lib
+    prob = round_f32(make_problem(seed=970, dims=[8, 8, 1], N=130, M=32, S=3, inner_q_scale=0.3, num_data=1300))
+    m = build_model(prob)
+    ctx = m._ensure_ctx(prob['N'], prob['S'])
+    e_own, grads, _ = m.compute_log_likelihood_and_grad(zs=prob['zs'])
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    e_user, grads_u, _ = m.compute_log_likelihood_and_grad(zs=prob['zs'])
+    stream.synchronize()
+    assert abs(e_user - e_own) <= 1e-9 * abs(e_own)
+    assert_allclose(grads_u[0]['q_mu'], grads[0]['q_mu'], rtol=1e-5, atol=1e-6 * np.abs(grads[0]['q_mu']).max())
+    p_ptr, g_ptr, n = ctx.device_buffers()
+    assert p_ptr and g_ptr and n > 0
+    buf = torch.empty(n, dtype=torch.float32, device="cuda")
+    gbuf = torch.empty(n, dtype=torch.float32, device="cuda")
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    assert rt.cudaMemcpy(buf.data_ptr(), p_ptr, n * 4, 3) == 0       # cudaMemcpyDeviceToDevice
+    assert rt.cudaMemcpy(gbuf.data_ptr(), g_ptr, n * 4, 3) == 0
+    torch.cuda.synchronize()
+    for l, layer in enumerate(m.layers):
+        off = ctx.param_offset(l, _lib.F_Q_MU)
+        cnt = layer.q_mu.shape[0] * layer.q_mu.shape[1]
+        assert off >= 0
+        assert_allclose(buf[off:off + cnt].cpu().numpy().reshape(layer.q_mu.shape), np.float32(prob['layers'][l]['q_mu']), atol=0)
+        assert_allclose(gbuf[off:off + cnt].cpu().numpy().reshape(layer.q_mu.shape), grads_u[l]['q_mu'], rtol=1e-6, atol=1e-30)
+    assert ctx.param_offset(0, _lib.F_WHITE_VARIANCE) >= 0 and ctx.param_offset(99, _lib.F_Z) == -1
+    ctx.set_stream(None)
+    assert abs(m.compute_log_likelihood(zs=prob['zs']) - e_own) <= 1e-9 * abs(e_own)
