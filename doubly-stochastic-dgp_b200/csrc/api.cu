@@ -117,9 +117,9 @@ struct dsdgp_ctx {
     // graphs
     bool use_graph;
     int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
-    int dbg_layer; long long* dbg_buf;
+    int dbg_layer; long long* dbg_buf; bool timeline = false;
     int g2_passes;                   // 0: automatic (per layer, from the size of q_sqrt), 1 / 3: forced
-    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain;
+    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true;
     float* wpack[DSDGP_MAX_LAYERS];
     std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, int, int, unsigned>, long long> graph_launches;
@@ -451,6 +451,9 @@ int dsdgp_get_grad(dsdgp_ctx* c, int layer, int field, double* host, size_t n) {
 }
 
 // ---- one step, enqueued on the ctx stream (captured into a CUDA graph on first use) --------------------------------
+// in-graph timeline (option "timeline"): one-thread kernels that write %globaltimer behind the stages of the step DAG
+__global__ void k_stamp(long long* p) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); *p = t; }
+#define TL(i, s) do { if (c->timeline && (i) < 64) k_stamp<<<1, 1, 0, (s)>>>(c->dbg_buf + (i)); } while (0)
 #define PROF_BEGIN(i) do { if (prof) { cudaEventRecord(c->prof_ev[2 * (i)], st); c->prof_used[i] = true; } } while (0)
 #define PROF_END(i) do { if (prof) cudaEventRecord(c->prof_ev[2 * (i) + 1], st); } while (0)
 static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, long long* nl, bool prof) {
@@ -465,6 +468,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         CK(cudaMemsetAsync(c->accf, 0, c->accf_n * sizeof(float), st));
         CK(cudaMemsetAsync(c->grads, 0, (c->n_params + 2) * sizeof(float), st));
     }
+    TL(0, st);
     PROF_BEGIN(0);
     bool any_tc = false;
     for (int l = 0; l < L; ++l) any_tc |= c->path == 1 && tc_fwd_supported(c->ls.l[l]);
@@ -481,6 +485,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 4], 0));
     } else if (any_tc) launch_pack_fwd(c->ls, 0, c->acc, st, nl);
     PROF_END(0);
+    TL(1, st);
     // forward
     const bool chain = c->chain && c->path == 1 && mode != MODE_PROPAGATE && tc_chain_fwd_supported(c->ls);
     FwdChain fc;
@@ -515,6 +520,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         }
         PROF_END(5);
     }
+    TL(2, st);
     if (mode == MODE_PROPAGATE) return DSDGP_OK;
     // likelihood
     const int Rlast = (L == 1) ? N : N * S;
@@ -530,6 +536,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         launch_lik_multiclass(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.num_classes, c->mubar[L - 1],
                               c->vbar[L - 1], c->acc, c->sa_dev, grad, sw, st, nl);
     PROF_END(1);
+    TL(3, st);
     if (grad) {
         for (int l = L - 1; l >= 0; --l) {
             BwdArgs b;
@@ -542,12 +549,20 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             b.z = c->zs[l];          // injected draws, or the Philox draws the forward pass stored
             b.mubar = c->mubar[l]; b.vbar = c->vbar[l]; b.W = c->Wbuf[l];
             b.xbar = (l == 0) ? nullptr : c->xbar[l];
+            // tile hand-over between the tcgen05 row kernels of consecutive layers (same row tiling: R equal, no layer-1 fold)
+            const bool tc_l = c->path == 1 && tc_bwd_supported(c->ls.l[l]);
+            unsigned* bflags = c->chain_flags + (size_t)DSDGP_MAX_LAYERS * c->chain_max_tiles;
+            b.tile_done = tc_l ? bflags + (size_t)l * c->chain_max_tiles : nullptr;
+            b.tile_wait = nullptr;
+            if (tc_l && c->bwd_handover && l < L - 1 && l > 0 && b.S_rep == 1 && c->path == 1 && tc_bwd_supported(c->ls.l[l + 1]))
+                b.tile_wait = bflags + (size_t)(l + 1) * c->chain_max_tiles;
             b.dbg = (c->dbg_layer == 100 + l) ? c->dbg_buf : nullptr;
             b.dbg_rr = (c->dbg_layer == 200 + l) ? c->dbg_buf : nullptr;
             PROF_BEGIN(6 + 3 * l);
-            if (c->path == 1 && tc_bwd_supported(c->ls.l[l])) launch_bwd_rows_tc(c->ls.l[l], b, st, nl);
+            if (tc_l) launch_bwd_rows_tc(c->ls.l[l], b, st, nl, b.tile_wait != nullptr && !prof && !c->timeline);
             else launch_bwd_rows(c->ls.l[l], b, c->num_sms, st, nl);
             PROF_END(6 + 3 * l);
+            TL(4 + l, st);
             PROF_BEGIN(7 + 3 * l);
             // the row reductions of layer l only feed the final gradient assembly: side branch of the DAG, so they
             // overlap with the (latency-bound, second-wave-starved) row kernel of layer l-1
@@ -556,6 +571,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             if (c->path == 1 && tc_rowred_supported(c->ls.l[l])) launch_bwd_rowred_tc(c->ls.l[l], b, c->num_sms, sr, nl);
             else launch_bwd_rowred(c->ls.l[l], b, c->num_sms, sr, nl);
             PROF_END(7 + 3 * l);
+            TL(10 + l, sr);
             // gradient assembly of layer l needs only this layer's accumulators and the KL preparation (same side branch):
             // it runs behind the row reductions, off the critical path, instead of for all layers at the end of the step
             // (its own branch: queued behind the next layer's row reductions on stream2 it would delay them)
@@ -563,6 +579,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
                 CK(cudaEventRecord(c->ev_dag[2 + DSDGP_MAX_LAYERS + l], sr));
                 CK(cudaStreamWaitEvent(c->stream3, c->ev_dag[2 + DSDGP_MAX_LAYERS + l], 0));
                 launch_fin(c->ls, l, l + 1, c->acc, c->sa_dev, c->stream3, nl);
+                TL(16 + l, c->stream3);
             }
         }
         if (side) { CK(cudaEventRecord(c->ev_dag[1], c->stream2)); CK(cudaStreamWaitEvent(st, c->ev_dag[1], 0)); }
@@ -570,6 +587,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 3], c->stream3));
             CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 3], 0));
         }
+        TL(22, st);
         PROF_BEGIN(2);
         if (!(side && c->fin_per_layer)) launch_fin(c->ls, 0, L, c->acc, c->sa_dev, st, nl);
         PROF_END(2);
@@ -590,6 +608,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     launch_tail(c->params, c->free_, c->adam_m, c->adam_v, c->grads, c->kinds, c->n_params, c->sa_dev, c->acc,
                 grad ? c->off_likvar : (size_t)-1, c->comm != nullptr, mode == MODE_TRAIN, c->result_dev, st, nl);
     PROF_END(4);
+    TL(23, st);
     CK(cudaGetLastError());
     return DSDGP_OK;
 }
@@ -1148,6 +1167,10 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
         c->chain = value != 0;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "bwd_handover") {
+        c->bwd_handover = value != 0;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
     } else if (n == "fin_per_layer") {
         c->fin_per_layer = value != 0;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
@@ -1157,7 +1180,21 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     }
-    else if (n == "dbg_layer") {
+    else if (n == "timeline") {
+        c->timeline = value != 0;
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemset(c->dbg_buf, 0, 64 * sizeof(long long)));
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "timeline_dump") {
+        long long h[64];
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpy(h, c->dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+        static const char* nm[24] = {"start", "prep+pack", "fwd chain", "likelihood", "bwd L1", "bwd L2", "bwd L3", "bwd L4", "bwd L5", "bwd L6",
+                                     "rowred L1", "rowred L2", "rowred L3", "rowred L4", "rowred L5", "rowred L6",
+                                     "fin L1", "fin L2", "fin L3", "fin L4", "fin L5", "fin L6", "joined", "tail"};
+        for (int i = 0; i < 24; ++i) if (h[i]) fprintf(stderr, "timeline %-12s end at %8.1f us\n", nm[i], (h[i] - h[0]) * 1e-3);
+    } else if (n == "dbg_layer") {
         c->dbg_layer = (int)value;
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaMemset(c->dbg_buf, 0, 64 * sizeof(long long)));

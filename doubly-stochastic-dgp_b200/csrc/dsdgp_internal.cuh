@@ -215,6 +215,11 @@ struct BwdArgs {
     const StepArgs* sa;
     long long* dbg;       // optional clock64() stamps of CTA 0 (diagnostics), else NULL
     long long* dbg_rr;    // the same for the row-reduction kernel
+    // tile-level hand-over between the row kernels of consecutive layers (tcgen05 path): tile t of layer l reads only what
+    // tile t of layer l+1 wrote (xbar rows of the same 128-row tile), so the kernel of layer l is launched as a programmatic
+    // dependent of the kernel of layer l+1 and each tile waits for ITS producer's flag (== StepArgs::epoch) instead of the grid
+    unsigned* tile_done;          // [tiles] written by this launch when a tile's outputs are published, or NULL
+    const unsigned* tile_wait;    // [tiles] flags of the upstream launch to wait for before reading fbar, or NULL
 };
 
 void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* sa, cudaStream_t st, cudaStream_t st_kl,
@@ -246,7 +251,7 @@ bool tc_chain_fwd_supported(const LayerSet& ls);
 bool launch_chain_fwd_tc(const LayerSet& ls, const FwdChain& fc, int num_sms, cudaStream_t st, long long* nlaunch);
 cudaError_t layer_tc_bwd_init();
 bool tc_bwd_supported(const LayerDev& P);
-void launch_bwd_rows_tc(const LayerDev& P, const BwdArgs& a, cudaStream_t st, long long* nlaunch);
+void launch_bwd_rows_tc(const LayerDev& P, const BwdArgs& a, cudaStream_t st, long long* nlaunch, bool programmatic = false);
 cudaError_t rowred_tc_init();
 bool tc_rowred_supported(const LayerDev& P);
 void launch_bwd_rowred_tc(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);

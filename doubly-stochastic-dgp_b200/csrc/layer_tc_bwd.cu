@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     const uint32_t band_full = 128u * (uint32_t)NPAD;           // one k-block of a square (S_d) operand
     auto slot_addr = [&](int s) { return s < BW_NR ? ring + (uint32_t)s * band_full : A_c + (uint32_t)(s - BW_NR) * band_full; };
 
+    // every CTA of this grid is resident (or done) once the last one has issued this: from then on the next layer's row kernel
+    // (launched as a programmatic dependent) may take the SMs this grid's tail wave leaves idle; its tiles wait on tile_done
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
         for (int s = 0; s < BW_NSA; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_au, TC_ROWTHREADS);
@@ -262,6 +265,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         float xs[DINP];
 #pragma unroll
         for (int q = 0; q < DINP; ++q) xs[q] = valid ? a.Xin[(size_t)row * Din + q] : 0.f;
+        if (a.tile_wait) {       // upstream dE/dF of this tile's rows: published by tile blockIdx.x of the previous launch
+            if (lane == 0) {
+                const unsigned epoch = a.sa->epoch;
+                while (ld_acquire_gpu(a.tile_wait + blockIdx.x) != epoch) __nanosleep(100);
+            }
+            __syncwarp();
+        }
         // mubar / vbar (this quarter: d = qt, qt+4, ...)
         constexpr int NDQ = (DOUTP + 3) / 4;
         float fv[NDQ], fm[NDQ], fz[NDQ];
@@ -632,6 +642,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
     }
     tc_fence_before();
     __syncthreads();
+    if (a.tile_done && threadIdx.x == 0) {      // xbar / mubar / vbar / W of this tile are written (barrier above): publish
+        __threadfence();
+        st_release_gpu(a.tile_done + blockIdx.x, a.sa->epoch);
+    }
     if (warp == TC_WARP_TMA) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
@@ -654,11 +668,17 @@ cudaError_t layer_tc_bwd_init() {
     return cudaSuccess;
 }
 
-void launch_bwd_rows_tc(const LayerDev& P, const BwdArgs& a, cudaStream_t st, long long* nl) {
+void launch_bwd_rows_tc(const LayerDev& P, const BwdArgs& a, cudaStream_t st, long long* nl, bool programmatic) {
     int grid = (a.R + TC_ROWS - 1) / TC_ROWS;
     size_t sm = bwd_smem_plan(P.M, P.Din, P.Dout).total + 1024;
     const bool wh = P.white != 0;
-#define X(a_, b_, k_, w_) if (P.Din == a_ && P.Dout == b_ && P.kern == k_ && wh == w_) k_layer_bwd_tc<a_, b_, k_, w_><<<grid, TC_THREADS, sm, st>>>(P, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = programmatic ? 1 : 0;
+#define X(a_, b_, k_, w_) if (P.Din == a_ && P.Dout == b_ && P.kern == k_ && wh == w_) cudaLaunchKernelEx(&cfg, k_layer_bwd_tc<a_, b_, k_, w_>, P, a);
     TC_BWD_INSTANCES(X)
 #undef X
     *nl += 1;
