@@ -98,6 +98,9 @@ struct dsdgp_ctx {
     float* vbar[DSDGP_MAX_LAYERS];
     float* Wbuf[DSDGP_MAX_LAYERS];
     cudaStream_t stream2;                       // side branch of the step DAG (KL prep, row reductions)
+    cudaStream_t stream_tl[4]; cudaEvent_t ev_tl[28]; bool tl_used[4] = {false, false, false, false};   // timeline stamps
+    cudaStream_t stream5, stream6; cudaEvent_t ev_fin[2 * DSDGP_MAX_LAYERS];   // second half of a layer's assembly (fork / join)
+    cudaStream_t stream4;                       // (the per-layer assemblies alternate between stream3 and stream4)
     cudaStream_t stream3;                       // second side branch: per-layer gradient assembly behind the row reductions
     cudaEvent_t ev_dag[2 * DSDGP_MAX_LAYERS + 8];
     bool overlap;
@@ -119,7 +122,7 @@ struct dsdgp_ctx {
     int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
     int dbg_layer; long long* dbg_buf; bool timeline = false;
     int g2_passes;                   // 0: automatic (per layer, from the size of q_sqrt), 1 / 3: forced
-    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true;
+    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true; bool lik_handover = false;
     float* wpack[DSDGP_MAX_LAYERS];
     std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, int, int, unsigned>, long long> graph_launches;
@@ -219,7 +222,13 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, desc->device));
     c->num_sms = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    // the main branch of the step DAG (factorisation -> forward chain -> backward row kernels) is the critical path: its CTAs
+    // go ahead of the side branches' (row reductions, gradient assembly) whenever both wait for an SM
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const char* pe = getenv("DSDGP_STREAM_PRIORITY");
+    if (pe && pe[0] == '0') prio_hi = prio_lo;
+    CK(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_hi));
     c->stream = c->own_stream;
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     CK(cudaEventCreate(&c->tm0)); CK(cudaEventCreate(&c->tm1));
@@ -303,8 +312,19 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
     for (int l = 0; l < L; ++l) { Dmax = max(Dmax, (size_t)desc->layers[l].D_out); Mmax = max(Mmax, (size_t)desc->layers[l].M); }
     CK(dmalloc(&c->Xd, (size_t)desc->N_max * desc->layers[0].D_in));
     CK(dmalloc(&c->Yd, (size_t)desc->N_max * desc->D_y));
-    CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    {
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
+        // (the small assembly launches go first: they free their dependants and leave the SMs within microseconds)
+        CK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));
+        CK(cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prio_hi));
+        CK(cudaStreamCreateWithPriority(&c->stream5, cudaStreamNonBlocking, prio_hi));
+        CK(cudaStreamCreateWithPriority(&c->stream6, cudaStreamNonBlocking, prio_hi));
+        for (int i = 0; i < 2 * DSDGP_MAX_LAYERS; ++i) CK(cudaEventCreateWithFlags(&c->ev_fin[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 4; ++i) CK(cudaStreamCreateWithFlags(&c->stream_tl[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 28; ++i) CK(cudaEventCreateWithFlags(&c->ev_tl[i], cudaEventDisableTiming));
     for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 8; ++i) CK(cudaEventCreateWithFlags(&c->ev_dag[i], cudaEventDisableTiming));
     c->overlap = true; c->fin_per_layer = true;
     (void)Dmax; (void)Mmax;
@@ -353,7 +373,7 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
     c->dbg_layer = -1; CK(dmalloc(&c->dbg_buf, 64));
     c->g2_passes = 0;
     c->chain_max_tiles = (int)((Rmax + 127) / 128);
-    CK(dmalloc(&c->chain_flags, (size_t)2 * DSDGP_MAX_LAYERS * c->chain_max_tiles));
+    CK(dmalloc(&c->chain_flags, (size_t)(2 * DSDGP_MAX_LAYERS + 1) * c->chain_max_tiles));   // forward | backward | likelihood
     c->epoch = 0; c->chain = true;
     return DSDGP_OK;
 }
@@ -377,7 +397,9 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
     for (int i = 0; i < 2 * (5 + 3 * DSDGP_MAX_LAYERS); ++i) cudaEventDestroy(c->prof_ev[i]);
     for (int i = 0; i < 16; ++i) cudaEventDestroy(c->sa_ev[i]);
-    cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3);
+    cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3); cudaStreamDestroy(c->stream4); cudaStreamDestroy(c->stream5); cudaStreamDestroy(c->stream6);
+    for (int i = 0; i < 2 * DSDGP_MAX_LAYERS; ++i) cudaEventDestroy(c->ev_fin[i]); for (int i = 0; i < 4; ++i) cudaStreamDestroy(c->stream_tl[i]);
+    for (int i = 0; i < 28; ++i) cudaEventDestroy(c->ev_tl[i]);
     for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 8; ++i) cudaEventDestroy(c->ev_dag[i]);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -453,7 +475,16 @@ int dsdgp_get_grad(dsdgp_ctx* c, int layer, int field, double* host, size_t n) {
 // ---- one step, enqueued on the ctx stream (captured into a CUDA graph on first use) --------------------------------
 // in-graph timeline (option "timeline"): one-thread kernels that write %globaltimer behind the stages of the step DAG
 __global__ void k_stamp(long long* p) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); *p = t; }
-#define TL(i, s) do { if (c->timeline && (i) < 64) k_stamp<<<1, 1, 0, (s)>>>(c->dbg_buf + (i)); } while (0)
+// (on a stamp stream of their own behind an event, so that the kernel -> kernel order of the stamped stream -- and with it the
+// programmatic launch of the next row kernel -- is what it is without the stamps; one stamp stream per branch of the DAG: the
+// stamps of one branch are ordered anyway, a shared stream would hold a stamp back behind another branch's earlier-enqueued one)
+#define TL(i, s) do { if (c->timeline && (i) < 24) { \
+        const int ti_ = (s) == c->stream2 ? 1 : (s) == c->stream3 ? 2 : (s) == c->stream4 ? 3 : 0; \
+        cudaStream_t tls_ = c->stream_tl[ti_]; c->tl_used[ti_] = true; \
+        cudaEventRecord(c->ev_tl[i], (s)); cudaStreamWaitEvent(tls_, c->ev_tl[i], 0); \
+        k_stamp<<<1, 1, 0, tls_>>>(c->dbg_buf + (i)); } } while (0)
+#define TL_JOIN() do { if (c->timeline) for (int j_ = 0; j_ < 4; ++j_) if (c->tl_used[j_]) { c->tl_used[j_] = false; \
+        CK(cudaEventRecord(c->ev_tl[24 + j_], c->stream_tl[j_])); CK(cudaStreamWaitEvent(st, c->ev_tl[24 + j_], 0)); } } while (0)
 #define PROF_BEGIN(i) do { if (prof) { cudaEventRecord(c->prof_ev[2 * (i)], st); c->prof_used[i] = true; } } while (0)
 #define PROF_END(i) do { if (prof) cudaEventRecord(c->prof_ev[2 * (i) + 1], st); } while (0)
 static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, long long* nl, bool prof) {
@@ -512,21 +543,35 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         else launch_fwd(c->ls.l[l], a, c->num_sms, st, nl);
         PROF_END(5 + 3 * l);
     }
+    bool chained = false;
     if (chain) {          // profile mode: the whole chain is reported in the first layer's forward slot
         PROF_BEGIN(5);
-        if (!launch_chain_fwd_tc(c->ls, fc, c->num_sms, st, nl)) {
+        chained = launch_chain_fwd_tc(c->ls, fc, c->num_sms, st, nl);
+        if (!chained) {
             // the cooperative launch was refused (not every CTA can be resident: MPS limits, green contexts): one launch per layer
             for (int l = 0; l < L; ++l) launch_fwd_tc(c->ls.l[l], fc.a[l], st, nl);
         }
         PROF_END(5);
     }
     TL(2, st);
-    if (mode == MODE_PROPAGATE) return DSDGP_OK;
+    if (mode == MODE_PROPAGATE) {
+        TL_JOIN();
+        return DSDGP_OK;
+    }
     // likelihood
     const int Rlast = (L == 1) ? N : N * S;
     const float* sw = (c->sw_n > 0 && L > 1) ? c->sw_dev : nullptr;
     PROF_BEGIN(1);
-    if (c->desc.likelihood == DSDGP_LIK_GAUSSIAN)
+    // tile hand-over forward chain -> likelihood -> last layer's backward rows (Gaussian, tcgen05 row kernel)
+    unsigned* lik_flags = c->chain_flags + (size_t)(2 * DSDGP_MAX_LAYERS) * c->chain_max_tiles;
+    const bool lik_tiled = c->desc.likelihood == DSDGP_LIK_GAUSSIAN && grad && c->bwd_handover && c->lik_handover && c->path == 1 &&
+                           tc_bwd_supported(c->ls.l[L - 1]);
+    if (lik_tiled)
+        launch_lik_gaussian_tiled(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.D_y, c->params + c->off_likvar,
+                                  c->mubar[L - 1], c->vbar[L - 1], c->acc, c->sa_dev, grad, sw,
+                                  chained ? c->chain_flags + (size_t)(L - 1) * c->chain_max_tiles : nullptr, lik_flags,
+                                  chained && !prof, st, nl);
+    else if (c->desc.likelihood == DSDGP_LIK_GAUSSIAN)
         launch_lik_gaussian(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.D_y, c->params + c->off_likvar,
                             c->mubar[L - 1], c->vbar[L - 1], c->acc, c->sa_dev, grad, sw, st, nl);
     else if (c->desc.likelihood == DSDGP_LIK_BERNOULLI)
@@ -538,6 +583,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     PROF_END(1);
     TL(3, st);
     if (grad) {
+        bool fin_used[2] = {false, false};
         for (int l = L - 1; l >= 0; --l) {
             BwdArgs b;
             b.Xin = (l == 0) ? c->Xd : c->F[l - 1];
@@ -553,13 +599,17 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             const bool tc_l = c->path == 1 && tc_bwd_supported(c->ls.l[l]);
             unsigned* bflags = c->chain_flags + (size_t)DSDGP_MAX_LAYERS * c->chain_max_tiles;
             b.tile_done = tc_l ? bflags + (size_t)l * c->chain_max_tiles : nullptr;
-            b.tile_wait = nullptr;
+            b.tile_wait = nullptr; b.wait_before_loads = 0;
+            // behind the forward chain's tail NOTHING of a tile may be read before its flag: on a small problem every launch of
+            // the backward chain is resident while the forward pass still runs (the flags order tile t of all of them)
+            if (tc_l && l == L - 1 && lik_tiled) b.tile_wait = lik_flags;
+            b.wait_before_loads = lik_tiled && chained;
             if (tc_l && c->bwd_handover && l < L - 1 && l > 0 && b.S_rep == 1 && c->path == 1 && tc_bwd_supported(c->ls.l[l + 1]))
                 b.tile_wait = bflags + (size_t)(l + 1) * c->chain_max_tiles;
             b.dbg = (c->dbg_layer == 100 + l) ? c->dbg_buf : nullptr;
             b.dbg_rr = (c->dbg_layer == 200 + l) ? c->dbg_buf : nullptr;
             PROF_BEGIN(6 + 3 * l);
-            if (tc_l) launch_bwd_rows_tc(c->ls.l[l], b, st, nl, b.tile_wait != nullptr && !prof && !c->timeline);
+            if (tc_l) launch_bwd_rows_tc(c->ls.l[l], b, st, nl, b.tile_wait != nullptr && !prof);
             else launch_bwd_rows(c->ls.l[l], b, c->num_sms, st, nl);
             PROF_END(6 + 3 * l);
             TL(4 + l, st);
@@ -577,15 +627,26 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             // (its own branch: queued behind the next layer's row reductions on stream2 it would delay them)
             if (side && c->fin_per_layer) {
                 CK(cudaEventRecord(c->ev_dag[2 + DSDGP_MAX_LAYERS + l], sr));
-                CK(cudaStreamWaitEvent(c->stream3, c->ev_dag[2 + DSDGP_MAX_LAYERS + l], 0));
-                launch_fin(c->ls, l, l + 1, c->acc, c->sa_dev, c->stream3, nl);
-                TL(16 + l, c->stream3);
+                // (alternating between two streams: a layer's assembly is a chain of small launches that has to find room
+                // next to the row kernels' CTAs -- ~30-60 us per layer -- and must not queue behind the previous layer's)
+                cudaStream_t sf = (l & 1) ? c->stream4 : c->stream3;
+                CK(cudaStreamWaitEvent(sf, c->ev_dag[2 + DSDGP_MAX_LAYERS + l], 0));
+                // the two halves of the assembly are independent: variational parameters on stream5/6, kernel side on sf
+                CK(cudaEventRecord(c->ev_fin[2 * l], sf));
+                cudaStream_t sq = (l & 1) ? c->stream6 : c->stream5;
+                CK(cudaStreamWaitEvent(sq, c->ev_fin[2 * l], 0));
+                launch_fin(c->ls, l, l + 1, c->acc, c->sa_dev, sq, nl, 1);
+                CK(cudaEventRecord(c->ev_fin[2 * l + 1], sq));
+                launch_fin(c->ls, l, l + 1, c->acc, c->sa_dev, sf, nl, 2);
+                CK(cudaStreamWaitEvent(sf, c->ev_fin[2 * l + 1], 0));
+                TL(16 + l, sf);
+                fin_used[l & 1] = true;
             }
         }
         if (side) { CK(cudaEventRecord(c->ev_dag[1], c->stream2)); CK(cudaStreamWaitEvent(st, c->ev_dag[1], 0)); }
         if (side && c->fin_per_layer) {
-            CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 3], c->stream3));
-            CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 3], 0));
+            if (fin_used[0]) { CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 3], c->stream3)); CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 3], 0)); }
+            if (fin_used[1]) { CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 5], c->stream4)); CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 5], 0)); }
         }
         TL(22, st);
         PROF_BEGIN(2);
@@ -609,6 +670,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
                 grad ? c->off_likvar : (size_t)-1, c->comm != nullptr, mode == MODE_TRAIN, c->result_dev, st, nl);
     PROF_END(4);
     TL(23, st);
+    TL_JOIN();
     CK(cudaGetLastError());
     return DSDGP_OK;
 }
@@ -1165,6 +1227,10 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     else if (n == "profile") c->profile = value != 0;
     else if (n == "chain") {
         c->chain = value != 0;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "lik_handover") {
+        c->lik_handover = value != 0;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     } else if (n == "bwd_handover") {

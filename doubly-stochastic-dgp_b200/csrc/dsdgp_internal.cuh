@@ -220,6 +220,7 @@ struct BwdArgs {
     // dependent of the kernel of layer l+1 and each tile waits for ITS producer's flag (== StepArgs::epoch) instead of the grid
     unsigned* tile_done;          // [tiles] written by this launch when a tile's outputs are published, or NULL
     const unsigned* tile_wait;    // [tiles] flags of the upstream launch to wait for before reading fbar, or NULL
+    int wait_before_loads;        // 1: nothing of the tile may be read before the flag (last layer behind the forward tail)
 };
 
 void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* sa, cudaStream_t st, cudaStream_t st_kl,
@@ -227,7 +228,10 @@ void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* 
 void launch_fwd(const LayerDev& P, const FwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
 void launch_bwd_rows(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
 void launch_bwd_rowred(const LayerDev& P, const BwdArgs& a, int num_sms, cudaStream_t st, long long* nlaunch);
-void launch_fin(const LayerSet& ls, int l0, int l1, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nlaunch);
+void launch_fin(const LayerSet& ls, int l0, int l1, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nlaunch, int part = 0);
+void launch_lik_gaussian_tiled(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy, const float* lik_var,
+                               float* mubar, float* vbar, Accum* acc, const StepArgs* sa, int want_grad, const float* sw,
+                               const unsigned* tile_wait, unsigned* tile_done, bool programmatic, cudaStream_t st, long long* nl);
 void launch_lik_gaussian(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy,
                          const float* lik_var, float* mubar, float* vbar, Accum* acc, const StepArgs* sa,
                          int want_grad, const float* sample_w, cudaStream_t st, long long* nlaunch);

@@ -581,6 +581,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_chain_fwd_tc(const __grid_con
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
     __shared__ uint32_t tmem_slot_s;
     const int warp = threadIdx.x >> 5;
+    // the likelihood and the last layer's backward rows are programmatic dependents that wait on this kernel's tile flags:
+    // they take the SMs of the CTAs that have no task left in the last round
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == TC_WARP_TMA) tmem_alloc(smem_u32(&tmem_slot_s), 512);
     tc_fence_before();
     __syncthreads();

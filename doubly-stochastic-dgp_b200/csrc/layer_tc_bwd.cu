@@ -254,6 +254,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
 
         // ---- R0 / R1: every global load of the tile's inputs is issued before the first dependent instruction: a dependent
         // round trip costs ~2k cycles here (measured: x 2.1k, mubar/vbar 1.9k per d, u 2-5k when they were serialised)
+        // upstream dE/dF of this tile's rows: published by tile blockIdx.x of the previous launch.  Behind another backward
+        // launch only fbar is new (U, x, Fvar, z date from the forward pass), behind the forward chain's tail everything is
+        auto wait_upstream = [&]() {
+            if (a.tile_wait) {
+                if (lane == 0) {
+                    const unsigned epoch = a.sa->epoch;
+                    while (ld_acquire_gpu(a.tile_wait + blockIdx.x) != epoch) __nanosleep(100);
+                }
+                __syncwarp();
+            }
+        };
+        if (a.wait_before_loads) wait_upstream();
         auto load_u4 = [&](int c0) -> float4 {       // M % 4 == 0 (tc_bwd_supported)
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid && c0 < c_hi && c0 + 4 <= M) v = *reinterpret_cast<const float4*>(a.U + (size_t)row * M + c0);
@@ -265,13 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         float xs[DINP];
 #pragma unroll
         for (int q = 0; q < DINP; ++q) xs[q] = valid ? a.Xin[(size_t)row * Din + q] : 0.f;
-        if (a.tile_wait) {       // upstream dE/dF of this tile's rows: published by tile blockIdx.x of the previous launch
-            if (lane == 0) {
-                const unsigned epoch = a.sa->epoch;
-                while (ld_acquire_gpu(a.tile_wait + blockIdx.x) != epoch) __nanosleep(100);
-            }
-            __syncwarp();
-        }
+        if (!a.wait_before_loads) wait_upstream();
         // mubar / vbar (this quarter: d = qt, qt+4, ...)
         constexpr int NDQ = (DOUTP + 3) / 4;
         float fv[NDQ], fm[NDQ], fz[NDQ];
@@ -294,6 +300,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
             if (qt == 0) xs_s[t * Din + q] = xs[q];
         }
         BSTAMP();   // 1: inputs loaded
+        float fsum[NDQ], fsz[NDQ];
+#pragma unroll
+        for (int j = 0; j < NDQ; ++j) { fsum[j] = 0.f; fsz[j] = 0.f; }
+        if (!single && a.fbar && valid) {
+            // layer-1 fold: the row's S samples.  Four samples of every d of this thread are loaded before the first use
+            // (one sample at a time this was 2 * S dependent round trips of ~2k cycles: half of the 8-tile launch's 77 us)
+#pragma unroll 1
+            for (int s0 = 0; s0 < a.S_rep; s0 += 4) {
+                float fb[4][NDQ], zz[4][NDQ];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int j = 0; j < NDQ; ++j) {
+                        const int d = qt + 4 * j;
+                        const bool ok = s0 + e < a.S_rep && d < D;
+                        const size_t o = ((size_t)(s0 + e) * a.N + row) * D + d;
+                        fb[e][j] = ok ? a.fbar[o] : 0.f;
+                        zz[e][j] = ok ? a.z[o] : 0.f;
+                    }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int j = 0; j < NDQ; ++j) { fsum[j] += fb[e][j]; fsz[j] = fmaf(fb[e][j], zz[e][j], fsz[j]); }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < NDQ; ++j) {
             const int d = qt + 4 * j;
@@ -305,15 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                         const float sd = sqrtf(fmaxf(fv[j] + jit, 1e-30f));
                         float sz;
                         if (single) { m = fm[j]; sz = fm[j] * fz[j]; }
-                        else {
-                            sz = 0.f;
-#pragma unroll 1
-                            for (int ss = 0; ss < a.S_rep; ++ss) {      // layer-1 dedup: the row's S samples
-                                const size_t o = ((size_t)ss * a.N + row) * D + d;
-                                const float fb = a.fbar[o];
-                                m += fb; sz = fmaf(fb, a.z[o], sz);
-                            }
-                        }
+                        else { m = fsum[j]; sz = fsz[j]; }
                         v = sz / (2.f * sd);
                         a.mubar[(size_t)row * D + d] = m;
                         a.vbar[(size_t)row * D + d] = v;

@@ -16,6 +16,11 @@ __constant__ double c_gh_w[20] = {
     0.0032437733422378567, 0.00022833863601635365, 7.8025564785320599e-06, 1.0860693707692782e-07,
     4.3993409922731747e-10, 2.2293936455341447e-13};
 
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 // Gaussian: VE = -1/2 log 2pi - 1/2 log s2 - 1/2 ((y-mu)^2 + v)/s2 ; rows r = s*N + n share y_n (utils.py:72-73)
 __global__ void k_lik_gaussian(const float* __restrict__ Fmean, const float* __restrict__ Fvar, const float* __restrict__ Y,
                                int R, int N, int Dy, const float* __restrict__ lik_var, float* __restrict__ mubar,
@@ -43,6 +48,63 @@ __global__ void k_lik_gaussian(const float* __restrict__ Fmean, const float* __r
         atomicAdd(&acc->lik, ve);
         if (want_grad) atomicAdd(&acc->glikvar, gl);
     }
+}
+
+// The same per 128-row tile of the last layer (the tiling of the tcgen05 kernels): block b waits for forward tile b's flag and
+// publishes its own, so the likelihood and the last layer's backward rows start under the forward chain's tail wave.
+__global__ void __launch_bounds__(128) k_lik_gaussian_tiled(const float* __restrict__ Fmean, const float* __restrict__ Fvar,
+                                                            const float* __restrict__ Y, int R, int N, int Dy,
+                                                            const float* __restrict__ lik_var, float* __restrict__ mubar,
+                                                            float* __restrict__ vbar, Accum* acc, const StepArgs* sa, int want_grad,
+                                                            const float* __restrict__ sw, const unsigned* tile_wait,
+                                                            unsigned* tile_done) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const unsigned epoch = sa->epoch;
+    if (tile_wait) {
+        if (threadIdx.x == 0)
+            while (ld_acquire_gpu_u32(tile_wait + blockIdx.x) != epoch) __nanosleep(200);
+        __syncthreads();
+    }
+    const double s2 = (double)lik_var[0], c0 = sa->lik_scale;
+    const double base = -0.5 * 1.8378770664093453 - 0.5 * log(s2);
+    double ve = 0.0, gl = 0.0;
+    const size_t i0 = (size_t)blockIdx.x * 128 * Dy, i1 = min((size_t)R * Dy, i0 + (size_t)128 * Dy);
+    for (size_t idx = i0 + threadIdx.x; idx < i1; idx += 128) {
+        int r = idx / Dy, d = idx % Dy, n = r % N;
+        const double c = sw ? c0 * (double)sw[r / N] : c0;
+        double y = Y[(size_t)n * Dy + d], mu = Fmean[idx], v = Fvar[idx];
+        double e2 = (y - mu) * (y - mu) + v;
+        ve += c * (base - 0.5 * e2 / s2);
+        if (want_grad) {
+            mubar[idx] = (float)(c * (y - mu) / s2);
+            vbar[idx] = (float)(-0.5 * c / s2);
+            gl += c * (-0.5 / s2 + 0.5 * e2 / (s2 * s2));
+        }
+    }
+    ve = warp_sum_d(ve); gl = warp_sum_d(gl);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&acc->lik, ve);
+        if (want_grad) atomicAdd(&acc->glikvar, gl);
+    }
+    __syncthreads();
+    if (tile_done && threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(tile_done + blockIdx.x), "r"(epoch) : "memory");
+    }
+}
+
+void launch_lik_gaussian_tiled(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy, const float* lik_var,
+                               float* mubar, float* vbar, Accum* acc, const StepArgs* sa, int want_grad, const float* sw,
+                               const unsigned* tile_wait, unsigned* tile_done, bool programmatic, cudaStream_t st, long long* nl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((R + 127) / 128); cfg.blockDim = dim3(128); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = programmatic ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_lik_gaussian_tiled, Fmean, Fvar, Y, R, N, Dy, lik_var, mubar, vbar, acc, sa, want_grad, sw, tile_wait,
+                       tile_done);
+    *nl += 1;
 }
 
 void launch_lik_gaussian(const float* Fmean, const float* Fvar, const float* Y, int R, int N, int Dy, const float* lik_var,

@@ -801,7 +801,9 @@ __global__ void k_elbo_finish(Accum* acc, const StepArgs* sa, float* glikvar, fl
 
 // layers [l0, l1): everything here depends only on that layer's accumulators and on the KL preparation, so the step DAG
 // runs it per layer on the side branch right behind the layer's row reductions (api.cu)
-void launch_fin(const LayerSet& ls, int l0, int l1, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nl) {
+// part 0 = everything; the two halves are independent of each other and may run on different streams:
+// part 1 = variational parameters (q_sqrt, q_mu), part 2 = kernel side (whitened chain, Kuu-bar, Z / hyper-parameters)
+void launch_fin(const LayerSet& ls, int l0, int l1, Accum* acc, const StepArgs* sa, cudaStream_t st, long long* nl, int part) {
     int Mmax = 0, Dmax = 0, MDmax = 0, MDin = 0;
     bool any_white = false;
     const int nL = l1 - l0;
@@ -811,15 +813,18 @@ void launch_fin(const LayerSet& ls, int l0, int l1, Accum* acc, const StepArgs* 
         any_white |= ls.l[l].white != 0;
     }
     int nb = (Mmax * Mmax + 255) / 256;
-    if (ls.fin_algo == 1) {
-        const int nt = (Mmax + FT - 1) / FT;
-        k_fin_qsqrt_t<<<dim3(nt * (nt + 1) / 2, Dmax, nL), 256, 0, st>>>(ls, sa, l0);
-        k_fin_qmu_w<<<dim3((MDmax + 7) / 8, nL), 256, 0, st>>>(ls, sa, l0);
-    } else {
-        k_fin_qsqrt<<<dim3(nb, Dmax, nL), 256, 0, st>>>(ls, sa, l0);
-        k_fin_qmu<<<dim3((MDmax + 255) / 256, nL), 256, 0, st>>>(ls, sa, l0);
+    if (part != 2) {
+        if (ls.fin_algo == 1) {
+            const int nt = (Mmax + FT - 1) / FT;
+            k_fin_qsqrt_t<<<dim3(nt * (nt + 1) / 2, Dmax, nL), 256, 0, st>>>(ls, sa, l0);
+            k_fin_qmu_w<<<dim3((MDmax + 7) / 8, nL), 256, 0, st>>>(ls, sa, l0);
+        } else {
+            k_fin_qsqrt<<<dim3(nb, Dmax, nL), 256, 0, st>>>(ls, sa, l0);
+            k_fin_qmu<<<dim3((MDmax + 255) / 256, nL), 256, 0, st>>>(ls, sa, l0);
+        }
+        *nl += 2;
     }
-    *nl += 2;
+    if (part == 1) return;
     if (any_white) {
         k_fin_w1<<<dim3(nb, nL), 256, 0, st>>>(ls, l0);
         k_fin_w2<<<dim3(nb, nL), 256, 0, st>>>(ls, l0);
