@@ -494,19 +494,23 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     const float jit = (float)c->desc.jitter;
     const bool grad = mode >= MODE_GRAD;
     const bool side = grad && c->overlap && !prof;      // two-branch DAG (captured into the graph as parallel branches)
+    bool any_tc = false;
+    for (int l = 0; l < L; ++l) any_tc |= c->path == 1 && tc_fwd_supported(c->ls.l[l]);
+    const bool split_pack = any_tc && side;
     CK(cudaMemsetAsync(c->acc, 0, sizeof(Accum), st));
-    if (grad) {
+    if (grad && !split_pack) {
         CK(cudaMemsetAsync(c->accf, 0, c->accf_n * sizeof(float), st));
         CK(cudaMemsetAsync(c->grads, 0, (c->n_params + 2) * sizeof(float), st));
     }
     TL(0, st);
     PROF_BEGIN(0);
-    bool any_tc = false;
-    for (int l = 0; l < L; ++l) any_tc |= c->path == 1 && tc_fwd_supported(c->ls.l[l]);
-    const bool split_pack = any_tc && side;
     if (split_pack) {       // the q_sqrt weight tiles depend on parameters only: pack them beside the factorisation
         CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 2], st));
         CK(cudaStreamWaitEvent(c->stream2, c->ev_dag[2 * DSDGP_MAX_LAYERS + 2], 0));
+        // (the gradient accumulators are first touched by the backward pass: cleared on the side branch, which the main
+        // branch joins before the forward chain, instead of in front of the factorisation)
+        CK(cudaMemsetAsync(c->accf, 0, c->accf_n * sizeof(float), c->stream2));
+        CK(cudaMemsetAsync(c->grads, 0, (c->n_params + 2) * sizeof(float), c->stream2));
         launch_pack_fwd(c->ls, 2, c->acc, c->stream2, nl);
         CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 4], c->stream2));
     }
