@@ -122,7 +122,7 @@ struct dsdgp_ctx {
     int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
     int dbg_layer; long long* dbg_buf; bool timeline = false;
     int g2_passes;                   // 0: automatic (per layer, from the size of q_sqrt), 1 / 3: forced
-    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true; bool lik_handover = false;
+    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true; bool lik_handover = true;
     float* wpack[DSDGP_MAX_LAYERS];
     std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, int, int, unsigned>, long long> graph_launches;

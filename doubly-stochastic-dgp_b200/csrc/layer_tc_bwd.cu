@@ -265,7 +265,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
                 __syncwarp();
             }
         };
-        if (a.wait_before_loads) wait_upstream();
+        if (a.wait_before_loads && a.tile_wait) {
+            // possibly a long wait (the producer may be a forward tile still in flight): ONE polling thread per CTA with a long
+            // back-off, so that a hundred waiting CTAs do not hammer the L2 lines the producers publish through
+            if (threadIdx.x == 0) {
+                const unsigned epoch = a.sa->epoch;
+                while (ld_acquire_gpu(a.tile_wait + blockIdx.x) != epoch) __nanosleep(1000);
+            }
+            named_bar_sync(1, TC_ROWTHREADS);
+        }
         auto load_u4 = [&](int c0) -> float4 {       // M % 4 == 0 (tc_bwd_supported)
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid && c0 < c_hi && c0 + 4 <= M) v = *reinterpret_cast<const float4*>(a.U + (size_t)row * M + c0);

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) k_lik_gaussian_tiled(const float* __restr
     const unsigned epoch = sa->epoch;
     if (tile_wait) {
         if (threadIdx.x == 0)
-            while (ld_acquire_gpu_u32(tile_wait + blockIdx.x) != epoch) __nanosleep(200);
+            while (ld_acquire_gpu_u32(tile_wait + blockIdx.x) != epoch) __nanosleep(1000);
         __syncthreads();
     }
     const double s2 = (double)lik_var[0], c0 = sa->lik_scale;

@@ -1,5 +1,5 @@
 """Tile hand-over (programmatic dependent launches + flags) vs plain stream order on the same problem: ELBO and every
-gradient tensor must agree to atomic-ordering noise.  usage: python tools/handover_check.py"""
+gradient tensor must agree to atomic-ordering noise.  usage: python tools/handover_check.py ["opt=val,..."]"""
 import sys
 sys.path[:0] = ['/root/repo', '/root/repo/doubly-stochastic-dgp_b200']
 import numpy as np
@@ -16,6 +16,8 @@ for ci, cs in enumerate(CASES):
             m = build_model(prob)
             ctx = m._ensure_ctx(prob['N'], prob['S'])
             ctx.set_option("bwd_handover", ho)
+            for kv in filter(None, (sys.argv[1] if len(sys.argv) > 1 else "").split(",")):
+                ctx.set_option(kv.split("=")[0], float(kv.split("=")[1]))
             res = []
             for rep in range(3):
                 e, grads, glik = m.compute_log_likelihood_and_grad(zs=prob['zs'])
