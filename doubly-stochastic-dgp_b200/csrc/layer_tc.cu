@@ -526,7 +526,11 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
                     mean2[e] = mean;
                     sd2[e] = sqrtf(fmaxf(v + jit, 1e-30f));
                 }
-                if (a.F) {
+                if (a.F && a.S_rep > 1 && !a.z) {
+                    const size_t o0 = (size_t)row * D + d0;
+                    dsdgp_draw_fold(seed, P.idx, soff, row + noff, d0, nd, a.S_rep, (size_t)a.N * D, a.F + o0,
+                                    a.z_out ? a.z_out + o0 : nullptr, mean2[0], mean2[1], sd2[0], sd2[1]);
+                } else if (a.F) {
                     const int nrep = a.S_rep;
                     for (int ss = 0; ss < nrep; ++ss) {
                         // row r = s N + n (S_rep == 1), or layer-1 dedup: row = n, one draw per sample ss
