@@ -131,7 +131,11 @@ def make_workload():
     kw = dict(kern=c['kern'], n_classes=c['n_classes'])
     if CFG_ID == 4:
         kw['max_cond'] = None          # (a 512 x 512 condition-number search is not worth the start-up time; timing only)
-    return make_problem(seed=c['seed'], num_data=NUM_DATA, **WORKLOAD, **kw)
+    prob = make_problem(seed=c['seed'], num_data=NUM_DATA, **WORKLOAD, **kw)
+    if c['step'] == 'natgrad':
+        from workloads import well_conditioned_q
+        prob = well_conditioned_q(prob)      # a gamma < 1 natural-gradient step needs S = q_sqrt q_sqrt^T numerically PD
+    return prob
 
 
 def measured_peaks():

@@ -47,15 +47,7 @@ def positive_diag(prob):
     return prob
 
 
-def well_conditioned_q(prob, seed=0):
-    """Replace the last layer's q_sqrt (synth: tril(0.1 N(0,1)) + 0.3 I, whose S = q q^T has a condition number growing
-    exponentially with M -- 5e10 at M=100) by 0.3 I + tril(N(0,1)) 0.1/sqrt(M): GPflow's route forms S^-1 and
-    chol(eta2 - eta1 eta1^T), which needs S to be numerically positive definite."""
-    rng = np.random.default_rng(seed)
-    lay = prob['layers'][-1]
-    D, M, _ = lay['q_sqrt'].shape
-    lay['q_sqrt'] = 0.3 * np.eye(M)[None] + np.tril(rng.normal(size=(D, M, M)), -1) * (0.1 / np.sqrt(M))
-    return prob
+from workloads import well_conditioned_q  # noqa: E402,F401  (re-exported: other test modules import it from here)
 
 
 CASES = [

@@ -81,6 +81,17 @@ def make_problem(dims, N, M, S, seed, kern='rbf', white=False, ard=False, inner_
                 num_data=num_data or N, dims=list(dims), kern=kern, white=white, n_classes=n_classes)
 
 
+def well_conditioned_q(prob, seed=0):
+    """Replace the last layer's q_sqrt (make_problem: tril(0.1 N(0,1)) + 0.3 I, whose S = q q^T has a condition number growing
+    exponentially with M -- 5e10 at M=100, not numerically positive definite at M=512) by 0.3 I + tril(N(0,1)) 0.1/sqrt(M).
+    A natural-gradient step with gamma < 1 forms S^-1 (as GPflow's does), which needs S to be numerically positive definite."""
+    rng = np.random.default_rng(seed)
+    lay = prob['layers'][-1]
+    D, M, _ = lay['q_sqrt'].shape
+    lay['q_sqrt'] = 0.3 * np.eye(M)[None] + np.tril(rng.normal(size=(D, M, M)), -1) * (0.1 / np.sqrt(M))
+    return prob
+
+
 def round_f32(prob):
     """Round every input the device sees in fp32 to fp32 (returned as float64), so that the
     oracle and the CUDA path evaluate the SAME problem."""
