@@ -505,7 +505,7 @@ def main_b200(args):
                                     f"dp{world}: S_total={S} fixed, the S*N sample rows sharded ({primary['N_loc']} minibatch rows x all S per GPU), "
                                     "one NCCL all-reduce of [grad || ELBO]"),
                     "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events on the launch stream",
-                    "precision": "tcgen05 kind::tf32 (3xTF32 for the whitened projections / solves, 1xTF32 elsewhere), "
+                    "precision": "tcgen05 kind::tf32 (3xTF32 for the whitened projections / solves, weights-split 2xTF32 for the variance product once q_sqrt is non-negligible, 1xTF32 elsewhere), "
                                  "fp32 epilogues, fp64 MxM factorisation + KL"},
             "ms_per_step_back_to_back": primary["ms_per_step_back_to_back"], "gpu_launches": primary["gpu_launches"],
             "clocks": primary["clocks"], "e2e": primary["e2e"], "roofline": primary["roofline"], "cpu_baseline": cpu,
