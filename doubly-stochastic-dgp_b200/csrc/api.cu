@@ -122,7 +122,7 @@ struct dsdgp_ctx {
     int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
     int dbg_layer; long long* dbg_buf; bool timeline = false;
     int g2_passes;                   // 0: automatic (per layer, from the size of q_sqrt), 1 / 3: forced
-    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true; bool lik_handover = true;
+    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true; bool lik_handover = true; bool defer_fold = true;
     float* wpack[DSDGP_MAX_LAYERS];
     std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, int, int, unsigned>, long long> graph_launches;
@@ -523,6 +523,8 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     TL(1, st);
     // forward
     const bool chain = c->chain && c->path == 1 && mode != MODE_PROPAGATE && tc_chain_fwd_supported(c->ls);
+    // deferred layer-1 fold (FwdArgs::fold_*): layer 1's tiles publish after their marginals, layer 2's tiles draw their inputs
+    const bool defer = chain && c->defer_fold && L >= 2 && S > 1;
     FwdChain fc;
     fc.L = L; fc.max_tiles = c->chain_max_tiles; fc.flags = c->chain_flags; fc.sa = c->sa_dev; fc.base[0] = 0;
     for (int l = 0; l < L; ++l) {
@@ -538,6 +540,15 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         a.z_out = (a.z == nullptr && a.F != nullptr && mode >= MODE_GRAD) ? c->zs[l] : nullptr;
         a.dbg = (c->dbg_layer == l) ? c->dbg_buf : nullptr;
         a.acc = c->acc; a.g2_passes = c->g2_passes;
+        a.fold_mean = a.fold_var = a.fold_z = nullptr; a.fold_F = a.fold_zout = nullptr; a.fold_layer = 0;
+        if (defer && l == 0) { a.F = nullptr; a.z_out = nullptr; }       // its S draws per row are made by layer 2's tiles
+        if (defer && l == 1) {
+            a.fold_mean = c->Fmean[0]; a.fold_var = c->Fvar[0];
+            a.fold_z = (zmask & 1u) ? c->zs[0] : nullptr;
+            a.fold_F = c->F[0];
+            a.fold_zout = (a.fold_z == nullptr && mode >= MODE_GRAD) ? c->zs[0] : nullptr;
+            a.fold_layer = c->ls.l[0].idx;
+        }
         if (chain) {
             fc.a[l] = a; fc.tiles[l] = (a.R + 127) / 128; fc.base[l + 1] = fc.base[l] + fc.tiles[l];
             continue;
@@ -1231,6 +1242,10 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     else if (n == "profile") c->profile = value != 0;
     else if (n == "chain") {
         c->chain = value != 0;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "defer_fold") {
+        c->defer_fold = value != 0;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     } else if (n == "lik_handover") {

@@ -215,6 +215,15 @@ struct FwdArgs {
     long long* dbg;       // optional clock64() stamps of CTA 0 (diagnostics), else NULL
     const Accum* acc;     // g2flag (see Accum)
     int g2_passes;        // 0: per layer from acc->g2flag; 1 / 3: forced (option "g2_passes")
+    // Deferred layer-1 fold (chained forward only): when fold_mean != NULL this layer's input rows are not read from Xin but
+    // DRAWN here from the previous (de-duplicated, N-row) layer's marginals -- x(s, n, :) = fold_mean[n] + sqrt(fold_var[n] +
+    // jitter) z(s, n, :) -- and written to fold_F / fold_zout for the backward pass.  The previous layer's tiles then publish
+    // right after their mean / variance instead of drawing S samples per row first (46k of the 85k cycles of a north-star
+    // layer-1 tile, with every other CTA of the chain waiting for it).  Same counters and arithmetic as the in-tile fold.
+    const float *fold_mean, *fold_var;   // (N, Din)
+    const float* fold_z;                 // injected draws of the previous layer (S*N, Din) or NULL -> Philox
+    float *fold_F, *fold_zout;           // (S*N, Din) out; fold_zout may be NULL
+    int fold_layer;                      // Philox layer index of the previous layer
 };
 
 // all layers' forward tiles as one persistent launch (layer_tc.cu k_chain_fwd_tc)

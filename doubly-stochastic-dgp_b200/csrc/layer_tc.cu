@@ -161,9 +161,41 @@ __device__ __forceinline__ void fwd_tile_body(const LayerDev& P, const FwdArgs& 
 #pragma unroll
     for (int q = 0; q < DINP; ++q) xraw[q] = 0.f;
     if (warp < TC_WARP_TMA && row0 + (int)(threadIdx.x & 127) < R) {
+        const int r = row0 + (int)(threadIdx.x & 127);
+        if (a.fold_mean) {
+            // deferred layer-1 fold (see FwdArgs): every quarter thread of the row needs all Din inputs and draws them itself
+            // (the four quarters of a row sit in different warps); quarter qt stores pair qt, qt + 4, ... of the row
+            const int s_idx = r / a.N, n = r - s_idx * a.N, myq = (int)(threadIdx.x >> 7);
+            const unsigned long long seed = a.sa->seed;
+            const int noff = a.sa->n_offset, soff = a.sa->s_offset;
 #pragma unroll
-        for (int q = 0; q < DINP; ++q)
-            if (q < Din) xraw[q] = __ldcg(&a.Xin[(size_t)(row0 + (threadIdx.x & 127)) * Din + q]);
+            for (int q = 0; q < DINP; q += 2) {
+                if (q < Din) {
+                    const int nd = (q + 1 < Din) ? 2 : 1;
+                    float z2[2], m2[2] = {0.f, 0.f}, sd2[2] = {0.f, 0.f};
+                    for (int e = 0; e < nd; ++e) {
+                        m2[e] = __ldcg(&a.fold_mean[(size_t)n * Din + q + e]);
+                        sd2[e] = sqrtf(fmaxf(__ldcg(&a.fold_var[(size_t)n * Din + q + e]) + a.jitter, 1e-30f));
+                    }
+                    const size_t o = (size_t)r * Din + q;
+                    if (a.fold_z) { z2[0] = a.fold_z[o]; z2[1] = nd == 2 ? a.fold_z[o + 1] : 0.f; }
+                    else dsdgp_normal2(seed, a.fold_layer, s_idx + soff, n + noff, q, z2[0], z2[1]);
+                    const bool mine = ((q >> 1) & 3) == myq;
+                    for (int e = 0; e < nd; ++e) {
+                        const float x = fmaf(z2[e], sd2[e], m2[e]);
+                        xraw[q + e] = x;
+                        if (mine) {
+                            a.fold_F[o + e] = x;
+                            if (a.fold_zout) a.fold_zout[o + e] = z2[e];
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < DINP; ++q)
+                if (q < Din) xraw[q] = __ldcg(&a.Xin[(size_t)r * Din + q]);
+        }
     }
     if (threadIdx.x == 0) {
         if (reinit)
