@@ -100,6 +100,7 @@ struct dsdgp_ctx {
     cudaStream_t stream2;                       // side branch of the step DAG (KL prep, row reductions)
     cudaStream_t stream_tl[4]; cudaEvent_t ev_tl[28]; bool tl_used[4] = {false, false, false, false};   // timeline stamps
     cudaStream_t stream5, stream6; cudaEvent_t ev_fin[2 * DSDGP_MAX_LAYERS];   // second half of a layer's assembly (fork / join)
+    cudaStream_t stream2b; bool rowred_split = true;   // second row-reduction stream (layers alternate)
     cudaStream_t stream4;                       // (the per-layer assemblies alternate between stream3 and stream4)
     cudaStream_t stream3;                       // second side branch: per-layer gradient assembly behind the row reductions
     cudaEvent_t ev_dag[2 * DSDGP_MAX_LAYERS + 8];
@@ -316,6 +317,7 @@ static int create_device_state(dsdgp_ctx* c, const dsdgp_desc* desc) {
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
+        CK(cudaStreamCreateWithPriority(&c->stream2b, cudaStreamNonBlocking, prio_lo));
         // (the small assembly launches go first: they free their dependants and leave the SMs within microseconds)
         CK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));
         CK(cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prio_hi));
@@ -397,7 +399,7 @@ int dsdgp_destroy(dsdgp_ctx* c) {
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
     for (int i = 0; i < 2 * (5 + 3 * DSDGP_MAX_LAYERS); ++i) cudaEventDestroy(c->prof_ev[i]);
     for (int i = 0; i < 16; ++i) cudaEventDestroy(c->sa_ev[i]);
-    cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3); cudaStreamDestroy(c->stream4); cudaStreamDestroy(c->stream5); cudaStreamDestroy(c->stream6);
+    cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream2b); cudaStreamDestroy(c->stream3); cudaStreamDestroy(c->stream4); cudaStreamDestroy(c->stream5); cudaStreamDestroy(c->stream6);
     for (int i = 0; i < 2 * DSDGP_MAX_LAYERS; ++i) cudaEventDestroy(c->ev_fin[i]); for (int i = 0; i < 4; ++i) cudaStreamDestroy(c->stream_tl[i]);
     for (int i = 0; i < 28; ++i) cudaEventDestroy(c->ev_tl[i]);
     for (int i = 0; i < 2 * DSDGP_MAX_LAYERS + 8; ++i) cudaEventDestroy(c->ev_dag[i]);
@@ -479,7 +481,7 @@ __global__ void k_stamp(long long* p) { long long t; asm volatile("mov.u64 %0, %
 // programmatic launch of the next row kernel -- is what it is without the stamps; one stamp stream per branch of the DAG: the
 // stamps of one branch are ordered anyway, a shared stream would hold a stamp back behind another branch's earlier-enqueued one)
 #define TL(i, s) do { if (c->timeline && (i) < 24) { \
-        const int ti_ = (s) == c->stream2 ? 1 : (s) == c->stream3 ? 2 : (s) == c->stream4 ? 3 : 0; \
+        const int ti_ = ((s) == c->stream2 || (s) == c->stream2b) ? 1 : (s) == c->stream3 ? 2 : (s) == c->stream4 ? 3 : 0; \
         cudaStream_t tls_ = c->stream_tl[ti_]; c->tl_used[ti_] = true; \
         cudaEventRecord(c->ev_tl[i], (s)); cudaStreamWaitEvent(tls_, c->ev_tl[i], 0); \
         k_stamp<<<1, 1, 0, tls_>>>(c->dbg_buf + (i)); } } while (0)
@@ -515,6 +517,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
         CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 4], c->stream2));
     }
     launch_prep(c->ls, c->desc.jitter, c->acc, c->sa_dev, st, side ? c->stream2 : st, c->ev_dag[0], nl);
+    if (side) CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 6], c->stream2));      // KL preparation enqueued (for stream2b)
     if (split_pack) {
         launch_pack_fwd(c->ls, 1, c->acc, st, nl);
         CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 4], 0));
@@ -599,6 +602,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     TL(3, st);
     if (grad) {
         bool fin_used[2] = {false, false};
+        bool rr2_used = false;
         for (int l = L - 1; l >= 0; --l) {
             BwdArgs b;
             b.Xin = (l == 0) ? c->Xd : c->F[l - 1];
@@ -631,8 +635,15 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             PROF_BEGIN(7 + 3 * l);
             // the row reductions of layer l only feed the final gradient assembly: side branch of the DAG, so they
             // overlap with the (latency-bound, second-wave-starved) row kernel of layer l-1
-            cudaStream_t sr = side ? c->stream2 : st;
-            if (side) { CK(cudaEventRecord(c->ev_dag[2 + l], st)); CK(cudaStreamWaitEvent(c->stream2, c->ev_dag[2 + l], 0)); }
+            // (alternating between two streams, so that the reductions of layer l can start under the tail of layer l+1's:
+            // both are persistent kernels whose CTAs finish at different times)
+            cudaStream_t sr = !side ? st : (c->rowred_split && (l & 1)) ? c->stream2b : c->stream2;
+            if (side && sr == c->stream2b && !rr2_used) {
+                // the gradient assembly behind it reads the KL preparation, which lives on stream2
+                CK(cudaStreamWaitEvent(c->stream2b, c->ev_dag[2 * DSDGP_MAX_LAYERS + 6], 0));
+                rr2_used = true;
+            }
+            if (side) { CK(cudaEventRecord(c->ev_dag[2 + l], st)); CK(cudaStreamWaitEvent(sr, c->ev_dag[2 + l], 0)); }
             if (c->path == 1 && tc_rowred_supported(c->ls.l[l])) launch_bwd_rowred_tc(c->ls.l[l], b, c->num_sms, sr, nl);
             else launch_bwd_rowred(c->ls.l[l], b, c->num_sms, sr, nl);
             PROF_END(7 + 3 * l);
@@ -659,6 +670,7 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             }
         }
         if (side) { CK(cudaEventRecord(c->ev_dag[1], c->stream2)); CK(cudaStreamWaitEvent(st, c->ev_dag[1], 0)); }
+        if (rr2_used) { CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 7], c->stream2b)); CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 7], 0)); }
         if (side && c->fin_per_layer) {
             if (fin_used[0]) { CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 3], c->stream3)); CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 3], 0)); }
             if (fin_used[1]) { CK(cudaEventRecord(c->ev_dag[2 * DSDGP_MAX_LAYERS + 5], c->stream4)); CK(cudaStreamWaitEvent(st, c->ev_dag[2 * DSDGP_MAX_LAYERS + 5], 0)); }
@@ -1242,6 +1254,10 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     else if (n == "profile") c->profile = value != 0;
     else if (n == "chain") {
         c->chain = value != 0;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "rowred_split") {
+        c->rowred_split = value != 0;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     } else if (n == "defer_fold") {
