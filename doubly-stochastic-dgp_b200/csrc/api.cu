@@ -123,7 +123,7 @@ struct dsdgp_ctx {
     int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
     int dbg_layer; long long* dbg_buf; bool timeline = false;
     int g2_passes;                   // 0: automatic (per layer, from the size of q_sqrt), 1 / 3: forced
-    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true; bool lik_handover = true; bool defer_fold = true;
+    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true; bool lik_handover = true; bool defer_fold = true; bool l1_handover = true;
     float* wpack[DSDGP_MAX_LAYERS];
     std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, int, int, unsigned>, long long> graph_launches;
@@ -623,6 +623,14 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             // the backward chain is resident while the forward pass still runs (the flags order tile t of all of them)
             if (tc_l && l == L - 1 && lik_tiled) b.tile_wait = lik_flags;
             b.wait_before_loads = lik_tiled && chained;
+            b.wait_count = 0;
+            // the de-duplicated first layer: resident early (programmatic dependent of layer 2's launch, so its few CTAs do not
+            // queue for an SM behind the persistent row-reduction CTAs), starts when ALL of layer 2's tiles have published
+            if (tc_l && c->bwd_handover && c->l1_handover && l == 0 && L > 1 && b.S_rep > 1 && tc_bwd_supported(c->ls.l[1])) {
+                b.tile_wait = bflags + (size_t)1 * c->chain_max_tiles;
+                b.wait_count = (N * S + 127) / 128;
+                b.wait_before_loads = 1;
+            }
             if (tc_l && c->bwd_handover && l < L - 1 && l > 0 && b.S_rep == 1 && c->path == 1 && tc_bwd_supported(c->ls.l[l + 1]))
                 b.tile_wait = bflags + (size_t)(l + 1) * c->chain_max_tiles;
             b.dbg = (c->dbg_layer == 100 + l) ? c->dbg_buf : nullptr;
@@ -1254,6 +1262,10 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     else if (n == "profile") c->profile = value != 0;
     else if (n == "chain") {
         c->chain = value != 0;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "l1_handover") {
+        c->l1_handover = value != 0;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     } else if (n == "rowred_split") {

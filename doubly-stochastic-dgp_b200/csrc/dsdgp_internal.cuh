@@ -257,6 +257,8 @@ struct BwdArgs {
     unsigned* tile_done;          // [tiles] written by this launch when a tile's outputs are published, or NULL
     const unsigned* tile_wait;    // [tiles] flags of the upstream launch to wait for before reading fbar, or NULL
     int wait_before_loads;        // 1: nothing of the tile may be read before the flag (last layer behind the forward tail)
+    int wait_count;               // > 0: wait for tile_wait[0 .. wait_count) -- the de-duplicated first layer folds the S samples
+                                  // of its rows, which are spread over ALL tiles of the layer above
 };
 
 void launch_prep(const LayerSet& ls, double jitter, Accum* acc, const StepArgs* sa, cudaStream_t st, cudaStream_t st_kl,

@@ -268,8 +268,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_bwd_tc(LayerDev P, BwdA
         if (a.wait_before_loads && a.tile_wait) {
             // possibly a long wait (the producer may be a forward tile still in flight): ONE polling thread per CTA with a long
             // back-off, so that a hundred waiting CTAs do not hammer the L2 lines the producers publish through
-            if (threadIdx.x == 0) {
-                const unsigned epoch = a.sa->epoch;
+            const unsigned epoch = a.sa->epoch;
+            if (a.wait_count > 0) {
+                for (int i = threadIdx.x; i < a.wait_count; i += TC_ROWTHREADS)
+                    while (ld_acquire_gpu(a.tile_wait + i) != epoch) __nanosleep(1000);
+            } else if (threadIdx.x == 0) {
                 while (ld_acquire_gpu(a.tile_wait + blockIdx.x) != epoch) __nanosleep(1000);
             }
             named_bar_sync(1, TC_ROWTHREADS);
