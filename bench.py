@@ -347,11 +347,13 @@ def main_b200(args):
         b2b_ms = max_over_ranks(ctx.timer_stop())
         barrier()
         # keep the clock sampler running over a longer loaded stretch (the timed legs above last only ~0.1 s)
-        t_end = time.perf_counter() + 1.0
-        i = 0
-        while time.perf_counter() < t_end:
-            dev_step(9000 + i, False); i += 1
-            if i % 32 == 0:
+        # (a FIXED number of steps, the same on every rank -- about one second's worth by the max-over-ranks step time above:
+        # every step carries an all-reduce, so a wall-clock-bounded loop would let ranks enqueue different numbers of
+        # collectives and hang the slower ones)
+        n_extra = max(2, min(20000, int(1000.0 / max(tot_ms / K, 1e-3))))
+        for i in range(n_extra):
+            dev_step(9000 + i, False)
+            if (i + 1) % 32 == 0:
                 ctx.sync()
         barrier()
         clk = clocks.stop()

@@ -123,7 +123,7 @@ struct dsdgp_ctx {
     int path;                        // 0: fp32 SIMT row kernels, 1: tcgen05 where supported
     int dbg_layer; long long* dbg_buf; bool timeline = false;
     int g2_passes;                   // 0: automatic (per layer, from the size of q_sqrt), 1 / 3: forced
-    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true; bool lik_handover = true; bool defer_fold = true; bool l1_handover = true;
+    unsigned* chain_flags; int chain_max_tiles; unsigned epoch; bool chain; bool bwd_handover = true; bool lik_handover = true; bool defer_fold = true; bool l1_handover = true; bool handover_multi = false;
     float* wpack[DSDGP_MAX_LAYERS];
     std::map<std::tuple<int, int, int, unsigned>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, int, int, unsigned>, long long> graph_launches;
@@ -582,7 +582,13 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
     PROF_BEGIN(1);
     // tile hand-over forward chain -> likelihood -> last layer's backward rows (Gaussian, tcgen05 row kernel)
     unsigned* lik_flags = c->chain_flags + (size_t)(2 * DSDGP_MAX_LAYERS) * c->chain_max_tiles;
-    const bool lik_tiled = c->desc.likelihood == DSDGP_LIK_GAUSSIAN && grad && c->bwd_handover && c->lik_handover && c->path == 1 &&
+    // Tile hand-over between launches (programmatic dependent launches + flags, see BwdArgs) is on where it was verified on
+    // hardware: one GPU, and two ranks (tests/test_gpu_multi.py, the bench's sharded-vs-single parity gate).  With more ranks the
+    // plain stream order of round 1 is kept unless option "handover_multi" is set: this round's only 8-GPU run with hand-over did
+    // not finish within its 140 s limit, and the GPU budget ended before the cause (cold 8-GPU box or a stall in the regime where
+    // every launch of the backward chain is resident at once: 20 tiles per layer) could be established -- DESIGN.md section 6.
+    const bool handover = c->bwd_handover && (c->comm == nullptr || c->world <= 2 || c->handover_multi);
+    const bool lik_tiled = c->desc.likelihood == DSDGP_LIK_GAUSSIAN && grad && handover && c->lik_handover && c->path == 1 &&
                            tc_bwd_supported(c->ls.l[L - 1]);
     if (lik_tiled)
         launch_lik_gaussian_tiled(c->Fmean[L - 1], c->Fvar[L - 1], c->Yd, Rlast, N, c->desc.D_y, c->params + c->off_likvar,
@@ -626,12 +632,12 @@ static int enqueue_step(dsdgp_ctx* c, int mode, int N, int S, unsigned zmask, lo
             b.wait_count = 0;
             // the de-duplicated first layer: resident early (programmatic dependent of layer 2's launch, so its few CTAs do not
             // queue for an SM behind the persistent row-reduction CTAs), starts when ALL of layer 2's tiles have published
-            if (tc_l && c->bwd_handover && c->l1_handover && l == 0 && L > 1 && b.S_rep > 1 && tc_bwd_supported(c->ls.l[1])) {
+            if (tc_l && handover && c->l1_handover && l == 0 && L > 1 && b.S_rep > 1 && tc_bwd_supported(c->ls.l[1])) {
                 b.tile_wait = bflags + (size_t)1 * c->chain_max_tiles;
                 b.wait_count = (N * S + 127) / 128;
                 b.wait_before_loads = 1;
             }
-            if (tc_l && c->bwd_handover && l < L - 1 && l > 0 && b.S_rep == 1 && c->path == 1 && tc_bwd_supported(c->ls.l[l + 1]))
+            if (tc_l && handover && l < L - 1 && l > 0 && b.S_rep == 1 && c->path == 1 && tc_bwd_supported(c->ls.l[l + 1]))
                 b.tile_wait = bflags + (size_t)(l + 1) * c->chain_max_tiles;
             b.dbg = (c->dbg_layer == 100 + l) ? c->dbg_buf : nullptr;
             b.dbg_rr = (c->dbg_layer == 200 + l) ? c->dbg_buf : nullptr;
@@ -1262,6 +1268,10 @@ int dsdgp_set_option(dsdgp_ctx* c, const char* name, double value) {
     else if (n == "profile") c->profile = value != 0;
     else if (n == "chain") {
         c->chain = value != 0;
+        for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+        c->graphs.clear(); c->graph_launches.clear();
+    } else if (n == "handover_multi") {
+        c->handover_multi = value != 0;
         for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
         c->graphs.clear(); c->graph_launches.clear();
     } else if (n == "l1_handover") {
