@@ -26,6 +26,14 @@ closed-form SVGP / GPR written with different linear algebra
   I2  L=2 DGP with a 1e-24-variance inner layer == SVGP   (same, L=2 branch)
   I6  NatGrad gamma=1 on the last layer == SGPR optimum  (tests/test_collapsed.py:57-104)
   I8  reparameterize literal formula        (tests/test_utils.py:181-206)
+Since round 2 the restatement of the REFERENCE-OWNED files (dgp.py, layers.py, utils.py,
+layer_initializations.py) is additionally pinned by outputs of those files themselves: they are
+imported unmodified from /root/reference and executed over a torch stand-in for the TF ops / GPflow
+classes they touch (oracle/tf_gpflow_shim.py); the fixtures tests/golden/refshim_*.npz (generator:
+tests/golden/make_from_reference_shim.py) hold what the reference computed -- propagate, KL, ELBO,
+predict_*, full_cov, DGP_Quad, input propagation, Sum(RBF, White), Bernoulli broadcasting -- and
+tests/test_refshim_cpu.py requires this module to reproduce them to 1e-9.  GPflow itself is still
+not run anywhere, hence "unpinned at the GPflow/TF boundary" stands.
 
 Two execution modes:
   faithful=True   materialises exactly what the reference graph materialises
