@@ -133,3 +133,55 @@ def test_committed_fixture_is_what_the_generator_produces(tmp_path):
     for k in a.files:
         if k != "meta":
             assert_allclose(a[k], b[k], rtol=1e-12, atol=1e-13, err_msg=k)
+
+
+def _host_kernel(g, l, lm):
+    from doubly_stochastic_dgp import kernels as K
+    ls = g[f"in_lengthscales{l}"]
+    k = getattr(K, lm["kern"])(lm["input_dim"], variance=float(g[f"in_variance{l}"]),
+                               lengthscales=ls if lm["ard"] else float(ls[0]), ARD=lm["ard"])
+    if lm["has_white"]:
+        k = k + K.White(lm["input_dim"], variance=float(g[f"in_white_variance{l}"]))
+    return k
+
+
+def test_host_package_constructors_build_what_the_reference_built():
+    """The product's host mirror (doubly_stochastic_dgp.DGP / init_layers_linear / init_layers_input_prop: construction-time
+    NumPy, no device) against the layers the reference's constructors produced: inducing inputs, mean-function matrices,
+    q_sqrt initialisation, input_prop_dim."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "doubly-stochastic-dgp_b200"))
+    from doubly_stochastic_dgp.dgp import DGP
+    from doubly_stochastic_dgp.layer_initializations import init_layers_input_prop
+    from doubly_stochastic_dgp.likelihoods import Gaussian
+    # init_layers_linear through DGP(...): 5 -> 3 (PCA) -> 4 (padding) -> 2
+    g = np.load(os.path.join(HERE, "golden", "refshim_dgp3_linear_means_ard.npz"), allow_pickle=False)
+    meta = json.loads(str(g["meta"]))
+    kernels = [_host_kernel(g, l, lm) for l, lm in enumerate(meta["layers"])]
+    m = DGP(g["in_X"], g["in_Y"], g["in_Z"], kernels, Gaussian(), num_outputs=meta["spec"]["dims"][-1], white=False)
+    for l, lm in enumerate(meta["layers"]):
+        assert type(m.layers[l].mean_function).__name__ == lm["mean"]
+        assert m.layers[l].num_outputs == lm["num_outputs"]
+        assert_allclose(np.asarray(m.layers[l].feature.Z.value), g[f"in_Z{l}"], rtol=1e-12, atol=1e-13)
+        if lm["mean"] == "Linear":
+            assert_allclose(np.asarray(m.layers[l].mean_function.A.value), g[f"in_A{l}"], rtol=1e-12, atol=1e-13)
+    # q_sqrt = chol(Kuu + jitter I) of a non-white layer (layers.py:160-163): same prior as the reference's kernel gives
+    q0 = np.asarray(m.layers[0].q_sqrt.value)[0]
+    from oracle import reference_dgp as R
+    R.settings.jitter = meta["jitter"]
+    K = _kernel(g, 0, meta["layers"][0]).K(torch.as_tensor(g["in_Z0"])).numpy() + meta["jitter"] * np.eye(g["in_Z0"].shape[0])
+    assert_allclose(q0 @ q0.T, K, rtol=1e-9, atol=1e-11)
+    # init_layers_input_prop: Z padded with np.random.randn columns (same global seed as the generator), input_prop_dim = D
+    g = np.load(os.path.join(HERE, "golden", "refshim_dgp2_input_prop.npz"), allow_pickle=False)
+    meta = json.loads(str(g["meta"]))
+    kernels = [_host_kernel(g, l, lm) for l, lm in enumerate(meta["layers"])]
+    seed = 1 + sorted(f[8:-4] for f in map(os.path.basename, FILES)).index("dgp2_input_prop")
+    state = np.random.get_state()
+    try:
+        np.random.seed(seed)
+        layers = init_layers_input_prop(g["in_X"], g["in_Y"], g["in_Z"], kernels, num_outputs=1, white=True)
+    finally:
+        np.random.set_state(state)
+    for l, lm in enumerate(meta["layers"]):
+        assert (layers[l].input_prop_dim or 0) == lm["input_prop_dim"]
+        assert_allclose(np.asarray(layers[l].feature.Z.value), g[f"in_Z{l}"], rtol=1e-12, atol=1e-13)
