@@ -223,6 +223,35 @@ def main_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+class Watchdog:
+    """Bounds a stalled run: if the bench has not finished after `seconds`, say where it was (rank 0 prints a JSON error line)
+    and leave with os._exit, which tears the CUDA context down -- a multi-rank run that stalls in a collective or a spinning
+    kernel otherwise holds its GPUs until the caller's own limit.  DSDGP_BENCH_WATCHDOG=<seconds> (0 disables)."""
+    def __init__(self, rank, world, seconds=None):
+        self.rank, self.world, self.stage = rank, world, "start"
+        self.seconds = float(os.environ.get("DSDGP_BENCH_WATCHDOG", "420")) if seconds is None else float(seconds)
+        self.timer = None
+        if self.seconds > 0:
+            self.timer = threading.Timer(self.seconds, self._fire)
+            self.timer.daemon = True
+            self.timer.start()
+
+    def at(self, stage):
+        self.stage = stage
+
+    def _fire(self):
+        msg = f"bench watchdog: not finished after {self.seconds:.0f} s (rank {self.rank} of {self.world} was in stage '{self.stage}')"
+        sys.stderr.write(msg + "\n")
+        sys.stderr.flush()
+        if self.rank == 0:
+            print(json.dumps({"error": msg, "n_gpus": self.world, "stage": self.stage}), flush=True)
+        os._exit(3)
+
+    def done(self):
+        if self.timer is not None:
+            self.timer.cancel()
+
+
 def main_b200(args):
     import torch
     import torch.distributed as dist
@@ -236,6 +265,7 @@ def main_b200(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    dog = Watchdog(rank, world)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -475,11 +505,14 @@ def main_b200(args):
                                       seed, _lib.FLAG_DEVICE_PTRS, C.byref(e)))
         return e.value
 
+    dog.at("parity leg")
     parity = parity_leg()
+    dog.at(f"{args.scaling} leg (value, e2e, stage profile)")
     primary = run_mode(args.scaling, want_profile=True, want_e2e=not args.no_e2e)
     other = None
     if world > 1 and not natgrad:
         other_mode = "strong" if args.scaling == "weak" else "weak"
+        dog.at(f"{other_mode} leg (other_scaling)")
         o = run_mode(other_mode, want_profile=False, want_e2e=False)
         other = {"scaling": other_mode, "value": o["value"], "ms_per_step": o["ms_per_step"], "rows_per_gpu": o["rows_per_gpu"],
                  "note": "weak: S=20 per GPU, S_total = 20 x n_gpus; value counts (N, S) evaluations/s" if other_mode == "weak"
@@ -487,6 +520,7 @@ def main_b200(args):
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample
     cpu = None
+    dog.at("cpu baseline")
     if rank == 0 and world == 1 and not args.no_cpu:
         sps, done, dt, cores = run_cpu_reference(steps=args.cpu_steps, warmup=1, max_seconds=25)
         cpu = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port", **run_cpu_reference.last_stats,
@@ -516,9 +550,11 @@ def main_b200(args):
         if primary.get("roofline_error"):
             out["roofline_error"] = primary["roofline_error"]
         print(json.dumps(out))
+    dog.at("final barrier")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    dog.done()
     if bad:
         raise SystemExit(f"parity gate failed: {bad} beyond {parity['tolerance_rel']}")
 
